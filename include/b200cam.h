@@ -1,0 +1,98 @@
+/* b200cam.h - C ABI of libb200cam.so: the B200 (sm_100a) optical-encoder hot path.
+ *
+ * The reference (carlosh93/privacy-preserving-vision) has no FFI layer on this path: its
+ * boundary is the PyTorch nn.Module `Camera` (Face-DeId/Camera/Optics.py:9).  This library sits
+ * directly under that module: `Camera.forward` -> torch.autograd.Function -> ctypes -> here.
+ * Each entry point names the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - every pointer except `kappa` is a DEVICE pointer to fp32 data owned by the caller
+ *    (PyTorch allocates; the library never allocates in a compute call, never synchronises,
+ *    never throws).  Complex arrays are interleaved (re,im) fp32 pairs.
+ *  - image tensors are NCHW contiguous, 16-byte aligned: img[b][c][y][x], c = 3 wavelengths.
+ *  - `stream` is a cudaStream_t; all work is enqueued on it and is CUDA-graph capturable
+ *    (b200cam_init must have been called for that N on that device before capture).
+ *  - return value: 0 on success, a positive cudaError_t value, or a negative B200CAM_E_* code.
+ *  - N must be one of 64, 128, 256, 512, 1024.
+ */
+#ifndef B200CAM_H_
+#define B200CAM_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CAM_VERSION 100            /* major*10000 + minor*100 + patch */
+#define B200CAM_MAX_TIES 8             /* recorded arg-max positions per image */
+
+#define B200CAM_E_BAD_SIZE   (-1)      /* unsupported N or B < 1 */
+#define B200CAM_E_NULL       (-2)      /* required pointer is NULL */
+#define B200CAM_E_WORKSPACE  (-3)      /* workspace too small */
+#define B200CAM_E_NOT_INIT   (-4)      /* b200cam_init(N) not called on this device */
+#define B200CAM_E_ALIGN      (-5)      /* pointer not 16-byte aligned */
+
+int b200cam_version(void);
+const char* b200cam_error_string(int code);
+int b200cam_supported(int N);
+
+/* Build the per-device twiddle table for N and opt the kernels into large dynamic shared
+ * memory.  Allocates (once per device and N) - call outside stream capture. */
+int b200cam_init(int N);
+
+size_t b200cam_otf_bytes(int N);                                   /* 3*(N/2+1)*N complex */
+size_t b200cam_psf_workspace_bytes(int N);
+size_t b200cam_sensor_workspace_bytes(int N, int B, int want_img_grad);
+
+/* PSF synthesis, forward.  Replaces Camera.get_psf + the regularisers
+ * (Face-DeId/Camera/Optics.py:89-120 and :124-125):
+ *   V_l = A_l * exp(i*kappa_l*h);  U = ifftn(fftn(V) * H) over (lambda,y,x);  psf = |U|^2 / sum.
+ *   h      [N][N]        lens height map in metres (Optics.py:79-83 output)
+ *   A      [3][N][N] cplx constant pupil table  rad * t * focus * pre-phase (Optics.py:95-100)
+ *   Ht     [3][N][N] cplx transfer function of Optics.py:103, TRANSPOSED to [m][u][v]
+ *   rho    [N][N]        0/1 mask of Optics.py:55
+ *   kappa  HOST [3]      k_l * flmb_l (Optics.py:89-90)
+ *   psf    [3][N][N]     out: `psfs[0]` (centred frame, as Camera.get_psf returns it)
+ *   field  [3][N][N] cplx out: propagated field U, kept for the backward pass
+ *   stats  [4]           out: { sum|U|^2, loss_rad (:113), centering_loss (:124-125), scratch } */
+int b200cam_psf_fwd(const float* h, const float* A, const float* Ht, const float* rho,
+                    const float* kappa, float* psf, float* field, float* stats,
+                    void* workspace, size_t workspace_bytes, int N, void* stream);
+
+/* PSF synthesis, backward (autograd through Optics.py:89-125 in closed form).
+ *   grad_psf     [3][N][N] or NULL   dL/dpsf
+ *   grad_scalars [2] or NULL         dL/dloss_rad, dL/dcentering_loss
+ *   grad_h       [N][N]              out: dL/dh */
+int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const float* h,
+                    const float* A, const float* Ht, const float* rho, const float* kappa,
+                    const float* psf, const float* field, float* stats, float* grad_h,
+                    void* workspace, size_t workspace_bytes, int N, void* stream);
+
+/* Sensor image, forward.  Replaces Optics.py:126-128 + conv2D (Face-DeId/Camera/Utils.py:7-12):
+ *   sensor_b = circconv(img_b, roll(psf, -N/2)) / max over (c,y,x).
+ *   img      [B][3][N][N]
+ *   psf      [3][N][N]                 centred PSF
+ *   sensor   [B][3][N][N]              out
+ *   img_max  [B]                       out: the per-image maximum before division
+ *   tie_count[B], tie_pos[B][MAX_TIES] out: how many positions attain the maximum, and the first
+ *                                      MAX_TIES of them as flat indices into (3,N,N)
+ *   otf      b200cam_otf_bytes(N)      out: rfft2(roll(psf))/N^2 in the library's transposed layout */
+int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float* img_max,
+                       int* tie_count, int* tie_pos, float* otf,
+                       void* workspace, size_t workspace_bytes, int B, int N, void* stream);
+
+/* Sensor image, backward (autograd through Optics.py:126-128 in closed form, incl. the amax term).
+ *   grad_sensor [B][3][N][N]   dL/dsensor
+ *   sensor, img_max, tie_count, tie_pos, otf: the outputs of b200cam_sensor_fwd on the same img/psf
+ *   grad_psf    [3][N][N]      out: dL/dpsf (centred frame), summed over the batch
+ *   grad_img    [B][3][N][N]   out or NULL (no reference caller needs it) */
+int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* sensor,
+                       const float* img_max, const int* tie_count, const int* tie_pos,
+                       const float* psf, const float* otf, float* grad_psf, float* grad_img,
+                       void* workspace, size_t workspace_bytes, int B, int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CAM_H_ */

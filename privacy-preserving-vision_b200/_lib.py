@@ -1,0 +1,107 @@
+"""ctypes binding of ``libb200cam.so`` (C ABI in ``include/b200cam.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``build_library()`` with
+``nvcc -gencode arch=compute_100a,code=sm_100a`` - no torch C++ headers, so it is ABI-stable.
+There is deliberately no fallback: if the shared object is missing, or a compute entry point
+is called without a CUDA device, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB_PATH = CSRC / "libb200cam.so"
+INCLUDE = Path(__file__).resolve().parent.parent / "include"
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+_lock = threading.Lock()
+_lib = None
+_inited: set[tuple[int, int]] = set()
+
+_f = ctypes.c_void_p      # device float*
+_SIGNATURES = {
+    "b200cam_version": (ctypes.c_int, []),
+    "b200cam_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "b200cam_supported": (ctypes.c_int, [ctypes.c_int]),
+    "b200cam_init": (ctypes.c_int, [ctypes.c_int]),
+    "b200cam_otf_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "b200cam_psf_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "b200cam_sensor_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "b200cam_psf_fwd": (ctypes.c_int, [_f, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _f, _f, _f,
+                                       _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "b200cam_psf_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _f, _f, _f, _f,
+                                       _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
+    "b200cam_sensor_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f,
+                                          _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "b200cam_sensor_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f,
+                                          _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def sources() -> list[Path]:
+    return sorted(CSRC.glob("*.cu"))
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """Compile csrc/*.cu into csrc/libb200cam.so for sm_100a (cross-compiles without a GPU)."""
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))
+    if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(s) for s in sources()]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the in-tree library and declare the prototypes.  Raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not LIB_PATH.exists():
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(b200cam has no CPU or PyTorch fallback)")
+            lib = ctypes.CDLL(str(LIB_PATH))
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+        return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        msg = load_library().b200cam_error_string(code)
+        raise RuntimeError(f"b200cam error {code}: {msg.decode() if msg else '?'}")
+
+
+def ensure_init(N: int, device_index: int) -> None:
+    """b200cam_init(N) once per (device, N); allocates, so it must happen outside graph capture."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("b200cam needs a CUDA device (sm_100a); there is no CPU path")
+    key = (device_index, N)
+    if key in _inited:
+        return
+    lib = load_library()
+    with torch.cuda.device(device_index):
+        check(lib.b200cam_init(N))
+    _inited.add(key)
+
+
+def ptr(t) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)

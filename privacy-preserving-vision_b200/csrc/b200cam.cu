@@ -1,0 +1,492 @@
+// b200cam: __global__ wrappers, launch sequencing and the C ABI (include/b200cam.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <mutex>
+
+#include "../../include/b200cam.h"
+#include "kernels.cuh"
+
+namespace b200cam {
+
+// ------------------------------------------------------------------------------------------
+// __global__ wrappers: one CUDA thread per Exec "tid", dynamic shared memory as float2[]
+// ------------------------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char smem_raw[];
+#define SMEM2 reinterpret_cast<float2*>(smem_raw)
+
+template <int N>
+__global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_r2c(RowsR2CParams p) {
+    DeviceExec ex;
+    rows_r2c_body<N>(ex, p, SMEM2);
+}
+template <int N>
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_conv(ColsConvParams p) {
+    DeviceExec ex;
+    cols_conv_body<N>(ex, p, SMEM2);
+}
+template <int N>
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_fwd(ColsFwdParams p) {
+    DeviceExec ex;
+    cols_fwd_body<N>(ex, p, SMEM2);
+}
+template <int N>
+__global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_c2r(RowsC2RParams p) {
+    DeviceExec ex;
+    rows_c2r_body<N>(ex, p, SMEM2);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_normalise(NormaliseParams p) {
+    DeviceExec ex;
+    normalise_body(ex, p, gridDim.x);
+}
+template <int N>
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_accum(ColsAccumParams p) {
+    DeviceExec ex;
+    AccumState<N> st;
+    cols_accum_body<N>(ex, p, SMEM2, &st);
+}
+template <int N>
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_reduce_inv(ColsReduceInvParams p) {
+    DeviceExec ex;
+    cols_reduce_inv_body<N>(ex, p, SMEM2);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_tie_coef(TieTermParams p) {
+    DeviceExec ex;
+    tie_coef_body(ex, p, gridDim.x);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_tie_term(TieTermParams p) {
+    DeviceExec ex;
+    tie_term_body(ex, p, gridDim.x);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_tie_term_img(TieTermImgParams p) {
+    DeviceExec ex;
+    tie_term_img_body(ex, p, gridDim.x);
+}
+template <int N, class Load>
+__global__ void __launch_bounds__(CRowsSmem<N>::THREADS) k_crows_fwd(CRowsFwdParams p, Load load) {
+    DeviceExec ex;
+    crows_fwd_body<N>(ex, p, load, SMEM2);
+}
+template <int N>
+__global__ void __launch_bounds__(CColsSmem<N>::THREADS) k_ccols_mix(CColsMixParams p) {
+    DeviceExec ex;
+    ccols_mix_body<N>(ex, p, SMEM2);
+}
+template <int N, class Epi>
+__global__ void __launch_bounds__(CRowsSmem<N>::THREADS) k_crows_inv(CRowsInvParams p, Epi epi) {
+    DeviceExec ex;
+    crows_inv_body<N>(ex, p, epi, SMEM2);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_reduce(ReduceParams p) {
+    __shared__ float red[3 * EW_THREADS];
+    DeviceExec ex;
+    reduce_body(ex, p, red);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_psf_finalise(PsfFinaliseParams p) {
+    __shared__ float red[3 * EW_THREADS];
+    DeviceExec ex;
+    psf_finalise_body(ex, p, gridDim.x, red);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_psf_grad_prepare(PsfGradPrepParams p) {
+    __shared__ float red[EW_THREADS];
+    DeviceExec ex;
+    psf_grad_prepare_body(ex, p, gridDim.x, red);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_sum3(Sum3Params p) {
+    DeviceExec ex;
+    sum3_body(ex, p, gridDim.x);
+}
+__global__ void k_fill_twiddle(float2* tw, int N) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < N) {
+        double s, c;
+        sincospi(-2.0 * j / N, &s, &c);
+        tw[j] = make_float2(static_cast<float>(c), static_cast<float>(s));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-device state: twiddle tables (the only thing the library owns)
+// ------------------------------------------------------------------------------------------
+constexpr int MAX_DEV = 64;
+constexpr int EW_GRID = 296;   // 2 x 148 SMs for the element-wise / reduction kernels
+
+inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+struct DeviceState { float2* tw[11] = {nullptr}; };
+static DeviceState g_state[MAX_DEV];
+static std::mutex g_mutex;
+
+static const float2* twiddle(int N) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    return g_state[dev].tw[log2i(N)];
+}
+
+template <class K>
+static cudaError_t optin(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+template <int N>
+static cudaError_t init_kernels() {
+    cudaError_t e;
+    if ((e = optin(k_rows_r2c<N>, RowsR2CSmem<N>::BYTES))) return e;
+    if ((e = optin(k_rows_c2r<N>, RowsR2CSmem<N>::BYTES))) return e;
+    if ((e = optin(k_cols_conv<N>, ColsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_cols_fwd<N>, ColsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_cols_accum<N>, ColsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_cols_reduce_inv<N>, ColsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_crows_fwd<N, PupilLoad>, CRowsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_crows_fwd<N, GradFieldLoad>, CRowsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_crows_inv<N, IntensityEpilogue>, CRowsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_crows_inv<N, HeightGradEpilogue>, CRowsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_ccols_mix<N>, CColsSmem<N>::BYTES))) return e;
+    return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace carving (256-byte aligned slices of the caller's buffer)
+// ------------------------------------------------------------------------------------------
+struct Carver {
+    unsigned char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<unsigned char*>(p)) {}
+    template <class T>
+    T* take(size_t count) {
+        T* r = reinterpret_cast<T*>(base + off);
+        off += (count * sizeof(T) + 255) / 256 * 256;
+        return r;
+    }
+};
+
+static int accum_chunks(int N, int B) {
+    const int colgroups = (3 * (N / 2 + 1) + 7) / 8;
+    int n = 592 / colgroups;
+    if (n < 1) n = 1;
+    if (n > B) n = B;
+    return n;
+}
+
+struct PsfWs {
+    float2* st; float* I; float* gtot; float* gh3; float* part_rows; float* part_ew;
+    size_t bytes;
+    PsfWs(void* p, int N) {
+        Carver c(p);
+        const size_t NN = static_cast<size_t>(N) * N;
+        st = c.take<float2>(3 * NN);
+        I = c.take<float>(3 * NN);
+        gtot = c.take<float>(3 * NN);
+        gh3 = c.take<float>(3 * NN);
+        part_rows = c.take<float>(3 * N);
+        part_ew = c.take<float>(3 * EW_GRID);
+        bytes = c.off;
+    }
+};
+
+struct SensorWs {
+    float2* stx; float2* stg; float2* partial; float2* stp; float* dot_partial; float* coef;
+    size_t bytes;
+    SensorWs(void* p, int N, int B, bool backward) {
+        Carver c(p);
+        const size_t plane = static_cast<size_t>(N / 2 + 1) * N;
+        stx = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
+        if (backward) {
+            stg = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
+            partial = c.take<float2>(static_cast<size_t>(accum_chunks(N, B)) * 3 * plane);
+            stp = c.take<float2>(3 * plane);
+            dot_partial = c.take<float>(static_cast<size_t>(B) * 3 * N);
+            coef = c.take<float>(B);
+        } else {
+            stg = nullptr; partial = nullptr; stp = nullptr; dot_partial = nullptr; coef = nullptr;
+        }
+        bytes = c.off;
+    }
+};
+
+#define CK(expr)                                   \
+    do {                                           \
+        cudaError_t e_ = (expr);                   \
+        if (e_ != cudaSuccess) return static_cast<int>(e_); \
+    } while (0)
+#define LAUNCH_CHECK() CK(cudaGetLastError())
+
+// ------------------------------------------------------------------------------------------
+// launch sequences
+// ------------------------------------------------------------------------------------------
+template <int N>
+static int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const float* rho, const float* kappa,
+                        float* psf, float2* field, float* stats, void* ws_ptr, cudaStream_t s) {
+    using T = Tile<N>;
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    PsfWs ws(ws_ptr, N);
+    PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
+    const dim3 rgrid(N / T::ROWS, 3);
+    k_crows_fwd<N, PupilLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsFwdParams{ws.st, tw}, load);
+    LAUNCH_CHECK();
+    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(
+        CColsMixParams{ws.st, Ht, tw, 0, 1.0f / (3.0f * N * N)});
+    LAUNCH_CHECK();
+    IntensityEpilogue epi{field, ws.I, ws.part_rows, N};
+    k_crows_inv<N, IntensityEpilogue><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsInvParams{ws.st, tw}, epi);
+    LAUNCH_CHECK();
+    k_reduce<<<1, EW_THREADS, 0, s>>>(ReduceParams{ws.part_rows, stats, 3 * (N / T::ROWS), 0, N});
+    LAUNCH_CHECK();
+    k_psf_finalise<<<EW_GRID, EW_THREADS, 0, s>>>(PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, N});
+    LAUNCH_CHECK();
+    k_reduce<<<1, EW_THREADS, 0, s>>>(ReduceParams{ws.part_ew, stats, EW_GRID, 1, N});
+    LAUNCH_CHECK();
+    return 0;
+}
+
+template <int N>
+static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, const float2* A, const float2* Ht,
+                        const float* rho, const float* kappa, const float* psf, const float2* field, float* stats,
+                        float* grad_h, void* ws_ptr, cudaStream_t s) {
+    using T = Tile<N>;
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    PsfWs ws(ws_ptr, N);
+    k_psf_grad_prepare<<<EW_GRID, EW_THREADS, 0, s>>>(PsfGradPrepParams{gpsf, gscal, psf, rho, stats, ws.gtot, ws.part_ew, N});
+    LAUNCH_CHECK();
+    k_reduce<<<1, EW_THREADS, 0, s>>>(ReduceParams{ws.part_ew, stats, EW_GRID, 2, N});
+    LAUNCH_CHECK();
+    const dim3 rgrid(N / T::ROWS, 3);
+    GradFieldLoad load{field, ws.gtot, stats, N};
+    k_crows_fwd<N, GradFieldLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsFwdParams{ws.st, tw}, load);
+    LAUNCH_CHECK();
+    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(
+        CColsMixParams{ws.st, Ht, tw, 1, 1.0f / (3.0f * N * N)});
+    LAUNCH_CHECK();
+    HeightGradEpilogue epi{PupilLoad{A, h, {kappa[0], kappa[1], kappa[2]}, N}, ws.gh3, N};
+    k_crows_inv<N, HeightGradEpilogue><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsInvParams{ws.st, tw}, epi);
+    LAUNCH_CHECK();
+    k_sum3<<<EW_GRID, EW_THREADS, 0, s>>>(Sum3Params{ws.gh3, grad_h, N * N});
+    LAUNCH_CHECK();
+    return 0;
+}
+
+template <int N>
+static int otf_impl(const float* psf, float2* otf, const float2* tw, cudaStream_t s) {
+    using T = Tile<N>;
+    k_rows_r2c<N><<<dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsR2CParams{psf, otf, tw, nullptr, nullptr, nullptr, nullptr});
+    LAUNCH_CHECK();
+    const int total = 3 * T::NC;
+    k_cols_fwd<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        ColsFwdParams{otf, tw, total, 1, 1.0f / (static_cast<float>(N) * N)});
+    LAUNCH_CHECK();
+    return 0;
+}
+
+template <int N>
+static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
+                           int* tie_pos, float2* otf, void* ws_ptr, int B, cudaStream_t s) {
+    using T = Tile<N>;
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    int rc = otf_impl<N>(psf, otf, tw, s);
+    if (rc) return rc;
+    SensorWs ws(ws_ptr, N, B, false);
+    const int planes = 3 * B;
+    const dim3 rgrid(N / T::ROWS, planes);
+    k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsR2CParams{img, ws.stx, tw, nullptr, nullptr, img_max, tie_count});
+    LAUNCH_CHECK();
+    const int total = planes * T::NC;
+    k_cols_conv<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        ColsConvParams{ws.stx, ws.stx, otf, tw, nullptr, total, 0});
+    LAUNCH_CHECK();
+    k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsC2RParams{ws.stx, sensor, tw, img_max, 1.0f});
+    LAUNCH_CHECK();
+    const long long n4 = static_cast<long long>(planes) * N * N / 4;
+    const int grid = static_cast<int>(n4 / EW_THREADS < 148 * 8 ? (n4 + EW_THREADS - 1) / EW_THREADS : 148 * 8);
+    k_normalise<<<grid, EW_THREADS, 0, s>>>(NormaliseParams{sensor, img_max, tie_count, tie_pos, n4, 3 * N * N / 4});
+    LAUNCH_CHECK();
+    return 0;
+}
+
+template <int N>
+static int sensor_bwd_impl(const float* g, const float* img, const float* sensor, const float* img_max,
+                           const int* tie_count, const int* tie_pos, const float* psf, const float2* otf, float* grad_psf,
+                           float* grad_img, void* ws_ptr, int B, cudaStream_t s) {
+    using T = Tile<N>;
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    SensorWs ws(ws_ptr, N, B, true);
+    const int planes = 3 * B, tiles = N / T::ROWS;
+    const dim3 rgrid(tiles, planes);
+    k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsR2CParams{img, ws.stx, tw, nullptr, nullptr, nullptr, nullptr});
+    LAUNCH_CHECK();
+    k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsR2CParams{g, ws.stg, tw, sensor, ws.dot_partial, nullptr, nullptr});
+    LAUNCH_CHECK();
+    const int nchunks = accum_chunks(N, B);
+    const int chunk = (B + nchunks - 1) / nchunks;
+    const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
+    k_cols_accum<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        ColsAccumParams{ws.stx, ws.stg, ws.partial, tw, img_max, B, chunk});
+    LAUNCH_CHECK();
+    k_cols_reduce_inv<N><<<colgroups, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        ColsReduceInvParams{ws.partial, ws.stp, tw, (B + chunk - 1) / chunk, 1.0f / (static_cast<float>(N) * N)});
+    LAUNCH_CHECK();
+    k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
+    LAUNCH_CHECK();
+    TieTermParams tp{grad_psf, img, img_max, tie_count, tie_pos, ws.dot_partial, ws.coef, B, N, tiles};
+    k_tie_coef<<<(B + EW_THREADS - 1) / EW_THREADS, EW_THREADS, 0, s>>>(tp);
+    LAUNCH_CHECK();
+    k_tie_term<<<(3 * N * N + EW_THREADS - 1) / EW_THREADS, EW_THREADS, 0, s>>>(tp);
+    LAUNCH_CHECK();
+    if (grad_img != nullptr) {
+        const int total = planes * T::NC;
+        k_cols_conv<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, total, 1});
+        LAUNCH_CHECK();
+        k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+            RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
+        LAUNCH_CHECK();
+        const long long tot = static_cast<long long>(planes) * N * N;
+        const int grid = static_cast<int>(tot / EW_THREADS < 148 * 8 ? (tot + EW_THREADS - 1) / EW_THREADS : 148 * 8);
+        k_tie_term_img<<<grid, EW_THREADS, 0, s>>>(TieTermImgParams{grad_img, psf, tie_count, tie_pos, ws.coef, B, N});
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace b200cam
+
+// ==========================================================================================
+//                                       C ABI
+// ==========================================================================================
+using namespace b200cam;
+
+#define DISPATCH_N(N_, CALL)                      \
+    switch (N_) {                                 \
+        case 64: { constexpr int NN_ = 64; return CALL; }     \
+        case 128: { constexpr int NN_ = 128; return CALL; }   \
+        case 256: { constexpr int NN_ = 256; return CALL; }   \
+        case 512: { constexpr int NN_ = 512; return CALL; }   \
+        case 1024: { constexpr int NN_ = 1024; return CALL; } \
+        default: return B200CAM_E_BAD_SIZE;       \
+    }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" {
+
+int b200cam_version(void) { return B200CAM_VERSION; }
+
+const char* b200cam_error_string(int code) {
+    switch (code) {
+        case 0: return "success";
+        case B200CAM_E_BAD_SIZE: return "b200cam: unsupported size (N must be 64,128,256,512,1024; B >= 1)";
+        case B200CAM_E_NULL: return "b200cam: required pointer is NULL";
+        case B200CAM_E_WORKSPACE: return "b200cam: workspace too small";
+        case B200CAM_E_NOT_INIT: return "b200cam: b200cam_init(N) was not called on this device";
+        case B200CAM_E_ALIGN: return "b200cam: pointer not 16-byte aligned";
+        default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "b200cam: unknown error";
+    }
+}
+
+int b200cam_supported(int N) { return N == 64 || N == 128 || N == 256 || N == 512 || N == 1024; }
+
+int b200cam_init(int N) {
+    if (!b200cam_supported(N)) return B200CAM_E_BAD_SIZE;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) return B200CAM_E_BAD_SIZE;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    const int l = log2i(N);
+    if (g_state[dev].tw[l] != nullptr) return 0;
+    float2* tw = nullptr;
+    CK(cudaMalloc(&tw, sizeof(float2) * N));
+    k_fill_twiddle<<<(N + 255) / 256, 256>>>(tw, N);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    cudaError_t e = cudaSuccess;
+    switch (N) {
+        case 64: e = init_kernels<64>(); break;
+        case 128: e = init_kernels<128>(); break;
+        case 256: e = init_kernels<256>(); break;
+        case 512: e = init_kernels<512>(); break;
+        case 1024: e = init_kernels<1024>(); break;
+    }
+    if (e != cudaSuccess) { cudaFree(tw); return static_cast<int>(e); }
+    g_state[dev].tw[l] = tw;
+    return 0;
+}
+
+size_t b200cam_otf_bytes(int N) {
+    return b200cam_supported(N) ? static_cast<size_t>(3) * (N / 2 + 1) * N * sizeof(float2) : 0;
+}
+
+size_t b200cam_psf_workspace_bytes(int N) {
+    if (!b200cam_supported(N)) return 0;
+    return PsfWs(nullptr, N).bytes;
+}
+
+size_t b200cam_sensor_workspace_bytes(int N, int B, int want_img_grad) {
+    (void)want_img_grad;
+    if (!b200cam_supported(N) || B < 1) return 0;
+    return SensorWs(nullptr, N, B, true).bytes;
+}
+
+int b200cam_psf_fwd(const float* h, const float* A, const float* Ht, const float* rho, const float* kappa,
+                    float* psf, float* field, float* stats, void* workspace, size_t workspace_bytes, int N,
+                    void* stream) {
+    if (!b200cam_supported(N)) return B200CAM_E_BAD_SIZE;
+    if (!h || !A || !Ht || !rho || !kappa || !psf || !field || !stats || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_psf_workspace_bytes(N)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(A) || !aligned16(Ht) || !aligned16(field) || !aligned16(workspace)) return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (psf_fwd_impl<NN_>(h, reinterpret_cast<const float2*>(A), reinterpret_cast<const float2*>(Ht), rho,
+                                     kappa, psf, reinterpret_cast<float2*>(field), stats, workspace, s)));
+}
+
+int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const float* h, const float* A,
+                    const float* Ht, const float* rho, const float* kappa, const float* psf, const float* field,
+                    float* stats, float* grad_h, void* workspace, size_t workspace_bytes, int N, void* stream) {
+    if (!b200cam_supported(N)) return B200CAM_E_BAD_SIZE;
+    if (!h || !A || !Ht || !rho || !kappa || !psf || !field || !stats || !grad_h || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_psf_workspace_bytes(N)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(A) || !aligned16(Ht) || !aligned16(field) || !aligned16(workspace)) return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (psf_bwd_impl<NN_>(grad_psf, grad_scalars, h, reinterpret_cast<const float2*>(A),
+                                     reinterpret_cast<const float2*>(Ht), rho, kappa, psf,
+                                     reinterpret_cast<const float2*>(field), stats, grad_h, workspace, s)));
+}
+
+int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
+                       int* tie_pos, float* otf, void* workspace, size_t workspace_bytes, int B, int N,
+                       void* stream) {
+    if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
+    if (!img || !psf || !sensor || !img_max || !tie_count || !tie_pos || !otf || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_sensor_workspace_bytes(N, B, 0)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(img) || !aligned16(sensor) || !aligned16(otf) || !aligned16(workspace) || !aligned16(psf))
+        return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (sensor_fwd_impl<NN_>(img, psf, sensor, img_max, tie_count, tie_pos,
+                                        reinterpret_cast<float2*>(otf), workspace, B, s)));
+}
+
+int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* sensor, const float* img_max,
+                       const int* tie_count, const int* tie_pos, const float* psf, const float* otf,
+                       float* grad_psf, float* grad_img, void* workspace, size_t workspace_bytes, int B, int N,
+                       void* stream) {
+    if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
+    if (!grad_sensor || !img || !sensor || !img_max || !tie_count || !tie_pos || !psf || !otf || !grad_psf || !workspace)
+        return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_sensor_workspace_bytes(N, B, grad_img != nullptr)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(grad_sensor) || !aligned16(img) || !aligned16(sensor) || !aligned16(otf) || !aligned16(workspace) ||
+        !aligned16(grad_psf) || (grad_img && !aligned16(grad_img)))
+        return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (sensor_bwd_impl<NN_>(grad_sensor, img, sensor, img_max, tie_count, tie_pos, psf,
+                                        reinterpret_cast<const float2*>(otf), grad_psf, grad_img, workspace, B, s)));
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// b200cam: host/device compatibility layer.
+//
+// The kernel bodies in this directory are written as `B200_HD` function templates split into
+// barrier-separated phases (see exec.cuh).  nvcc compiles them for sm_100a; the test-only
+// emulator (tests/emu/) compiles the very same bodies with g++ and runs the phases as loops
+// over thread ids, which lets the index arithmetic be checked on a machine without a GPU.
+// Nothing in the shipped library executes on the CPU.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_D __device__ __forceinline__
+#else
+#define B200_HD inline
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+#endif
+
+namespace b200cam {
+
+// ---- complex helpers (float2 = re, im) -------------------------------------------------
+B200_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+B200_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+B200_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * conj(b)
+B200_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+B200_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+B200_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+// multiply by +i / -i
+B200_HD float2 cmul_i(float2 a) { return make_float2(-a.y, a.x); }
+B200_HD float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+// ---- read-only loads --------------------------------------------------------------------
+template <class T>
+B200_HD T ld_ro(const T* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// ---- float max through integer atomics (order independent => deterministic) --------------
+B200_HD void atomic_max_float(float* addr, float v) {
+#if defined(__CUDA_ARCH__)
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+#else
+    if (v > *addr) *addr = v;
+#endif
+}
+
+B200_HD int atomic_add_int(int* addr, int v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(addr, v);
+#else
+    int old = *addr; *addr = old + v; return old;
+#endif
+}
+
+B200_HD float neg_inf() {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(0xff800000);
+#else
+    return -INFINITY;
+#endif
+}
+
+}  // namespace b200cam

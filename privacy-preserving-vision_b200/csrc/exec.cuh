@@ -1,0 +1,41 @@
+// b200cam: execution policies for phase-structured kernel bodies.
+//
+// A kernel body is a function template `body(Exec& ex, const Params& p, char* smem, State* st)`
+// that calls `ex.phase(nthreads_active, lambda(tid))` repeatedly.  A phase boundary is a block
+// barrier.  Per-thread values that must survive a barrier live in `st[ex.slot(tid)]`.
+//
+//   DeviceExec : one CUDA thread runs each lambda once, `__syncthreads()` after every phase.
+//   HostExec   : (test-only emulator) each phase is a loop over all thread ids of the block.
+#pragma once
+
+#include "compat.cuh"
+
+namespace b200cam {
+
+#if defined(__CUDACC__)
+struct DeviceExec {
+    __device__ __forceinline__ int bx() const { return blockIdx.x; }
+    __device__ __forceinline__ int by() const { return blockIdx.y; }
+    __device__ __forceinline__ int nthreads() const { return blockDim.x; }
+    __device__ __forceinline__ int slot(int) const { return 0; }
+    template <class F>
+    __device__ __forceinline__ void phase(F&& f) {
+        f(static_cast<int>(threadIdx.x));
+        __syncthreads();
+    }
+};
+#endif
+
+struct HostExec {
+    int bx_, by_, nthreads_;
+    int bx() const { return bx_; }
+    int by() const { return by_; }
+    int nthreads() const { return nthreads_; }
+    int slot(int tid) const { return tid; }
+    template <class F>
+    void phase(F&& f) {
+        for (int t = 0; t < nthreads_; ++t) f(t);
+    }
+};
+
+}  // namespace b200cam

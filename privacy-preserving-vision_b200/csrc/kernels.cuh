@@ -1,0 +1,1015 @@
+// b200cam: phase-structured kernel bodies of the generic (any power-of-two N) pipeline.
+//
+// Data layouts in HBM
+//   image planes        x[plane][y][x]                 fp32, plane = b*3 + c (NCHW contiguous)
+//   half spectrum  "ST" s[plane][u][y or v]            complex64, u < NC = N/2+1, TRANSPOSED:
+//                       each spectral column u is a contiguous run of N complex values, so the
+//                       column pass streams 8N-byte runs and the row passes write/read 128-byte
+//                       segments (16 rows x 8 B) per u.
+//   full spectrum  (PSF chain, complex fields)  f[lambda][u][y], u < N, same transposed form.
+//
+// Reference lines each body replaces are cited at the body.
+#pragma once
+
+#include "compat.cuh"
+#include "exec.cuh"
+#include "fft_plan.cuh"
+
+namespace b200cam {
+
+template <int N>
+struct Tile {
+    static constexpr int ROWS = (N <= 256) ? 16 : 8;   // image rows per CTA in the row passes
+    static constexpr int NP = ROWS / 2;                // real rows are transformed in pairs
+    static constexpr int NC = N / 2 + 1;
+    static constexpr int FP_PAIR = N + 16 / NP;        // natural-order smem row pitch (float2)
+    static constexpr int FP_ROW = N + 16 / ROWS;
+    static constexpr int COLS = 8;                     // spectral columns per CTA in column passes
+};
+
+// ---------------------------------------------------------------------------------------------
+// K1  rows_r2c : real rows -> transposed half spectrum (first half of rfftn, Utils.py:8-9)
+//      grid (N/ROWS, planes), block NP*LANES.
+//      optional: dot_with != nullptr accumulates sum(x*dot_with) per CTA into dot_partial
+//      (the s_b = sum(g*y) term of the amax backward), and init_max/init_count (tile 0 of channel
+//      0) reset the per-image max / tie counters for the kernels that follow in the stream.
+// ---------------------------------------------------------------------------------------------
+struct RowsR2CParams {
+    const float* x;          // [planes][N][N]
+    float2* st;              // [planes][NC][N]
+    const float2* tw;
+    const float* dot_with;   // nullable, same shape as x
+    float* dot_partial;      // [planes][N/ROWS]
+    float* init_max;         // nullable, [planes/3]
+    int* init_count;         // nullable, [planes/3]
+};
+
+template <int N>
+struct RowsR2CSmem {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    static constexpr int E_OFF = 0;
+    static constexpr int F_OFF = T::NP * P::E_SIZE;
+    static constexpr int RED_OFF = F_OFF + T::NP * T::FP_PAIR;            // float2 units
+    static constexpr int FLOAT2S = RED_OFF + (T::NP * P::LANES + 1) / 2;  // reduction scratch (floats)
+    static constexpr int BYTES = FLOAT2S * 8;
+    static constexpr int THREADS = T::NP * P::LANES;
+};
+
+template <int N, class Exec>
+B200_HD void rows_r2c_body(Exec& ex, const RowsR2CParams& p, float2* smem) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = RowsR2CSmem<N>;
+    const int tile = ex.bx(), plane = ex.by();
+    const int y0 = tile * T::ROWS;
+    float2* E = smem + S::E_OFF;
+    float2* F = smem + S::F_OFF;
+    float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
+
+    ex.phase([&](int tid) {
+        const int j = tid / P::LANES, a = tid % P::LANES;
+        float dot = 0.f;
+        if (a < P::R2) {
+            const float* r0 = p.x + (static_cast<size_t>(plane) * N + y0 + 2 * j) * N;
+            const float* r1 = r0 + N;
+            float2 v[P::R1];
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) v[i] = make_float2(ld_ro(r0 + P::R2 * i + a), ld_ro(r1 + P::R2 * i + a));
+            if (p.dot_with != nullptr) {
+                const float* d0 = p.dot_with + (static_cast<size_t>(plane) * N + y0 + 2 * j) * N;
+                const float* d1 = d0 + N;
+#pragma unroll
+                for (int i = 0; i < P::R1; ++i)
+                    dot += v[i].x * ld_ro(d0 + P::R2 * i + a) + v[i].y * ld_ro(d1 + P::R2 * i + a);
+            }
+            P::stepA(v, a, E + j * P::E_SIZE, p.tw);
+        }
+        red[tid] = dot;
+        if (tid == 0 && tile == 0 && plane % 3 == 0) {
+            if (p.init_max != nullptr) p.init_max[plane / 3] = neg_inf();
+            if (p.init_count != nullptr) p.init_count[plane / 3] = 0;
+        }
+    });
+    ex.phase([&](int tid) {
+        const int j = tid / P::LANES, b = tid % P::LANES;
+        if (b < P::R1) {
+            float2 v[P::R2];
+            P::stepB(v, b, E + j * P::E_SIZE);
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) F[j * T::FP_PAIR + b + P::R1 * i] = v[i];
+        }
+        if (tid == 0 && p.dot_with != nullptr) {
+            float s = 0.f;
+            for (int t = 0; t < S::THREADS; ++t) s += red[t];
+            p.dot_partial[plane * (N / T::ROWS) + tile] = s;
+        }
+    });
+    ex.phase([&](int tid) {
+        // unpack the pair spectrum Z = FFT(row_even + i*row_odd) into the two Hermitian halves
+        for (int w = tid; w < T::NP * T::NC; w += S::THREADS) {
+            const int u = w / T::NP, j = w % T::NP;
+            const float2 z1 = F[j * T::FP_PAIR + u];
+            const float2 z2 = F[j * T::FP_PAIR + ((N - u) & (N - 1))];
+            const float4 o = make_float4(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y),    // X_even[u]
+                                         0.5f * (z1.y + z2.y), -0.5f * (z1.x - z2.x));  // X_odd[u]
+            *reinterpret_cast<float4*>(p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0 + 2 * j) = o;
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  cols_conv : per spectral column  FFT_v -> x OTF -> IFFT_v, in place on ST
+//      (second half of rfftn, the multiply Utils.py:10 and first half of irfftn Utils.py:11)
+//      grid ceil(planes*NC / COLS), block COLS*LANES.  OTF layout [3][NC][N] (column = channel,u),
+//      pre-scaled by 1/N^2.  conj_otf: multiply by conj(OTF) (adjoint, for dL/dimg).
+//      col_scale (nullable, [planes/3]): extra per-image factor (1/max for the backward).
+// ---------------------------------------------------------------------------------------------
+struct ColsConvParams {
+    const float2* in;        // [planes][NC][N]
+    float2* out;             // same layout (may alias in)
+    const float2* otf;       // [3][NC][N]
+    const float2* tw;
+    const float* img_scale;  // nullable: per image multiplier is 1/img_scale[b]
+    int total_cols;          // planes*NC
+    int conj_otf;
+};
+
+template <int N>
+struct ColsSmem {
+    using P = Plan<N>;
+    static constexpr int COLS = Tile<N>::COLS;
+    static constexpr int THREADS = COLS * P::LANES;
+    static constexpr int FLOAT2S = 2 * COLS * P::E_SIZE;
+    static constexpr int BYTES = FLOAT2S * 8;
+};
+
+template <int N, class Exec>
+B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = ColsSmem<N>;
+    float2* E1 = smem;
+    float2* E2 = smem + S::COLS * P::E_SIZE;
+    const int col0 = ex.bx() * S::COLS;
+
+    ex.phase([&](int tid) {
+        const int jc = tid / P::LANES, a = tid % P::LANES;
+        const int col = col0 + jc;
+        if (col < p.total_cols && a < P::R2) {
+            const float2* src = p.in + static_cast<size_t>(col) * N;   // may alias p.out: plain loads
+            float2 v[P::R1];
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) v[i] = src[P::R2 * i + a];
+            P::stepA(v, a, E1 + jc * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int jc = tid / P::LANES, b = tid % P::LANES;
+        const int col = col0 + jc;
+        if (col < p.total_cols && b < P::R1) {
+            const int plane = col / T::NC, u = col % T::NC, c = plane % 3;
+            const float2* k = p.otf + (static_cast<size_t>(c) * T::NC + u) * N;
+            const float s = p.img_scale != nullptr ? 1.0f / ld_ro(p.img_scale + plane / 3) : 1.0f;
+            float2 v[P::R2];
+            P::stepB(v, b, E1 + jc * P::E_SIZE);
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) {
+                const float2 kk = ld_ro(k + b + P::R1 * i);
+                v[i] = p.conj_otf ? cmulc(v[i], kk) : cmul(v[i], kk);
+                if (p.img_scale != nullptr) v[i] = cscale(v[i], s);
+            }
+            P::stepC(v, b, E2 + jc * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int jc = tid / P::LANES, a = tid % P::LANES;
+        const int col = col0 + jc;
+        if (col < p.total_cols && a < P::R2) {
+            float2 v[P::R1];
+            P::stepD(v, a, E2 + jc * P::E_SIZE);
+            float2* dst = p.out + static_cast<size_t>(col) * N;
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = v[i];
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b cols_fwd : per spectral column FFT_v only, then a point-wise sign/scale, in place
+//      (used for the OTF: K = rfft2(roll(psf,-N/2)) = (-1)^(u+v) rfft2(psf), Optics.py:126 + Utils.py:9)
+// ---------------------------------------------------------------------------------------------
+struct ColsFwdParams {
+    float2* st;          // [planes][NC][N] in place; output is written in Q order = natural v index
+    const float2* tw;
+    int total_cols;
+    int checker_sign;    // multiply by (-1)^(u+v)
+    float scale;
+};
+
+template <int N, class Exec>
+B200_HD void cols_fwd_body(Exec& ex, const ColsFwdParams& p, float2* smem) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = ColsSmem<N>;
+    float2* E1 = smem;
+    const int col0 = ex.bx() * S::COLS;
+    ex.phase([&](int tid) {
+        const int jc = tid / P::LANES, a = tid % P::LANES;
+        const int col = col0 + jc;
+        if (col < p.total_cols && a < P::R2) {
+            const float2* src = p.st + static_cast<size_t>(col) * N;
+            float2 v[P::R1];
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) v[i] = src[P::R2 * i + a];
+            P::stepA(v, a, E1 + jc * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int jc = tid / P::LANES, b = tid % P::LANES;
+        const int col = col0 + jc;
+        if (col < p.total_cols && b < P::R1) {
+            const int u = col % T::NC;
+            float2 v[P::R2];
+            P::stepB(v, b, E1 + jc * P::E_SIZE);
+            float2* dst = p.st + static_cast<size_t>(col) * N;
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) {
+                const int k = b + P::R1 * i;
+                const float s = (p.checker_sign && ((u + k) & 1)) ? -p.scale : p.scale;
+                dst[k] = cscale(v[i], s);
+            }
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  rows_c2r : transposed half spectrum (already inverse-transformed along v) -> real rows
+//      (second half of irfftn, Utils.py:11) + per-image max (Optics.py:128, amax part)
+//      grid (N/ROWS, planes), block NP*LANES
+// ---------------------------------------------------------------------------------------------
+struct RowsC2RParams {
+    const float2* st;    // [planes][NC][N]
+    float* out;          // [planes][N][N]
+    const float2* tw;
+    float* img_max;      // nullable, [planes/3], atomically maximised
+    float scale;
+};
+
+template <int N, class Exec>
+B200_HD void rows_c2r_body(Exec& ex, const RowsC2RParams& p, float2* smem) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = RowsR2CSmem<N>;
+    const int tile = ex.bx(), plane = ex.by();
+    const int y0 = tile * T::ROWS;
+    float2* E = smem + S::E_OFF;
+    float2* F = smem + S::F_OFF;
+    float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
+
+    ex.phase([&](int tid) {
+        for (int w = tid; w < T::NP * T::NC; w += S::THREADS) {
+            const int u = w / T::NP, j = w % T::NP;
+            const float4 q = ld_ro(reinterpret_cast<const float4*>(
+                p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0 + 2 * j));
+            // Z = X_even + i X_odd ; Z[N-u] = conj(X_even[u]) + i conj(X_odd[u])
+            if (u == 0 || u == N / 2) {
+                F[j * T::FP_PAIR + u] = make_float2(q.x, q.z);   // irfft ignores Im at DC/Nyquist
+            } else {
+                F[j * T::FP_PAIR + u] = make_float2(q.x - q.w, q.y + q.z);
+                F[j * T::FP_PAIR + N - u] = make_float2(q.x + q.w, q.z - q.y);
+            }
+        }
+    });
+    ex.phase([&](int tid) {
+        const int j = tid / P::LANES, b = tid % P::LANES;
+        if (b < P::R1) {
+            float2 v[P::R2];
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) v[i] = F[j * T::FP_PAIR + b + P::R1 * i];
+            P::stepC(v, b, E + j * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int j = tid / P::LANES, a = tid % P::LANES;
+        float mx = neg_inf();
+        if (a < P::R2) {
+            float2 v[P::R1];
+            P::stepD(v, a, E + j * P::E_SIZE);
+            float* r0 = p.out + (static_cast<size_t>(plane) * N + y0 + 2 * j) * N;
+            float* r1 = r0 + N;
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) {
+                const float e = v[i].x * p.scale, o = v[i].y * p.scale;
+                r0[P::R2 * i + a] = e;
+                r1[P::R2 * i + a] = o;
+                mx = fmaxf(mx, fmaxf(e, o));
+            }
+        }
+        red[tid] = mx;
+    });
+    if (p.img_max != nullptr) {
+        ex.phase([&](int tid) {
+            if (tid == 0) {
+                float mx = red[0];
+                for (int t = 1; t < S::THREADS; ++t) mx = fmaxf(mx, red[t]);
+                atomic_max_float(p.img_max + plane / 3, mx);
+            }
+        });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4  normalise : y = conv / max_b  (Optics.py:128) + record positions that attain the max
+//      (torch's amax backward splits the gradient evenly between exact ties)
+//      1-D grid-stride over float4 elements; tie_pos[b][MAX_TIES], tie_count[b]
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_TIES = 8;
+
+struct NormaliseParams {
+    float* y;               // [B][3][N][N] in place: conv -> sensor
+    const float* img_max;   // [B]
+    int* tie_count;         // [B]
+    int* tie_pos;           // [B][MAX_TIES] flat index into (3,N,N)
+    long long n4;           // number of float4 elements
+    int per_image4;         // 3*N*N/4
+};
+
+template <class Exec>
+B200_HD void normalise_body(Exec& ex, const NormaliseParams& p, int grid_x) {
+    ex.phase([&](int tid) {
+        const long long stride = static_cast<long long>(grid_x) * ex.nthreads();
+        for (long long i = static_cast<long long>(ex.bx()) * ex.nthreads() + tid; i < p.n4; i += stride) {
+            const int b = static_cast<int>(i / p.per_image4);
+            const float m = ld_ro(p.img_max + b);
+            float4 v = reinterpret_cast<float4*>(p.y)[i];
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (e[q] == m) {
+                    const int slot = atomic_add_int(p.tie_count + b, 1);
+                    if (slot < MAX_TIES)
+                        p.tie_pos[b * MAX_TIES + slot] = static_cast<int>(i % p.per_image4) * 4 + q;
+                }
+            }
+            v.x = e[0] / m; v.y = e[1] / m; v.z = e[2] / m; v.w = e[3] / m;
+            reinterpret_cast<float4*>(p.y)[i] = v;
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6  cols_accum : batch reduction of the backward pass in the frequency domain
+//        acc[c][u][v] = sum_{b in chunk} conj(X_b[c][v,u]) * G_b[c][v,u] / max_b
+//      (closed form of autograd through Utils.py:7-12 w.r.t. the kernel)
+//      grid (ceil(3*NC/COLS), nchunks), block COLS*LANES.  Output partial[chunk][3][NC][N].
+//      Deterministic: fixed b order inside a chunk, chunks summed in order by K7.
+// ---------------------------------------------------------------------------------------------
+struct ColsAccumParams {
+    const float2* stx;      // [B*3][NC][N] row-transformed image
+    const float2* stg;      // [B*3][NC][N] row-transformed upstream gradient
+    float2* partial;        // [nchunks][3][NC][N]
+    const float2* tw;
+    const float* img_max;   // [B]
+    int B;
+    int chunk;              // images per chunk
+};
+
+template <int N>
+struct AccumState {
+    float2 acc[Plan<N>::R2];
+};
+
+template <int N, class Exec>
+B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, AccumState<N>* st) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = ColsSmem<N>;
+    float2* Ex = smem;
+    float2* Eg = smem + S::COLS * P::E_SIZE;
+    const int cu0 = ex.bx() * S::COLS;
+    const int b0 = ex.by() * p.chunk;
+    const int b1 = (b0 + p.chunk < p.B) ? b0 + p.chunk : p.B;
+    constexpr int TOTAL = 3 * T::NC;
+
+    ex.phase([&](int tid) {
+        AccumState<N>& s = st[ex.slot(tid)];
+#pragma unroll
+        for (int i = 0; i < P::R2; ++i) s.acc[i] = make_float2(0.f, 0.f);
+    });
+    for (int b = b0; b < b1; ++b) {
+        ex.phase([&](int tid) {
+            const int jc = tid / P::LANES, a = tid % P::LANES;
+            const int cu = cu0 + jc;
+            if (cu < TOTAL && a < P::R2) {
+                const int c = cu / T::NC, u = cu % T::NC;
+                const size_t off = (static_cast<size_t>(b * 3 + c) * T::NC + u) * N;
+                float2 v[P::R1];
+#pragma unroll
+                for (int i = 0; i < P::R1; ++i) v[i] = ld_ro(p.stx + off + P::R2 * i + a);
+                P::stepA(v, a, Ex + jc * P::E_SIZE, p.tw);
+#pragma unroll
+                for (int i = 0; i < P::R1; ++i) v[i] = ld_ro(p.stg + off + P::R2 * i + a);
+                P::stepA(v, a, Eg + jc * P::E_SIZE, p.tw);
+            }
+        });
+        ex.phase([&](int tid) {
+            const int jc = tid / P::LANES, bb = tid % P::LANES;
+            const int cu = cu0 + jc;
+            if (cu < TOTAL && bb < P::R1) {
+                AccumState<N>& s = st[ex.slot(tid)];
+                const float inv_m = 1.0f / ld_ro(p.img_max + b);
+                float2 vx[P::R2], vg[P::R2];
+                P::stepB(vx, bb, Ex + jc * P::E_SIZE);
+                P::stepB(vg, bb, Eg + jc * P::E_SIZE);
+#pragma unroll
+                for (int i = 0; i < P::R2; ++i) {
+                    const float2 t = cmulc(vg[i], vx[i]);   // G * conj(X)
+                    s.acc[i].x += t.x * inv_m;
+                    s.acc[i].y += t.y * inv_m;
+                }
+            }
+        });
+    }
+    ex.phase([&](int tid) {
+        const int jc = tid / P::LANES, bb = tid % P::LANES;
+        const int cu = cu0 + jc;
+        if (cu < TOTAL && bb < P::R1) {
+            const AccumState<N>& s = st[ex.slot(tid)];
+            float2* dst = p.partial + (static_cast<size_t>(ex.by()) * TOTAL + cu) * N;
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) dst[bb + P::R1 * i] = s.acc[i];
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7  cols_reduce_inv : sum the chunk partials in order, apply (-1)^(u+v) (the adjoint of the
+//      roll at Optics.py:126) and 1/N^2, inverse FFT along v -> ST layout for rows_c2r
+//      grid ceil(3*NC/COLS), block COLS*LANES
+// ---------------------------------------------------------------------------------------------
+struct ColsReduceInvParams {
+    const float2* partial;   // [nchunks][3][NC][N]
+    float2* st;              // [3][NC][N]
+    const float2* tw;
+    int nchunks;
+    float scale;
+};
+
+template <int N, class Exec>
+B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2* smem) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = ColsSmem<N>;
+    float2* E = smem;
+    const int cu0 = ex.bx() * S::COLS;
+    constexpr int TOTAL = 3 * T::NC;
+    ex.phase([&](int tid) {
+        const int jc = tid / P::LANES, b = tid % P::LANES;
+        const int cu = cu0 + jc;
+        if (cu < TOTAL && b < P::R1) {
+            const int u = cu % T::NC;
+            float2 v[P::R2];
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) v[i] = make_float2(0.f, 0.f);
+            for (int ch = 0; ch < p.nchunks; ++ch) {
+                const float2* src = p.partial + (static_cast<size_t>(ch) * TOTAL + cu) * N;
+#pragma unroll
+                for (int i = 0; i < P::R2; ++i) v[i] = cadd(v[i], ld_ro(src + b + P::R1 * i));
+            }
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) {
+                const int k = b + P::R1 * i;
+                v[i] = cscale(v[i], ((u + k) & 1) ? -p.scale : p.scale);
+            }
+            P::stepC(v, b, E + jc * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int jc = tid / P::LANES, a = tid % P::LANES;
+        const int cu = cu0 + jc;
+        if (cu < TOTAL && a < P::R2) {
+            float2 v[P::R1];
+            P::stepD(v, a, E + jc * P::E_SIZE);
+            float2* dst = p.st + static_cast<size_t>(cu) * N;
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = v[i];
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8  tie_term : the arg-max part of the amax backward, in the spatial domain
+//      gpsf[c][p] -= sum_b sum_{ties t of image b in channel c} (s_b/(n_b m_b)) * x_b[c][(p*_t - p + N/2) mod N]
+//      with s_b = sum(g_b * y_b) assembled from the K1 partials in fixed order.
+//      grid-stride over 3*N*N outputs.
+// ---------------------------------------------------------------------------------------------
+struct TieTermParams {
+    float* gpsf;              // [3][N][N] in place
+    const float* x;           // [B][3][N][N]
+    const float* img_max;     // [B]
+    const int* tie_count;     // [B]
+    const int* tie_pos;       // [B][MAX_TIES]
+    const float* dot_partial; // [B*3][tiles]
+    float* coef;              // [B] scratch: s_b / (n_b m_b), filled by tie_coef_body
+    int B, N, tiles;
+};
+
+template <class Exec>
+B200_HD void tie_coef_body(Exec& ex, const TieTermParams& p, int grid_x) {
+    ex.phase([&](int tid) {
+        const int b = ex.bx() * ex.nthreads() + tid;
+        (void)grid_x;
+        if (b < p.B) {
+            float s = 0.f;
+            for (int t = 0; t < 3 * p.tiles; ++t) s += p.dot_partial[b * 3 * p.tiles + t];
+            const int n = p.tie_count[b] > 0 ? p.tie_count[b] : 1;
+            p.coef[b] = s / (static_cast<float>(n) * p.img_max[b]);
+        }
+    });
+}
+
+template <class Exec>
+B200_HD void tie_term_body(Exec& ex, const TieTermParams& p, int grid_x) {
+    ex.phase([&](int tid) {
+        const int N = p.N, NN = N * N, total = 3 * NN;
+        const int stride = grid_x * ex.nthreads();
+        for (int idx = ex.bx() * ex.nthreads() + tid; idx < total; idx += stride) {
+            const int c = idx / NN, py = (idx % NN) / N, px = idx % N;
+            float acc = 0.f;
+            for (int b = 0; b < p.B; ++b) {
+                const int n = p.tie_count[b] < MAX_TIES ? p.tie_count[b] : MAX_TIES;
+                for (int t = 0; t < n; ++t) {
+                    const int pos = p.tie_pos[b * MAX_TIES + t];
+                    if (pos / NN != c) continue;
+                    const int ty = (pos % NN) / N, tx = pos % N;
+                    const int sy = (ty - py + N / 2 + N) & (N - 1), sx = (tx - px + N / 2 + N) & (N - 1);
+                    acc += p.coef[b] * ld_ro(p.x + (static_cast<size_t>(b) * 3 + c) * NN + sy * N + sx);
+                }
+            }
+            p.gpsf[idx] -= acc;
+        }
+    });
+}
+
+// K9  tie_term_img : the same arg-max term for dL/dimg (optional output)
+//      gimg[b][c][q] -= coef_b * sum_{ties t of b in channel c} psf[c][(p*_t - q + N/2) mod N]
+struct TieTermImgParams {
+    float* gimg;              // [B][3][N][N] in place
+    const float* psf;         // [3][N][N] centred
+    const int* tie_count;
+    const int* tie_pos;
+    const float* coef;        // [B]
+    int B, N;
+};
+
+template <class Exec>
+B200_HD void tie_term_img_body(Exec& ex, const TieTermImgParams& p, int grid_x) {
+    ex.phase([&](int tid) {
+        const int N = p.N, NN = N * N;
+        const long long total = static_cast<long long>(p.B) * 3 * NN;
+        const long long stride = static_cast<long long>(grid_x) * ex.nthreads();
+        for (long long idx = static_cast<long long>(ex.bx()) * ex.nthreads() + tid; idx < total; idx += stride) {
+            const int b = static_cast<int>(idx / (3 * NN));
+            const int r = static_cast<int>(idx % (3 * NN));
+            const int c = r / NN, qy = (r % NN) / N, qx = r % N;
+            const int n = p.tie_count[b] < MAX_TIES ? p.tie_count[b] : MAX_TIES;
+            float acc = 0.f;
+            for (int t = 0; t < n; ++t) {
+                const int pos = p.tie_pos[b * MAX_TIES + t];
+                if (pos / NN != c) continue;
+                const int ty = (pos % NN) / N, tx = pos % N;
+                const int sy = (ty - qy + N / 2 + N) & (N - 1), sx = (tx - qx + N / 2 + N) & (N - 1);
+                acc += ld_ro(p.psf + c * NN + sy * N + sx);
+            }
+            if (acc != 0.f) p.gimg[idx] -= p.coef[b] * acc;
+        }
+    });
+}
+
+// =============================================================================================
+//                      PSF chain (complex fields, 3 wavelengths)
+// =============================================================================================
+
+// loaders / epilogues of the complex row passes
+struct PupilLoad {     // V = A * exp(i*kappa_l*h)   (Optics.py:89-100)
+    const float2* A;   // [3][N][N] constant pupil table (aperture, lens, defocus and pre-phase)
+    const float* h;    // [N][N]
+    float kappa[3];
+    int N;
+    B200_HD float2 operator()(int l, int y, int x) const {
+        const size_t i = static_cast<size_t>(y) * N + x;
+        const float phi = kappa[l] * ld_ro(h + i);
+        float s, c;
+#if defined(__CUDA_ARCH__)
+        sincosf(phi, &s, &c);
+#else
+        s = sinf(phi); c = cosf(phi);
+#endif
+        return cmul(ld_ro(A + static_cast<size_t>(l) * N * N + i), make_float2(c, s));
+    }
+};
+
+struct GradFieldLoad {  // GU = 2 * (gtot - dot)/S * U      (adjoint of |U|^2 / sum, Optics.py:109-110)
+    const float2* U;    // [3][N][N]
+    const float* gtot;  // [3][N][N]
+    const float* scal;  // device scalars: [0]=S, [3]=dot
+    int N;
+    B200_HD float2 operator()(int l, int y, int x) const {
+        const size_t i = (static_cast<size_t>(l) * N + y) * N + x;
+        const float gi = 2.0f * (ld_ro(gtot + i) - ld_ro(scal + 3)) / ld_ro(scal + 0);
+        return cscale(ld_ro(U + i), gi);
+    }
+};
+
+// P1  crows_fwd : complex rows -> transposed full spectrum.  grid (N/ROWS, 3), block ROWS*LANES
+template <int N>
+struct CRowsSmem {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    static constexpr int THREADS = T::ROWS * P::LANES;
+    static constexpr int E_OFF = 0;
+    static constexpr int F_OFF = T::ROWS * P::E_SIZE;
+    static constexpr int RED_OFF = F_OFF + T::ROWS * T::FP_ROW;
+    static constexpr int FLOAT2S = RED_OFF + THREADS;   // 2 floats per thread of scratch
+    static constexpr int BYTES = FLOAT2S * 8;
+};
+
+struct CRowsFwdParams {
+    float2* st;         // [3][N][N] transposed: st[l][u][y]
+    const float2* tw;
+};
+
+template <int N, class Load, class Exec>
+B200_HD void crows_fwd_body(Exec& ex, const CRowsFwdParams& p, const Load& load, float2* smem) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = CRowsSmem<N>;
+    const int tile = ex.bx(), l = ex.by();
+    const int y0 = tile * T::ROWS;
+    float2* E = smem + S::E_OFF;
+    float2* F = smem + S::F_OFF;
+    ex.phase([&](int tid) {
+        const int j = tid / P::LANES, a = tid % P::LANES;
+        if (a < P::R2) {
+            float2 v[P::R1];
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) v[i] = load(l, y0 + j, P::R2 * i + a);
+            P::stepA(v, a, E + j * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int j = tid / P::LANES, b = tid % P::LANES;
+        if (b < P::R1) {
+            float2 v[P::R2];
+            P::stepB(v, b, E + j * P::E_SIZE);
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) F[j * T::FP_ROW + b + P::R1 * i] = v[i];
+        }
+    });
+    ex.phase([&](int tid) {
+        for (int w = tid; w < T::ROWS * N; w += S::THREADS) {
+            const int u = w / T::ROWS, j = w % T::ROWS;
+            p.st[(static_cast<size_t>(l) * N + u) * N + y0 + j] = F[j * T::FP_ROW + u];
+        }
+    });
+}
+
+// P2  ccols_mix : per spectral column u, for the three wavelengths together:
+//      FFT_v, 3-point DFT across wavelength, x H_m (or conj), inverse 3-point DFT, IFFT_v, in place.
+//      This is `fftn` / `ifftn` WITHOUT a dim argument at Optics.py:101,105 (they also transform
+//      the wavelength axis; H is indexed by the DFT bin m - SURVEY trap T1).
+//      grid ceil(N/CC), block CC*3*LANES.  H layout [m][u][v] (the reference's table transposed);
+//      scale = 1/(3 N^2) makes the pair an exact (normalised) inverse.
+struct CColsMixParams {
+    float2* st;         // [3][N][N] transposed, in place
+    const float2* H;    // [3][N][N] TRANSPOSED (m, u, v) so that a column's run is contiguous
+    const float2* tw;
+    int conj_h;
+    float scale;
+};
+
+template <int N>
+struct CColsSmem {
+    using P = Plan<N>;
+    static constexpr int CC = 4;                      // columns per CTA
+    static constexpr int THREADS = CC * 3 * P::LANES;
+    static constexpr int E_OFF = 0;
+    static constexpr int G_OFF = CC * 3 * P::E_SIZE;  // natural-order exchange for the 3-pt DFT
+    static constexpr int GP = N + 1;
+    static constexpr int FLOAT2S = G_OFF + 2 * CC * 3 * GP;
+    static constexpr int BYTES = FLOAT2S * 8;
+};
+
+template <int N, class Exec>
+B200_HD void ccols_mix_body(Exec& ex, const CColsMixParams& p, float2* smem) {
+    using P = Plan<N>;
+    using S = CColsSmem<N>;
+    float2* E = smem + S::E_OFF;
+    float2* G1 = smem + S::G_OFF;
+    float2* G2 = G1 + S::CC * 3 * S::GP;
+    const int u0 = ex.bx() * S::CC;
+    // w3 = exp(-2*pi*i/3)
+    const float2 w3 = make_float2(-0.5f, -0.86602540378443864676f);
+
+    ex.phase([&](int tid) {
+        const int f = tid / P::LANES, a = tid % P::LANES;   // f = jc*3 + l
+        const int jc = f / 3, l = f % 3, u = u0 + jc;
+        if (u < N && a < P::R2) {
+            const float2* src = p.st + (static_cast<size_t>(l) * N + u) * N;
+            float2 v[P::R1];
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) v[i] = src[P::R2 * i + a];
+            P::stepA(v, a, E + f * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int f = tid / P::LANES, b = tid % P::LANES;
+        const int u = u0 + f / 3;
+        if (u < N && b < P::R1) {
+            float2 v[P::R2];
+            P::stepB(v, b, E + f * P::E_SIZE);
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) G1[f * S::GP + b + P::R1 * i] = v[i];
+        }
+    });
+    ex.phase([&](int tid) {
+        // thread (jc, m, b): W_m[k] = H_m[k,u] * sum_l w3^(m*l) Vhat_l[k]
+        const int f = tid / P::LANES, b = tid % P::LANES;
+        const int jc = f / 3, m = f % 3, u = u0 + jc;
+        if (u < N && b < P::R1) {
+            const float2 wa = (m == 0) ? make_float2(1.f, 0.f) : (m == 1 ? w3 : cconj(w3));   // w3^m
+            const float2 wb = (m == 0) ? make_float2(1.f, 0.f) : (m == 1 ? cconj(w3) : w3);   // w3^(2m)
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) {
+                const int k = b + P::R1 * i;
+                const float2 a0 = G1[(jc * 3 + 0) * S::GP + k];
+                const float2 a1 = G1[(jc * 3 + 1) * S::GP + k];
+                const float2 a2 = G1[(jc * 3 + 2) * S::GP + k];
+                const float2 s = cadd(a0, cadd(cmul(a1, wa), cmul(a2, wb)));
+                const float2 h = ld_ro(p.H + (static_cast<size_t>(m) * N + u) * N + k);
+                G2[f * S::GP + k] = p.conj_h ? cmulc(s, h) : cmul(s, h);
+            }
+        }
+    });
+    ex.phase([&](int tid) {
+        // thread (jc, l', b): out_l'[k] = scale * sum_m conj(w3)^(m*l') W_m[k]; then IFFT along v
+        const int f = tid / P::LANES, b = tid % P::LANES;
+        const int jc = f / 3, l = f % 3, u = u0 + jc;
+        if (u < N && b < P::R1) {
+            const float2 wa = (l == 0) ? make_float2(1.f, 0.f) : (l == 1 ? cconj(w3) : w3);
+            const float2 wb = (l == 0) ? make_float2(1.f, 0.f) : (l == 1 ? w3 : cconj(w3));
+            float2 v[P::R2];
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) {
+                const int k = b + P::R1 * i;
+                const float2 a0 = G2[(jc * 3 + 0) * S::GP + k];
+                const float2 a1 = G2[(jc * 3 + 1) * S::GP + k];
+                const float2 a2 = G2[(jc * 3 + 2) * S::GP + k];
+                v[i] = cscale(cadd(a0, cadd(cmul(a1, wa), cmul(a2, wb))), p.scale);
+            }
+            P::stepC(v, b, E + f * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int f = tid / P::LANES, a = tid % P::LANES;
+        const int jc = f / 3, l = f % 3, u = u0 + jc;
+        if (u < N && a < P::R2) {
+            float2 v[P::R1];
+            P::stepD(v, a, E + f * P::E_SIZE);
+            float2* dst = p.st + (static_cast<size_t>(l) * N + u) * N;
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = v[i];
+        }
+    });
+}
+
+// P3  crows_inv : transposed spectrum (already inverse-transformed along v) -> complex rows,
+//      with an epilogue functor.  grid (N/ROWS, 3), block ROWS*LANES.
+struct CRowsInvParams {
+    const float2* st;   // [3][N][N] transposed
+    const float2* tw;
+};
+
+// forward epilogue: save the field, emit intensity and a per-CTA partial sum (Optics.py:109-110)
+struct IntensityEpilogue {
+    float2* U;          // [3][N][N]
+    float* I;           // [3][N][N]
+    float* partial;     // [3][N/ROWS]
+    int N;
+    B200_HD float operator()(int l, int y, int x, float2 v) const {
+        const size_t i = (static_cast<size_t>(l) * N + y) * N + x;
+        U[i] = v;
+        const float in = v.x * v.x + v.y * v.y;
+        I[i] = in;
+        return in;
+    }
+    B200_HD void finish(int l, int tile, int tiles, float s) const { partial[l * tiles + tile] = s; }
+};
+
+// backward epilogue: dL/dh contribution of one wavelength: kappa_l * Im(GV * conj(V)), V recomputed
+struct HeightGradEpilogue {
+    PupilLoad pupil;
+    float* gh3;         // [3][N][N]
+    int N;
+    B200_HD float operator()(int l, int y, int x, float2 gv) const {
+        const float2 v = pupil(l, y, x);
+        const float2 t = cmulc(gv, v);
+        gh3[(static_cast<size_t>(l) * N + y) * N + x] = pupil.kappa[l] * t.y;
+        return 0.f;
+    }
+    B200_HD void finish(int, int, int, float) const {}
+};
+
+template <int N, class Epi, class Exec>
+B200_HD void crows_inv_body(Exec& ex, const CRowsInvParams& p, const Epi& epi, float2* smem) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = CRowsSmem<N>;
+    const int tile = ex.bx(), l = ex.by();
+    const int y0 = tile * T::ROWS;
+    float2* E = smem + S::E_OFF;
+    float2* F = smem + S::F_OFF;
+    float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
+    ex.phase([&](int tid) {
+        for (int w = tid; w < T::ROWS * N; w += S::THREADS) {
+            const int u = w / T::ROWS, j = w % T::ROWS;
+            F[j * T::FP_ROW + u] = ld_ro(p.st + (static_cast<size_t>(l) * N + u) * N + y0 + j);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int j = tid / P::LANES, b = tid % P::LANES;
+        if (b < P::R1) {
+            float2 v[P::R2];
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) v[i] = F[j * T::FP_ROW + b + P::R1 * i];
+            P::stepC(v, b, E + j * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int j = tid / P::LANES, a = tid % P::LANES;
+        float s = 0.f;
+        if (a < P::R2) {
+            float2 v[P::R1];
+            P::stepD(v, a, E + j * P::E_SIZE);
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) s += epi(l, y0 + j, P::R2 * i + a, v[i]);
+        }
+        red[tid] = s;
+    });
+    ex.phase([&](int tid) {
+        if (tid == 0) {
+            float s = 0.f;
+            for (int t = 0; t < S::THREADS; ++t) s += red[t];
+            epi.finish(l, tile, N / T::ROWS, s);
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// small element-wise / reduction bodies of the PSF chain.  Device scalars `scal`:
+//   [0] S = sum |U|^2   [1] loss_rad   [2] centering_loss   [3] dot = sum(gtot * psf)
+// ---------------------------------------------------------------------------------------------
+constexpr int EW_THREADS = 256;
+
+struct ReduceParams {
+    const float* partial;  // [count]
+    float* scal;
+    int count;
+    int mode;              // 0: scal[0] = sum ; 1: PSF losses from 3 interleaved partial sets ; 2: scal[3] = sum
+    int N;
+};
+
+// single CTA, deterministic tree (fixed thread->element map, fixed tree)
+template <class Exec>
+B200_HD void reduce_body(Exec& ex, const ReduceParams& p, float* red) {
+    const int nsets = (p.mode == 1) ? 3 : 1;
+    ex.phase([&](int tid) {
+        for (int s = 0; s < nsets; ++s) {
+            float acc = 0.f;
+            for (int i = tid; i < p.count; i += EW_THREADS) acc += p.partial[s * p.count + i];
+            red[s * EW_THREADS + tid] = acc;
+        }
+    });
+    for (int half = EW_THREADS / 2; half > 0; half /= 2) {
+        ex.phase([&](int tid) {
+            if (tid < half)
+                for (int s = 0; s < nsets; ++s) red[s * EW_THREADS + tid] += red[s * EW_THREADS + tid + half];
+        });
+    }
+    ex.phase([&](int tid) {
+        if (tid == 0) {
+            if (p.mode == 0) p.scal[0] = red[0];
+            else if (p.mode == 2) p.scal[3] = red[0];
+            else {
+                p.scal[1] = sqrtf(red[0]);                                                     // Optics.py:113
+                p.scal[2] = red[EW_THREADS] / (3.0f * p.N * p.N) + red[2 * EW_THREADS] / (3.0f * p.N * p.N);  // :124-125
+            }
+        }
+    });
+}
+
+// P4  psf_finalise: psf = I/S (Optics.py:110); partial sums for loss_rad (:113) and the centering loss (:124-125)
+struct PsfFinaliseParams {
+    const float* I;        // [3][N][N]
+    const float* rho;      // [N][N]
+    const float* scal;
+    float* psf;            // [3][N][N]
+    float* partial;        // [3 sets][grid]
+    int N;
+};
+
+template <class Exec>
+B200_HD void psf_finalise_body(Exec& ex, const PsfFinaliseParams& p, int grid_x, float* red) {
+    const int N = p.N, NN = N * N, total = 3 * NN;
+    ex.phase([&](int tid) {
+        const float S = p.scal[0];
+        float r2 = 0.f, cy = 0.f, cx = 0.f;
+        const int stride = grid_x * EW_THREADS;
+        for (int idx = ex.bx() * EW_THREADS + tid; idx < total; idx += stride) {
+            const int l = idx / NN, y = (idx % NN) / N, x = idx % N;
+            const float v = p.I[idx] / S;
+            const float vy = p.I[l * NN + ((y + N / 2) & (N - 1)) * N + x] / S;
+            const float vx = p.I[l * NN + y * N + ((x + N / 2) & (N - 1))] / S;
+            p.psf[idx] = v;
+            const float r = p.rho[y * N + x] * v;
+            r2 += r * r;
+            cy += (v - vy) * (v - vy);
+            cx += (v - vx) * (v - vx);
+        }
+        red[tid] = r2; red[EW_THREADS + tid] = cy; red[2 * EW_THREADS + tid] = cx;
+    });
+    for (int half = EW_THREADS / 2; half > 0; half /= 2) {
+        ex.phase([&](int tid) {
+            if (tid < half)
+                for (int s = 0; s < 3; ++s) red[s * EW_THREADS + tid] += red[s * EW_THREADS + tid + half];
+        });
+    }
+    ex.phase([&](int tid) {
+        if (tid < 3) p.partial[tid * grid_x + ex.bx()] = red[tid * EW_THREADS];
+    });
+}
+
+// Q1  psf_grad_prepare: gtot = gpsf + g_rad * d loss_rad/dpsf + g_cen * d centering/dpsf ; partial sum(gtot*psf)
+struct PsfGradPrepParams {
+    const float* gpsf;     // nullable [3][N][N]
+    const float* gscal;    // nullable device [2]: upstream grads of (loss_rad, centering_loss)
+    const float* psf;      // [3][N][N]
+    const float* rho;
+    const float* scal;
+    float* gtot;           // [3][N][N]
+    float* partial;        // [grid]
+    int N;
+};
+
+template <class Exec>
+B200_HD void psf_grad_prepare_body(Exec& ex, const PsfGradPrepParams& p, int grid_x, float* red) {
+    const int N = p.N, NN = N * N, total = 3 * NN;
+    ex.phase([&](int tid) {
+        const float g_rad = p.gscal != nullptr ? p.gscal[0] : 0.f;
+        const float g_cen = p.gscal != nullptr ? p.gscal[1] : 0.f;
+        const float loss_rad = p.scal[1];
+        const float kc = g_cen * 4.0f / static_cast<float>(total);
+        float dot = 0.f;
+        const int stride = grid_x * EW_THREADS;
+        for (int idx = ex.bx() * EW_THREADS + tid; idx < total; idx += stride) {
+            const int l = idx / NN, y = (idx % NN) / N, x = idx % N;
+            const float v = p.psf[idx];
+            float g = p.gpsf != nullptr ? p.gpsf[idx] : 0.f;
+            if (g_rad != 0.f) g += g_rad * p.rho[y * N + x] * v / loss_rad;
+            if (g_cen != 0.f) {
+                const float vy = p.psf[l * NN + ((y + N / 2) & (N - 1)) * N + x];
+                const float vx = p.psf[l * NN + y * N + ((x + N / 2) & (N - 1))];
+                g += kc * ((v - vy) + (v - vx));
+            }
+            p.gtot[idx] = g;
+            dot += g * v;
+        }
+        red[tid] = dot;
+    });
+    for (int half = EW_THREADS / 2; half > 0; half /= 2) {
+        ex.phase([&](int tid) {
+            if (tid < half) red[tid] += red[tid + half];
+        });
+    }
+    ex.phase([&](int tid) {
+        if (tid == 0) p.partial[ex.bx()] = red[0];
+    });
+}
+
+// Q5  sum3: gh = gh3[0] + gh3[1] + gh3[2]   (sum over wavelengths of Optics.py:89-90's adjoint)
+struct Sum3Params {
+    const float* gh3;
+    float* gh;
+    int NN;
+};
+template <class Exec>
+B200_HD void sum3_body(Exec& ex, const Sum3Params& p, int grid_x) {
+    ex.phase([&](int tid) {
+        const int stride = grid_x * EW_THREADS;
+        for (int i = ex.bx() * EW_THREADS + tid; i < p.NN; i += stride)
+            p.gh[i] = (p.gh3[i] + p.gh3[p.NN + i]) + p.gh3[2 * p.NN + i];
+    });
+}
+
+}  // namespace b200cam

@@ -1,0 +1,162 @@
+"""torch.autograd glue between the nn.Module boundary and the C ABI.
+
+Two differentiable ops, both thin ctypes calls into ``libb200cam.so`` on the current CUDA stream:
+
+* ``psf_synth(h, plan)        -> psf (1,3,N,N), losses (2,) = (loss_rad, centering_loss)``
+  (``Face-DeId/Camera/Optics.py:89-120,124-125``)
+* ``sensor_conv(img, psf, plan) -> sensor (B,3,N,N)``
+  (``Optics.py:126-128`` + ``Face-DeId/Camera/Utils.py:7-12``)
+
+PyTorch owns every buffer (outputs, saved tensors, scratch); the library only enqueues kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from . import constants as K
+
+
+class DevicePlan:
+    """Per-(device, N) constant tables and scratch buffers for the kernels."""
+
+    def __init__(self, N: int, device: torch.device, tables=None):
+        if device.type != "cuda":
+            raise RuntimeError("b200cam runs on CUDA (sm_100a) only; there is no CPU path "
+                               f"(got device={device})")
+        self.N = N
+        self.device = device
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self.lib = _lib.load_library()
+        if not self.lib.b200cam_supported(N):
+            raise ValueError(f"b200cam supports N in (64,128,256,512,1024), got {N}")
+        _lib.ensure_init(N, self.index)
+        t = tables if tables is not None else K.build(N)
+        self.A = torch.view_as_real(t.table_A).contiguous().to(device)
+        self.Ht = torch.view_as_real(t.table_Ht).contiguous().to(device)
+        self.rho = t.rho.to(torch.float32).contiguous().to(device)
+        self.kappa = (ctypes.c_float * 3)(*t.kappa)
+        self.kappa_list = list(t.kappa)
+        self._psf_ws = torch.empty(self.lib.b200cam_psf_workspace_bytes(N), dtype=torch.uint8, device=device)
+        self._sensor_ws: dict[int, torch.Tensor] = {}
+        self.otf_floats = self.lib.b200cam_otf_bytes(N) // 4
+        self.process_group = None      # set by Camera.data_parallel(): all-reduce dL/dh over ranks
+        self.average_grads = True
+
+    def psf_workspace(self) -> torch.Tensor:
+        return self._psf_ws
+
+    def sensor_workspace(self, B: int) -> torch.Tensor:
+        ws = self._sensor_ws.get(B)
+        if ws is None:
+            nbytes = self.lib.b200cam_sensor_workspace_bytes(self.N, B, 1)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._sensor_ws = {B: ws}          # keep one: batch size rarely changes
+        return ws
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _as_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    if t.device != device:
+        raise RuntimeError(f"b200cam: tensor on {t.device}, camera tables on {device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"b200cam computes in fp32, got {t.dtype}")
+    return t.contiguous()
+
+
+class PsfSynth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h: torch.Tensor, plan: DevicePlan):
+        N = plan.N
+        hc = _as_f32(h.detach(), plan.device).reshape(N, N)
+        psf = torch.empty(1, 3, N, N, dtype=torch.float32, device=plan.device)
+        field = torch.empty(3, N, N, 2, dtype=torch.float32, device=plan.device)
+        stats = torch.empty(4, dtype=torch.float32, device=plan.device)
+        ws = plan.psf_workspace()
+        with torch.cuda.device(plan.index):
+            _lib.check(plan.lib.b200cam_psf_fwd(
+                _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho), plan.kappa,
+                _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), N, _stream()))
+        ctx.plan = plan
+        ctx.h_shape = h.shape
+        ctx.save_for_backward(hc, psf, field, stats)
+        return psf, stats[1:3].clone()          # losses = (loss_rad, centering_loss)
+
+    @staticmethod
+    def backward(ctx, g_psf, g_losses):
+        plan: DevicePlan = ctx.plan
+        N = plan.N
+        hc, psf, field, stats = ctx.saved_tensors
+        gp = _as_f32(g_psf, plan.device).reshape(3, N, N) if g_psf is not None else None
+        gs = _as_f32(g_losses, plan.device) if g_losses is not None else None
+        grad_h = torch.empty(N, N, dtype=torch.float32, device=plan.device)
+        ws = plan.psf_workspace()
+        with torch.cuda.device(plan.index):
+            _lib.check(plan.lib.b200cam_psf_bwd(
+                _lib.ptr(gp), _lib.ptr(gs), _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho),
+                plan.kappa, _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(grad_h),
+                _lib.ptr(ws), ws.numel(), N, _stream()))
+        if plan.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(grad_h, op=dist.ReduceOp.SUM, group=plan.process_group)
+            if plan.average_grads:
+                grad_h /= dist.get_world_size(plan.process_group)
+        return grad_h.reshape(ctx.h_shape), None
+
+
+class SensorConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan):
+        N = plan.N
+        if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] != N or img.shape[3] != N:
+            raise ValueError(f"expected img of shape (B,3,{N},{N}), got {tuple(img.shape)}")
+        x = _as_f32(img.detach(), plan.device)
+        p = _as_f32(psf.detach(), plan.device).reshape(3, N, N)
+        B = x.shape[0]
+        sensor = torch.empty_like(x)
+        img_max = torch.empty(B, dtype=torch.float32, device=plan.device)
+        tie_count = torch.empty(B, dtype=torch.int32, device=plan.device)
+        tie_pos = torch.empty(B, 8, dtype=torch.int32, device=plan.device)
+        otf = torch.empty(plan.otf_floats, dtype=torch.float32, device=plan.device)
+        if B > 0:
+            ws = plan.sensor_workspace(B)
+            with torch.cuda.device(plan.index):
+                _lib.check(plan.lib.b200cam_sensor_fwd(
+                    _lib.ptr(x), _lib.ptr(p), _lib.ptr(sensor), _lib.ptr(img_max), _lib.ptr(tie_count),
+                    _lib.ptr(tie_pos), _lib.ptr(otf), _lib.ptr(ws), ws.numel(), B, N, _stream()))
+        ctx.plan = plan
+        ctx.psf_shape = psf.shape
+        ctx.save_for_backward(x, p, sensor, img_max, tie_count, tie_pos, otf)
+        return sensor
+
+    @staticmethod
+    def backward(ctx, g):
+        plan: DevicePlan = ctx.plan
+        N = plan.N
+        x, p, sensor, img_max, tie_count, tie_pos, otf = ctx.saved_tensors
+        B = x.shape[0]
+        want_img = ctx.needs_input_grad[0]
+        grad_psf = torch.zeros(3, N, N, dtype=torch.float32, device=plan.device)
+        grad_img = torch.empty_like(x) if want_img else None
+        if B > 0:
+            gc = _as_f32(g, plan.device)
+            ws = plan.sensor_workspace(B)
+            with torch.cuda.device(plan.index):
+                _lib.check(plan.lib.b200cam_sensor_bwd(
+                    _lib.ptr(gc), _lib.ptr(x), _lib.ptr(sensor), _lib.ptr(img_max), _lib.ptr(tie_count),
+                    _lib.ptr(tie_pos), _lib.ptr(p), _lib.ptr(otf), _lib.ptr(grad_psf), _lib.ptr(grad_img),
+                    _lib.ptr(ws), ws.numel(), B, N, _stream()))
+        return grad_img, grad_psf.reshape(ctx.psf_shape), None
+
+
+def psf_synth(h: torch.Tensor, plan: DevicePlan):
+    return PsfSynth.apply(h, plan)
+
+
+def sensor_conv(img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan) -> torch.Tensor:
+    return SensorConv.apply(img, psf, plan)

@@ -1,0 +1,121 @@
+"""``Camera`` - drop-in for the reference Face-DeId optical encoder (``Face-DeId/Camera/Optics.py:9``).
+
+Same constructor, parameters / ``state_dict`` keys (``Zer_no_train``, ``Zer_train``, ``ca``),
+public attributes and methods; ``forward`` / ``get_psf`` run in the b200cam CUDA kernels.
+
+Differences a caller can observe (all documented in DESIGN.md):
+* forward needs a CUDA device - there is no CPU path;
+* the constant tensors (``XY``, ``FF``, ``rho`` ...) are built once; the kernel tables follow the
+  input's device lazily, so ``Camera(...).cuda()`` works even though the reference keeps such
+  tensors on the constructor device;
+* optional ``data_parallel(group)`` all-reduces dL/dh across ranks inside backward.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import constants as K
+from . import functional as F
+from .zernike import zernike_volume as _zernike_volume
+
+
+def get_zernike_volume(resolution, n_terms, scale_factor=1e-6, height_tolerance=2e-8):
+    """Noll Zernike stack in metres (reference: ``Face-DeId/Camera/Utils.py:60-63``, via poppy)."""
+    return _zernike_volume(resolution, n_terms, scale_factor)
+
+
+class Camera(nn.Module):
+    def __init__(self, device="cpu", N=256, lamdas=3, zernike_terms=50, height_tolerance=2e-8):
+        super().__init__()
+        if lamdas != 3:
+            raise ValueError("the optical model has three fixed wavelengths (640/550/440 nm)")
+        self.lamdas = lamdas
+        self.device = device
+        self.height_tolerance = height_tolerance
+
+        tables = K.build(N)
+        self._tables = tables
+        for name in ("zi", "z0", "f", "radii", "N", "c", "L_len", "px", "L_sen", "du", "dx2"):
+            setattr(self, name, getattr(tables, name))
+        self.R = tables.R.to(device) if torch.is_tensor(tables.R) else tables.R
+        for name in K.TENSOR_ATTRS:
+            setattr(self, name, getattr(tables, name).to(device))
+        self.z = tables.z                      # the reference keeps this one on the CPU (Optics.py:36)
+
+        # Zernike parameters: same RNG calls, in the same order, as Optics.py:59-70
+        self.zernike_inits = torch.rand((zernike_terms, 1, 1), device=self.device) / 100
+        self.zernike_inits[:3] = 0
+        self.Zer_no_train = nn.Parameter(self.zernike_inits[:3, ...], requires_grad=False)
+        self.Zer_train = nn.Parameter(self.zernike_inits[3:, ...], requires_grad=True)
+        self.zernike_volume = torch.tensor(get_zernike_volume(resolution=self.N, n_terms=zernike_terms),
+                                           dtype=torch.float32, device=self.device)
+        size = (1, 1, 32, 32)
+        self.ca = torch.where(torch.rand(size=size) > 0.5, torch.ones(size), torch.zeros(size))
+        self.ca = nn.Parameter(self.ca, requires_grad=False)
+
+        self.loss_psf = 0.0
+        self.loss_rad = 0.0
+        self.psfs = None
+        self.centering_loss = None
+        self.psf_rad = None
+
+        self._plans: dict[torch.device, F.DevicePlan] = {}
+        self._pending_centering = None
+        self._process_group = None
+        self._average_grads = True
+
+    # ------------------------------------------------------------------ kernels' per-device state
+    def _plan(self, device: torch.device) -> F.DevicePlan:
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        plan = self._plans.get(device)
+        if plan is None:
+            plan = F.DevicePlan(self.N, device, self._tables)
+            plan.process_group = self._process_group
+            plan.average_grads = self._average_grads
+            self._plans[device] = plan
+        return plan
+
+    def data_parallel(self, process_group=None, average: bool = True, enabled: bool = True):
+        """All-reduce dL/dh (N*N floats) over ``process_group`` inside backward (one rank per GPU)."""
+        import torch.distributed as dist
+        self._process_group = (process_group or dist.group.WORLD) if enabled else None
+        self._average_grads = average
+        for plan in self._plans.values():
+            plan.process_group = self._process_group
+            plan.average_grads = average
+        return self
+
+    # ------------------------------------------------------------------ reference API
+    def get_Heith_Map(self):
+        zernike_coeffs_concat = torch.cat((self.Zer_no_train, self.Zer_train), 0)
+        volume = self.zernike_volume
+        if volume.device != zernike_coeffs_concat.device:
+            volume = self.zernike_volume = volume.to(zernike_coeffs_concat.device)
+        height_map = torch.sum(zernike_coeffs_concat * volume, dim=0)
+        return height_map.unsqueeze(0)
+
+    def load_ckpt(self):
+        ckpt = torch.load('./Camera/Cam_focus.pth', map_location=self.device)
+        self.load_state_dict(ckpt['camera'])
+
+    def get_phase_shift(self):
+        h = self.get_Heith_Map()
+        return self.k.to(h.device) * self.flmb.to(h.device) * h
+
+    def get_psf(self):
+        h = self.get_Heith_Map()
+        plan = self._plan(h.device)
+        psf, losses = F.psf_synth(h, plan)
+        self.psfs = psf
+        self.loss_rad = losses[0]
+        self._pending_centering = losses[1]
+        return self.psfs
+
+    def forward(self, img):
+        psf = self.get_psf()
+        self.centering_loss = self._pending_centering
+        return F.sensor_conv(img, psf, self._plan(psf.device))

@@ -1,0 +1,223 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the nn.Module / C ABI, against
+(1) the committed golden vectors of the unmodified reference and (2) the CPU oracle on seeded inputs.
+
+Tolerances are BASELINE.json's: rel-L2 <= 1e-4 on sensor images (and the PSF), <= 1e-3 on dL/dh.
+"""
+import ctypes
+
+import pytest
+import torch
+
+import b200cam.synthetic as synth
+from b200cam import _lib
+from b200cam.optics import Camera
+from conftest import GOLDEN_CASES, load_golden, rel_l2
+from oracle import camera_oracle as co
+
+pytestmark = pytest.mark.gpu
+TOL_SENSOR, TOL_GRAD = 1e-4, 1e-3
+
+
+def make_camera(N, h_cpu, terms=6):
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    cam = Camera(device=dev, N=N, zernike_terms=terms)
+    h = h_cpu.to(dev).requires_grad_(True)
+    cam.get_Heith_Map = lambda: h
+    return cam, h
+
+
+def oracle_step(img, w, h_cpu, N, g_rad=1.0, g_cen=1.0):
+    C = co.build_constants(N)
+    h = h_cpu.clone().requires_grad_(True)
+    out = co.camera_forward(img, h, C)
+    ((out["sensor"] * w).sum() + g_rad * out["loss_rad"] + g_cen * out["centering_loss"]).backward()
+    return out, h.grad
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_matches_reference_golden_vectors(name):
+    gold = load_golden(name)
+    N = gold["N"]
+    cam, h = make_camera(N, gold["h"])
+    y = cam(gold["img"].cuda())
+    ((y * gold["w"].cuda()).sum() + cam.loss_rad + cam.centering_loss).backward()
+    assert rel_l2(y, gold["sensor"]) <= TOL_SENSOR
+    assert rel_l2(cam.psfs, gold["psf"]) <= TOL_SENSOR
+    assert rel_l2(h.grad, gold["grad_h"]) <= TOL_GRAD
+    assert abs(cam.loss_rad.item() - gold["loss_rad"].item()) <= 1e-4 * gold["loss_rad"].item()
+    assert abs(cam.centering_loss.item() - gold["centering_loss"].item()) <= 1e-3 * gold["centering_loss"].item()
+    assert y.shape == gold["sensor"].shape and cam.psfs.shape == (1, 3, N, N)
+
+
+def test_config1_forward_batch8():
+    """BASELINE config 1: forward only, random height map, batch 8 of 256x256 RGB."""
+    N, B = 256, 8
+    h_cpu, img = synth.height_map(N, 99), synth.images(B, N, 100)
+    cam, _ = make_camera(N, h_cpu)
+    with torch.no_grad():
+        y = cam(img.cuda())
+    C = co.build_constants(N)
+    out = co.camera_forward(img, h_cpu, C)
+    assert rel_l2(y, out["sensor"]) <= TOL_SENSOR
+    assert torch.allclose(y.amax((1, 2, 3)).cpu(), torch.ones(B))       # Optics.py:128 property
+
+
+def test_config2_forward_backward_batch64():
+    """BASELINE config 2: forward+backward into the height map, batch 64 of 256x256 RGB."""
+    N, B = 256, 64
+    h_cpu, img, w = synth.height_map(N), synth.images(B, N), synth.upstream_grad(B, N)
+    out, gh = oracle_step(img, w, h_cpu, N)
+    assert synth.top2_relative_gap(out["conv"]).min() >= 1e-5           # amax margin (trap T2)
+    cam, h = make_camera(N, h_cpu)
+    y = cam(img.cuda())
+    ((y * w.cuda()).sum() + cam.loss_rad + cam.centering_loss).backward()
+    assert rel_l2(y, out["sensor"]) <= TOL_SENSOR
+    assert rel_l2(h.grad, gh) <= TOL_GRAD
+
+
+@pytest.mark.parametrize("N,B", [(64, 3), (128, 5), (512, 2), (1024, 1)])
+def test_other_resolutions(N, B):
+    h_cpu, img, w = synth.height_map(N, 5), synth.images(B, N, 6), synth.upstream_grad(B, N, 7)
+    out, gh = oracle_step(img, w, h_cpu, N, 0.5, 2.0)
+    cam, h = make_camera(N, h_cpu)
+    y = cam(img.cuda())
+    ((y * w.cuda()).sum() + 0.5 * cam.loss_rad + 2.0 * cam.centering_loss).backward()
+    assert rel_l2(y, out["sensor"]) <= TOL_SENSOR
+    assert rel_l2(cam.psfs, out["psf"]) <= TOL_SENSOR
+    assert rel_l2(h.grad, gh) <= TOL_GRAD
+
+
+def test_zernike_parameter_gradient():
+    """End to end through the module's own parameters (Zer_train), default-init lens, T=40."""
+    N, B = 256, 4
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(1)
+    cam = Camera(device=dev, N=N, zernike_terms=40)
+    img, w = synth.images(B, N, 21), synth.upstream_grad(B, N, 22)
+    y = cam(img.cuda())
+    ((y * w.cuda()).sum() + cam.loss_rad + cam.centering_loss).backward()
+    C = co.build_constants(N)
+    zt = cam.Zer_train.detach().cpu().clone().requires_grad_(True)
+    h = co.height_map(cam.Zer_no_train.detach().cpu(), zt, cam.zernike_volume.cpu())
+    out = co.camera_forward(img, h, C)
+    ((out["sensor"] * w).sum() + out["loss_rad"] + out["centering_loss"]).backward()
+    assert rel_l2(y, out["sensor"]) <= TOL_SENSOR
+    assert rel_l2(cam.Zer_train.grad, zt.grad) <= TOL_GRAD
+    assert cam.Zer_no_train.grad is None
+
+
+def test_image_gradient_optional_output():
+    N, B = 128, 3
+    h_cpu, w = synth.height_map(N, 5), synth.upstream_grad(B, N, 7)
+    img = synth.images(B, N, 6)
+    C = co.build_constants(N)
+    xo = img.clone().requires_grad_(True)
+    out = co.camera_forward(xo, h_cpu, C)
+    (out["sensor"] * w).sum().backward()
+    cam, _ = make_camera(N, h_cpu)
+    xg = img.cuda().requires_grad_(True)
+    (cam(xg) * w.cuda()).sum().backward()
+    assert rel_l2(xg.grad, xo.grad) <= TOL_GRAD
+
+
+def test_exact_ties_split_like_torch():
+    N = 64
+    img = torch.zeros(1, 3, N, N)
+    img[0, 0, 5, 7] = 1.0
+    img[0, 2, 40, 9] = 1.0
+    psf = torch.zeros(1, 3, N, N)
+    psf[0, :, N // 2, N // 2] = 0.25
+    psf[0, :, N // 2 + 1, N // 2] = 0.0625
+    w = synth.upstream_grad(1, N, 11)
+    from b200cam import functional as F
+    plan = F.DevicePlan(N, torch.device("cuda", 0))
+    p = psf.cuda().requires_grad_(True)
+    y = F.sensor_conv(img.cuda(), p, plan)
+    (y * w.cuda()).sum().backward()
+    n_ties = int((y == 1.0).sum())
+    if n_ties != 2:
+        pytest.skip("fp32 FFT rounding broke the exact tie")
+    gpsf, _ = co.sensor_backward(w.double(), img.double(), psf.double(), N)
+    assert rel_l2(p.grad, gpsf) <= 1e-5
+
+
+def test_size_independent_properties_full_batch():
+    """At the full config-2 size: PSF sums to one, every image peaks at exactly 1, an impulse image
+    reproduces the (shifted) PSF, circular shifts commute with the camera, runs are bit-reproducible."""
+    N, B = 256, 64
+    cam, _ = make_camera(N, synth.height_map(N, 3))
+    img = synth.images(B, N, 4).cuda()
+    with torch.no_grad():
+        y1 = cam(img)
+        psf = cam.psfs.clone()
+        y2 = cam(img)
+        ys = cam(torch.roll(img, (17, -40), (-2, -1)))
+        delta = torch.zeros(1, 3, N, N, device="cuda")
+        delta[0, :, 10, 20] = 1.0
+        yd = cam(delta)
+    assert torch.equal(y1, y2)
+    assert abs(psf.sum().item() - 1.0) <= 1e-5
+    assert torch.equal(y1.amax((1, 2, 3)), torch.ones(B, device="cuda"))
+    assert rel_l2(ys, torch.roll(y1, (17, -40), (-2, -1))) <= 1e-5
+    expect = torch.roll(psf, (10 - N // 2, 20 - N // 2), (-2, -1))
+    assert rel_l2(yd, expect / expect.max()) <= 1e-4
+
+
+def test_backward_is_deterministic():
+    N, B = 256, 16
+    h_cpu, img, w = synth.height_map(N), synth.images(B, N).cuda(), synth.upstream_grad(B, N).cuda()
+    grads = []
+    for _ in range(2):
+        cam, h = make_camera(N, h_cpu)
+        ((cam(img) * w).sum() + cam.loss_rad).backward()
+        grads.append(h.grad.clone())
+    assert torch.equal(grads[0], grads[1])
+
+
+def test_cuda_graph_capture_of_forward_backward():
+    N, B = 256, 8
+    h_cpu, img, w = synth.height_map(N), synth.images(B, N).cuda(), synth.upstream_grad(B, N).cuda()
+    cam, h = make_camera(N, h_cpu)
+    ((cam(img) * w).sum() + cam.loss_rad + cam.centering_loss).backward()      # warm-up, eager
+    eager = h.grad.clone()
+    h.grad = None
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ((cam(img) * w).sum() + cam.loss_rad + cam.centering_loss).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    h.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ((cam(img) * w).sum() + cam.loss_rad + cam.centering_loss).backward()
+    h.grad.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(h.grad, eager)
+
+
+def test_abi_error_codes_on_device():
+    lib = _lib.load_library()
+    N, B = 64, 1
+    _lib.ensure_init(N, 0)
+    t = torch.zeros(B, 3, N, N, device="cuda")
+    small = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    i32 = torch.zeros(8, dtype=torch.int32, device="cuda")
+    otf = torch.zeros(lib.b200cam_otf_bytes(N) // 4, device="cuda")
+    p = _lib.ptr
+    rc = lib.b200cam_sensor_fwd(p(t), p(t), p(t), p(t), p(i32), p(i32), p(otf), p(small), small.numel(), B, N,
+                                ctypes.c_void_p(0))
+    assert rc == -3                                                   # B200CAM_E_WORKSPACE
+    with pytest.raises(TypeError):
+        cam, _ = make_camera(N, synth.height_map(N))
+        cam(t.double())
+    with pytest.raises(ValueError):
+        cam(torch.zeros(1, 3, 32, 32, device="cuda"))
+
+
+def test_empty_batch():
+    N = 64
+    cam, _ = make_camera(N, synth.height_map(N))
+    y = cam(torch.zeros(0, 3, N, N, device="cuda"))
+    assert y.shape == (0, 3, N, N)

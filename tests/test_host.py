@@ -1,0 +1,110 @@
+"""CPU: host-side logic - C ABI exports, constants, Zernike basis, module construction, no-fallback rule."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import b200cam
+from b200cam import _lib, zernike
+import b200cam.constants as K
+from b200cam.optics import Camera
+from oracle import camera_oracle as co
+from oracle import ref_shim
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def library():
+    _lib.build_library()
+    return _lib.load_library()
+
+
+def test_abi_exports_every_declared_symbol(library):
+    header = (REPO / "include" / "b200cam.h").read_text()
+    declared = set(re.findall(r"\b(b200cam_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(library, name) is not None
+
+
+def test_abi_size_queries_without_gpu(library):
+    assert library.b200cam_version() == 100
+    assert [library.b200cam_supported(n) for n in (64, 100, 256, 1024, 2048)] == [1, 0, 1, 1, 0]
+    N = 256
+    assert library.b200cam_otf_bytes(N) == 3 * (N // 2 + 1) * N * 8
+    assert library.b200cam_otf_bytes(100) == 0
+    per_plane = (N // 2 + 1) * N * 8
+    assert library.b200cam_sensor_workspace_bytes(N, 64, 0) >= 2 * 64 * 3 * per_plane
+    assert library.b200cam_psf_workspace_bytes(N) >= 3 * N * N * 8
+    assert b"workspace" in library.b200cam_error_string(-3)
+
+
+def test_abi_rejects_bad_arguments_before_touching_the_gpu(library):
+    null = ctypes.c_void_p(0)
+    kappa = (ctypes.c_float * 3)(1, 2, 3)
+    assert library.b200cam_psf_fwd(null, null, null, null, kappa, null, null, null, null, 0, 100, null) == -1
+    assert library.b200cam_psf_fwd(null, null, null, null, kappa, null, null, null, null, 0, 256, null) == -2
+    assert library.b200cam_sensor_fwd(null, null, null, null, null, null, null, null, 0, 0, 256, null) == -1
+
+
+def test_no_cpu_fallback():
+    cam = Camera(N=64, zernike_terms=6)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cam(torch.rand(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cam.get_psf()
+
+
+def test_product_does_not_import_oracle():
+    for py in (REPO / "privacy-preserving-vision_b200").glob("*.py"):
+        text = py.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, py
+
+
+def test_constants_match_oracle():
+    for N in (64, 256):
+        T, C = K.build(N), co.build_constants(N)
+        A = co.pupil_field(torch.zeros(1, N, N), C)
+        assert (T.table_A - A).abs().max() <= 2e-6
+        assert torch.equal(T.table_Ht, co.transfer_function(C).transpose(-1, -2))
+        assert np.allclose(T.kappa, (C.k * C.flmb).flatten().numpy())
+        assert torch.equal(T.rho, C.rho)
+
+
+def test_noll_indices_and_orthonormality():
+    assert [zernike.noll_to_nm(j) for j in range(1, 12)] == [
+        (0, 0), (1, 1), (1, -1), (2, 0), (2, -2), (2, 2), (3, -1), (3, 1), (3, -3), (3, 3), (4, 0)]
+    Z = zernike.zernike_basis(15, 256, outside=0.0)
+    mask = Z[0] > 0
+    gram = np.einsum("iyx,jyx->ij", Z, Z) / mask.sum()
+    assert np.allclose(gram, np.eye(15), atol=3e-2)        # Noll-normalised: unit variance over the disk
+    assert zernike.zernike_volume(64, 5).max() <= 4e-6
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not mounted")
+def test_module_constructs_like_the_reference():
+    torch.manual_seed(3)
+    ours = Camera(N=64, zernike_terms=10)
+    torch.manual_seed(3)
+    ref = ref_shim.load_face_deid_camera()(N=64, zernike_terms=10)
+    so, sr = ours.state_dict(), ref.state_dict()
+    assert list(so.keys()) == list(sr.keys())
+    assert all(torch.equal(so[k], sr[k]) for k in sr)
+    assert [n for n, p in ours.named_parameters() if p.requires_grad] == ["Zer_train"]
+    for name in ("XY", "FF", "XY2", "rho", "rad", "k", "flmb", "lamb", "u", "x2", "fx1", "r", "r2"):
+        assert torch.equal(getattr(ours, name), getattr(ref, name)), name
+    assert torch.equal(ours.get_Heith_Map(), ref.get_Heith_Map())
+    assert torch.equal(ours.get_phase_shift(), ref.get_phase_shift())
+    ours.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_state_dict_roundtrip(tmp_path):
+    a = Camera(N=64, zernike_terms=8)
+    torch.save({"Camera": a.state_dict()}, tmp_path / "cam.pth")   # solver.py:90 layout
+    b = Camera(N=64, zernike_terms=8)
+    b.load_state_dict(torch.load(tmp_path / "cam.pth")["Camera"])  # solver.py:46-48
+    assert torch.equal(a.Zer_train, b.Zer_train) and torch.equal(a.ca, b.ca)
