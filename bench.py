@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py - encoded images/s, forward+backward, of the optical-encoder camera on B200.
+
+Workload (BASELINE.json configs[1]): Face-DeId Camera forward + backward into the height map,
+batch 64 of synthetic 256x256 RGB images per GPU, loss = sum(sensor*w) + loss_rad + centering_loss.
+A "step" is one such forward+backward over one batch.  Prints ONE JSON line (rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--size N] [--impl reference]
+
+* value      : images/s over all ranks, inputs resident in HBM, CUDA-graph replay of the step,
+               CUDA events, barrier + synchronize on both sides, max over ranks.
+* e2e        : the same step through the public nn.Module API with HOST (pinned) image buffers:
+               H2D copy of every batch and D2H read of loss + dL/dh inside the timed region.
+* roofline   : algorithmic bytes (48*N^2 per image) / measured step time vs the measured
+               HBM copy bandwidth in MEASURED_PEAKS.json; `breakdown_us` times the four C-ABI calls.
+* cpu_baseline: the oracle port (oracle/camera_oracle.py, torch CPU, all host threads) on a bounded
+               sample of the same workload - reported, not the target.
+* --impl reference : times only that CPU implementation (the reference itself is PyTorch code that is
+               not present on the GPU box; the oracle is its bit-exact restatement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+import torch  # noqa: E402
+
+METRIC = "encoded images/s fwd+bwd @1/2/4/8 B200; achieved HBM GB/s vs roofline"   # BASELINE.json: metric
+UNIT = "images/s"
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
+    ap.add_argument("--size", type=int, default=256, help="image side N")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--input-sets", type=int, default=4, help="distinct resident input batches rotated through")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="timed loop only (for ncu): no breakdown / e2e / cpu legs")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: oracle port on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_port_rate(N: int, B: int, budget_s: float, steps: int | None = None, warmup: int = 1):
+    """images/s of the oracle (fwd+bwd into h) with all host threads; bounded by budget_s."""
+    from oracle import camera_oracle as co
+    import b200cam.synthetic as synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    C = co.build_constants(N)
+    img, w = synth.images(B, N), synth.upstream_grad(B, N)
+    h = synth.height_map(N).requires_grad_(True)
+
+    def step():
+        h.grad = None
+        out = co.camera_forward(img, h, C)
+        ((out["sensor"] * w).sum() + out["loss_rad"] + out["centering_loss"]).backward()
+
+    for _ in range(max(1, warmup)):
+        step()
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while (steps is None and time.perf_counter() < t_end and len(times) < 50) or (steps is not None and len(times) < steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if steps is not None and time.perf_counter() > t_end + 120:
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    return B / med, med, len(times), torch.get_num_threads()
+
+
+def workload_config(args, world: int, launch: str) -> dict:
+    N, B, R = args.size, args.batch, max(1, args.input_sets)
+    return {"workload": f"Face-DeId Camera fwd+bwd into height map, batch {B}/GPU of {N}x{N} RGB, random height map",
+            "global_batch": B * world, "size": N, "parallelism": f"dp{world}" if world > 1 else "single",
+            "l2": (f"{R} distinct resident input sets rotated: {R * 2 * B * 3 * N * N * 4 / 1e6:.0f} MB of inputs "
+                   + ("(larger than the 126 MB L2)" if R * 2 * B * 3 * N * N * 4 > 126e6 else "(SMALLER than L2 - not a valid bench size)")),
+            "launch": launch}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, B = args.size, args.batch
+    steps = min(args.steps, 20)
+    rate, med, n, cores = cpu_port_rate(N, B, budget_s=120.0, steps=steps, warmup=min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": min(args.warmup, 2), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, max(1, args.gpus), f"torch {torch.__version__} CPU, {cores} threads, rank 0 only"),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} steps of batch {B} at N={N}, median (reference PyTorch module is not on the GPU box; "
+                                   "oracle/camera_oracle.py is its bit-exact torch restatement)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def hbm_peak():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def run_b200(args) -> None:
+    import torch.distributed as dist
+    import b200cam.synthetic as synth
+    from b200cam import _lib
+    from b200cam.optics import Camera
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the b200 arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N, B, R = args.size, args.batch, max(1, args.input_sets)
+    lib = _lib.load_library()
+
+    torch.manual_seed(0)
+    cam = Camera(device=dev, N=N, zernike_terms=12)
+    h = synth.height_map(N).to(dev).requires_grad_(True)     # "random height map" (configs[0..1])
+    cam.get_Heith_Map = lambda: h
+    if world > 1:
+        cam.data_parallel(average=True)
+    imgs_host = [synth.images(B, N, seed=1000 + 17 * rank + r).pin_memory() for r in range(R)]
+    imgs = [t.to(dev) for t in imgs_host]
+    ws = [synth.upstream_grad(B, N, seed=2000 + 17 * rank + r).to(dev) for r in range(R)]
+
+    one = torch.ones((), device=dev)
+
+    def step(i: int):
+        """forward + backward into h; upstream gradients: w for the sensor image, 1 for the two regularisers
+        (i.e. L = sum(sensor*w) + loss_rad + centering_loss without materialising the product)."""
+        h.grad = None
+        y = cam(imgs[i % R])
+        torch.autograd.backward([y, cam.loss_rad, cam.centering_loss], [ws[i % R], one, one])
+
+    def drop_graph_refs():
+        # the module keeps psfs / loss tensors (like the reference); they pin the previous autograd graph and
+        # its AccumulateGrad stream, which breaks stream capture - release them before capturing
+        cam.psfs = None
+        cam.loss_rad = cam.centering_loss = cam._pending_centering = None
+        h.grad = None
+
+    # eager warm-up (also builds the per-device plan outside any capture) + count our kernel launches per step
+    step(0)
+    torch.cuda.synchronize()
+    c0 = lib.b200cam_launch_count()
+    step(1)
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.b200cam_launch_count() - c0)
+
+    graphs = None
+    drop_graph_refs()
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for r in range(R):
+                    step(r)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graphs = []
+            for r in range(R):
+                g = torch.cuda.CUDAGraph()
+                drop_graph_refs()
+                with torch.cuda.graph(g):
+                    step(r)
+                graphs.append(g)
+        except Exception as exc:   # e.g. NCCL capture unsupported: fall back to eager launches of the same kernels
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
+            graphs = None
+            torch.cuda.synchronize()
+
+    def run_step(i: int):
+        if graphs is not None:
+            graphs[i % R].replay()
+        else:
+            step(i)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        t_spin = time.perf_counter()
+        while time.perf_counter() - t_spin < 1.0:      # nvidia-smi needs ~1 s to start sampling; keep the GPU under load meanwhile
+            run_step(0)
+            torch.cuda.synchronize()
+    for i in range(max(3, args.warmup)):
+        run_step(i)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(i)
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": ms_per_step, "quick": True, "launches_per_step": launches_per_step,
+                              "clocks": clocks}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- per-call breakdown (each C-ABI call timed alone over the same rotating inputs) -----------------
+    from b200cam import functional as F
+    plan = cam._plan(dev)
+    breakdown = {}
+
+    def time_call(name, fn, reps=20):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        breakdown[name] = a.elapsed_time(b) / reps * 1e3
+
+    with torch.no_grad():
+        hd = h.detach()
+        time_call("psf_fwd", lambda i: F.PsfSynth.apply(hd, plan))
+        psf = F.PsfSynth.apply(hd, plan)[0]
+        time_call("sensor_fwd", lambda i: F.SensorConv.apply(imgs[i % R], psf, plan))
+    p_req = psf.clone().requires_grad_(True)
+    ys = [F.sensor_conv(imgs[r], p_req, plan) for r in range(R)]
+    time_call("sensor_bwd", lambda i: torch.autograd.grad(ys[i % R], p_req, ws[i % R], retain_graph=True))
+    hr = h.detach().clone().requires_grad_(True)
+    pp, ll = F.psf_synth(hr, plan)
+    gp = torch.rand_like(pp)
+    time_call("psf_bwd", lambda i: torch.autograd.grad(pp, hr, gp, retain_graph=True))
+
+    # ---- end to end through the module API with host image buffers ------------------------------------
+    copy_stream = torch.cuda.Stream()
+    dev_bufs = [torch.empty_like(imgs[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    gh_host = torch.empty(1, N, N).pin_memory()
+    loss_host = torch.empty(1).pin_memory()
+    e2e_steps = max(10, min(args.steps, 50))
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream()
+        for i in range(n + 1):
+            if i < n:                                     # prefetch batch i
+                s = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[s])
+                    dev_bufs[s].copy_(imgs_host[i % R], non_blocking=True)
+                    ready[s].record(copy_stream)
+            if i >= 1:                                    # compute batch i-1
+                s = (i - 1) % 2
+                cur.wait_event(ready[s])
+                h.grad = None
+                y = cam(dev_bufs[s])
+                torch.autograd.backward([y, cam.loss_rad, cam.centering_loss], [ws[(i - 1) % R], one, one])
+                freed[s].record(cur)
+                gh_host.copy_(h.grad, non_blocking=True)
+                loss_host.copy_((cam.loss_rad + cam.centering_loss).detach().reshape(1), non_blocking=True)
+
+    for s in range(2):
+        freed[s].record(torch.cuda.current_stream())
+    e2e_loop(3)
+    sync_all()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_loop(e2e_steps)
+    t1.record()
+    sync_all()
+    ems = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(ems.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = hbm_peak()
+    bytes_per_image = 48 * N * N
+    achieved = B * bytes_per_image / (ms_per_step * 1e-3) / 1e9          # per GPU
+    traffic = None
+    tpath = REPO / "profiles" / "traffic.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text()).get(f"N{N}_B{B}")
+        except Exception:
+            traffic = None
+    cpu = None
+    if world == 1:
+        rate, med, n, cores = cpu_port_rate(N, B, args.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} fwd+bwd steps of batch {B} at N={N} (median), oracle/camera_oracle.py on torch CPU"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world, "cuda-graph replay" if graphs is not None else "eager"),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * N * N * 4, "d2h_bytes_per_step": N * N * 4 + 4,
+                "steps": e2e_steps, "note": "nn.Module API, pinned host images, double-buffered H2D, loss + dL/dh read back"},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "scope": "whole step: every kernel of fwd+bwd (algorithmic bytes 48*N^2 per image, SURVEY 8d)",
+                     "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()}},
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,8 @@ extern "C" {
 int b200cam_version(void);
 const char* b200cam_error_string(int code);
 int b200cam_supported(int N);
+/* number of kernels this library has enqueued so far in this process (bench.py's gpu_launches) */
+unsigned long long b200cam_launch_count(void);
 
 /* Build the per-device twiddle table for N and opt the kernels into large dynamic shared
  * memory.  Allocates (once per device and N) - call outside stream capture. */

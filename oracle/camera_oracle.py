@@ -205,7 +205,8 @@ def height_map(zer_no_train: torch.Tensor, zer_train: torch.Tensor, zernike_volu
 # ----------------------------------------------------------------------------
 
 
-def sensor_backward(g: torch.Tensor, img: torch.Tensor, psf: torch.Tensor, N: int, want_img_grad: bool = False):
+def sensor_backward(g: torch.Tensor, img: torch.Tensor, psf: torch.Tensor, N: int, want_img_grad: bool = False,
+                    tie_mask: torch.Tensor | None = None):
     """Adjoint of ``sensor_from_psf`` w.r.t. psf (and optionally img).
 
     y = conv/m, m = amax(conv) per image.  dL/dconv = (g - s*tie/n)/m with s = sum(g*y) and
@@ -220,7 +221,7 @@ def sensor_backward(g: torch.Tensor, img: torch.Tensor, psf: torch.Tensor, N: in
     m = conv.amax((1, 2, 3), keepdim=True)
     y = conv / m
     s = (g * y).sum((1, 2, 3), keepdim=True)
-    tie = (conv == m).to(g.dtype)
+    tie = (conv == m).to(g.dtype) if tie_mask is None else tie_mask.to(g.dtype)   # override: test hook
     n = tie.sum((1, 2, 3), keepdim=True)
     gconv = (g - s * tie / n) / m
     G = torch.fft.rfftn(gconv, dim=(-2, -1))

@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <mutex>
 
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_accum(ColsAccumPa
     cols_accum_body<N>(ex, p, SMEM2, &st);
 }
 template <int N>
-__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_reduce_inv(ColsReduceInvParams p) {
+__global__ void __launch_bounds__(Tile<N>::RCOLS * Plan<N>::LANES) k_cols_reduce_inv(ColsReduceInvParams p) {
     DeviceExec ex;
     cols_reduce_inv_body<N>(ex, p, SMEM2);
 }
@@ -56,8 +57,11 @@ __global__ void __launch_bounds__(EW_THREADS) k_tie_coef(TieTermParams p) {
     tie_coef_body(ex, p, gridDim.x);
 }
 __global__ void __launch_bounds__(EW_THREADS) k_tie_term(TieTermParams p) {
+    __shared__ float s_coef[TIE_PASS * MAX_TIES];
+    __shared__ int s_meta[3 * TIE_PASS * MAX_TIES];
+    __shared__ int s_cnt[TIE_PASS + 1];
     DeviceExec ex;
-    tie_term_body(ex, p, gridDim.x);
+    tie_term_body(ex, p, gridDim.x, s_coef, s_meta, s_cnt);
 }
 __global__ void __launch_bounds__(EW_THREADS) k_tie_term_img(TieTermImgParams p) {
     DeviceExec ex;
@@ -209,7 +213,12 @@ struct SensorWs {
         cudaError_t e_ = (expr);                   \
         if (e_ != cudaSuccess) return static_cast<int>(e_); \
     } while (0)
-#define LAUNCH_CHECK() CK(cudaGetLastError())
+static std::atomic<unsigned long long> g_launches{0};
+#define LAUNCH_CHECK()           \
+    do {                         \
+        CK(cudaGetLastError());  \
+        g_launches.fetch_add(1, std::memory_order_relaxed); \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------
 // launch sequences
@@ -222,7 +231,7 @@ static int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     PsfWs ws(ws_ptr, N);
     PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
-    const dim3 rgrid(N / T::ROWS, 3);
+    const dim3 rgrid(N / T::CROWS, 3);
     k_crows_fwd<N, PupilLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsFwdParams{ws.st, tw}, load);
     LAUNCH_CHECK();
     k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(
@@ -231,7 +240,7 @@ static int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const
     IntensityEpilogue epi{field, ws.I, ws.part_rows, N};
     k_crows_inv<N, IntensityEpilogue><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsInvParams{ws.st, tw}, epi);
     LAUNCH_CHECK();
-    k_reduce<<<1, EW_THREADS, 0, s>>>(ReduceParams{ws.part_rows, stats, 3 * (N / T::ROWS), 0, N});
+    k_reduce<<<1, EW_THREADS, 0, s>>>(ReduceParams{ws.part_rows, stats, 3 * (N / T::CROWS), 0, N});
     LAUNCH_CHECK();
     k_psf_finalise<<<EW_GRID, EW_THREADS, 0, s>>>(PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, N});
     LAUNCH_CHECK();
@@ -252,7 +261,7 @@ static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, c
     LAUNCH_CHECK();
     k_reduce<<<1, EW_THREADS, 0, s>>>(ReduceParams{ws.part_ew, stats, EW_GRID, 2, N});
     LAUNCH_CHECK();
-    const dim3 rgrid(N / T::ROWS, 3);
+    const dim3 rgrid(N / T::CROWS, 3);
     GradFieldLoad load{field, ws.gtot, stats, N};
     k_crows_fwd<N, GradFieldLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsFwdParams{ws.st, tw}, load);
     LAUNCH_CHECK();
@@ -330,7 +339,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     k_cols_accum<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
         ColsAccumParams{ws.stx, ws.stg, ws.partial, tw, img_max, B, chunk});
     LAUNCH_CHECK();
-    k_cols_reduce_inv<N><<<colgroups, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+    k_cols_reduce_inv<N><<<(3 * T::NC + T::RCOLS - 1) / T::RCOLS, T::RCOLS * Plan<N>::LANES, ColsSmem<N>::BYTES, s>>>(
         ColsReduceInvParams{ws.partial, ws.stp, tw, (B + chunk - 1) / chunk, 1.0f / (static_cast<float>(N) * N)});
     LAUNCH_CHECK();
     k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
@@ -339,7 +348,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     TieTermParams tp{grad_psf, img, img_max, tie_count, tie_pos, ws.dot_partial, ws.coef, B, N, tiles};
     k_tie_coef<<<(B + EW_THREADS - 1) / EW_THREADS, EW_THREADS, 0, s>>>(tp);
     LAUNCH_CHECK();
-    k_tie_term<<<(3 * N * N + EW_THREADS - 1) / EW_THREADS, EW_THREADS, 0, s>>>(tp);
+    k_tie_term<<<dim3((N * N / 4 + EW_THREADS - 1) / EW_THREADS, 3), EW_THREADS, 0, s>>>(tp);
     LAUNCH_CHECK();
     if (grad_img != nullptr) {
         const int total = planes * T::NC;
@@ -391,6 +400,8 @@ const char* b200cam_error_string(int code) {
         default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "b200cam: unknown error";
     }
 }
+
+unsigned long long b200cam_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int b200cam_supported(int N) { return N == 64 || N == 128 || N == 256 || N == 512 || N == 1024; }
 

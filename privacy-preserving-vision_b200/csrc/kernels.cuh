@@ -25,6 +25,9 @@ struct Tile {
     static constexpr int FP_PAIR = N + 16 / NP;        // natural-order smem row pitch (float2)
     static constexpr int FP_ROW = N + 16 / ROWS;
     static constexpr int COLS = 8;                     // spectral columns per CTA in column passes
+    static constexpr int CROWS = 4;                    // rows per CTA in the complex (PSF chain) row passes
+    static constexpr int FP_CROW = N + 16 / CROWS;
+    static constexpr int RCOLS = 2;                    // columns per CTA in the small batch-independent column passes
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -446,7 +449,7 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
 // ---------------------------------------------------------------------------------------------
 // K7  cols_reduce_inv : sum the chunk partials in order, apply (-1)^(u+v) (the adjoint of the
 //      roll at Optics.py:126) and 1/N^2, inverse FFT along v -> ST layout for rows_c2r
-//      grid ceil(3*NC/COLS), block COLS*LANES
+//      grid ceil(3*NC/RCOLS), block RCOLS*LANES
 // ---------------------------------------------------------------------------------------------
 struct ColsReduceInvParams {
     const float2* partial;   // [nchunks][3][NC][N]
@@ -462,7 +465,7 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
     using T = Tile<N>;
     using S = ColsSmem<N>;
     float2* E = smem;
-    const int cu0 = ex.bx() * S::COLS;
+    const int cu0 = ex.bx() * T::RCOLS;
     constexpr int TOTAL = 3 * T::NC;
     ex.phase([&](int tid) {
         const int jc = tid / P::LANES, b = tid % P::LANES;
@@ -529,27 +532,66 @@ B200_HD void tie_coef_body(Exec& ex, const TieTermParams& p, int grid_x) {
     });
 }
 
+constexpr int TIE_PASS = 256;   // images staged per pass (= block size of the kernel)
+
+// grid (blocks_per_channel, 3), block TIE_PASS.  A block only applies the ties of its own channel.
+// Staging is parallel (thread t <-> image b0+t) and the compaction offsets come from an ordered
+// scan, so the list - and therefore the floating-point subtraction order - is deterministic.
+// shared: s_coef[TIE_PASS*MAX_TIES], s_meta[3*TIE_PASS*MAX_TIES], s_cnt[TIE_PASS+1]
 template <class Exec>
-B200_HD void tie_term_body(Exec& ex, const TieTermParams& p, int grid_x) {
-    ex.phase([&](int tid) {
-        const int N = p.N, NN = N * N, total = 3 * NN;
-        const int stride = grid_x * ex.nthreads();
-        for (int idx = ex.bx() * ex.nthreads() + tid; idx < total; idx += stride) {
-            const int c = idx / NN, py = (idx % NN) / N, px = idx % N;
-            float acc = 0.f;
-            for (int b = 0; b < p.B; ++b) {
+B200_HD void tie_term_body(Exec& ex, const TieTermParams& p, int grid_x, float* s_coef, int* s_meta, int* s_cnt) {
+    const int N = p.N, NN = N * N, c = ex.by();
+    for (int b0 = 0; b0 < p.B; b0 += TIE_PASS) {
+        const int nb = (p.B - b0 < TIE_PASS) ? p.B - b0 : TIE_PASS;
+        ex.phase([&](int tid) {
+            int cnt = 0;
+            if (tid < nb) {
+                const int b = b0 + tid;
                 const int n = p.tie_count[b] < MAX_TIES ? p.tie_count[b] : MAX_TIES;
+                for (int t = 0; t < n; ++t) cnt += (p.tie_pos[b * MAX_TIES + t] / NN == c) ? 1 : 0;
+            }
+            if (tid < TIE_PASS) s_cnt[tid] = cnt;
+        });
+        ex.phase([&](int tid) {
+            if (tid == 0) {
+                int run = 0;
+                for (int t = 0; t < nb; ++t) { const int v = s_cnt[t]; s_cnt[t] = run; run += v; }
+                s_cnt[TIE_PASS] = run;
+            }
+        });
+        ex.phase([&](int tid) {
+            if (tid < nb) {
+                const int b = b0 + tid;
+                const int n = p.tie_count[b] < MAX_TIES ? p.tie_count[b] : MAX_TIES;
+                int k = s_cnt[tid];
                 for (int t = 0; t < n; ++t) {
                     const int pos = p.tie_pos[b * MAX_TIES + t];
                     if (pos / NN != c) continue;
-                    const int ty = (pos % NN) / N, tx = pos % N;
-                    const int sy = (ty - py + N / 2 + N) & (N - 1), sx = (tx - px + N / 2 + N) & (N - 1);
-                    acc += p.coef[b] * ld_ro(p.x + (static_cast<size_t>(b) * 3 + c) * NN + sy * N + sx);
+                    s_coef[k] = p.coef[b];
+                    s_meta[3 * k + 0] = b;
+                    s_meta[3 * k + 1] = (pos % NN) / N;
+                    s_meta[3 * k + 2] = pos % N;
+                    ++k;
                 }
             }
-            p.gpsf[idx] -= acc;
-        }
-    });
+        });
+        ex.phase([&](int tid) {
+            const int k = s_cnt[TIE_PASS];
+            if (k > 0) {
+                const int stride = grid_x * ex.nthreads();
+                for (int idx = ex.bx() * ex.nthreads() + tid; idx < NN; idx += stride) {
+                    const int py = idx / N, px = idx % N;
+                    float acc = 0.f;
+                    for (int e = 0; e < k; ++e) {
+                        const int sy = (s_meta[3 * e + 1] - py + N / 2 + N) & (N - 1);
+                        const int sx = (s_meta[3 * e + 2] - px + N / 2 + N) & (N - 1);
+                        acc += s_coef[e] * ld_ro(p.x + (static_cast<size_t>(s_meta[3 * e]) * 3 + c) * NN + sy * N + sx);
+                    }
+                    p.gpsf[c * NN + idx] -= acc;
+                }
+            }
+        });
+    }
 }
 
 // K9  tie_term_img : the same arg-max term for dL/dimg (optional output)
@@ -622,15 +664,15 @@ struct GradFieldLoad {  // GU = 2 * (gtot - dot)/S * U      (adjoint of |U|^2 / 
     }
 };
 
-// P1  crows_fwd : complex rows -> transposed full spectrum.  grid (N/ROWS, 3), block ROWS*LANES
+// P1  crows_fwd : complex rows -> transposed full spectrum.  grid (N/CROWS, 3), block CROWS*LANES
 template <int N>
 struct CRowsSmem {
     using P = Plan<N>;
     using T = Tile<N>;
-    static constexpr int THREADS = T::ROWS * P::LANES;
+    static constexpr int THREADS = T::CROWS * P::LANES;
     static constexpr int E_OFF = 0;
-    static constexpr int F_OFF = T::ROWS * P::E_SIZE;
-    static constexpr int RED_OFF = F_OFF + T::ROWS * T::FP_ROW;
+    static constexpr int F_OFF = T::CROWS * P::E_SIZE;
+    static constexpr int RED_OFF = F_OFF + T::CROWS * T::FP_CROW;
     static constexpr int FLOAT2S = RED_OFF + THREADS;   // 2 floats per thread of scratch
     static constexpr int BYTES = FLOAT2S * 8;
 };
@@ -646,7 +688,7 @@ B200_HD void crows_fwd_body(Exec& ex, const CRowsFwdParams& p, const Load& load,
     using T = Tile<N>;
     using S = CRowsSmem<N>;
     const int tile = ex.bx(), l = ex.by();
-    const int y0 = tile * T::ROWS;
+    const int y0 = tile * T::CROWS;
     float2* E = smem + S::E_OFF;
     float2* F = smem + S::F_OFF;
     ex.phase([&](int tid) {
@@ -664,13 +706,13 @@ B200_HD void crows_fwd_body(Exec& ex, const CRowsFwdParams& p, const Load& load,
             float2 v[P::R2];
             P::stepB(v, b, E + j * P::E_SIZE);
 #pragma unroll
-            for (int i = 0; i < P::R2; ++i) F[j * T::FP_ROW + b + P::R1 * i] = v[i];
+            for (int i = 0; i < P::R2; ++i) F[j * T::FP_CROW + b + P::R1 * i] = v[i];
         }
     });
     ex.phase([&](int tid) {
-        for (int w = tid; w < T::ROWS * N; w += S::THREADS) {
-            const int u = w / T::ROWS, j = w % T::ROWS;
-            p.st[(static_cast<size_t>(l) * N + u) * N + y0 + j] = F[j * T::FP_ROW + u];
+        for (int w = tid; w < T::CROWS * N; w += S::THREADS) {
+            const int u = w / T::CROWS, j = w % T::CROWS;
+            p.st[(static_cast<size_t>(l) * N + u) * N + y0 + j] = F[j * T::FP_CROW + u];
         }
     });
 }
@@ -692,7 +734,7 @@ struct CColsMixParams {
 template <int N>
 struct CColsSmem {
     using P = Plan<N>;
-    static constexpr int CC = 4;                      // columns per CTA
+    static constexpr int CC = 2;                      // columns per CTA: 128 CTAs at N=256
     static constexpr int THREADS = CC * 3 * P::LANES;
     static constexpr int E_OFF = 0;
     static constexpr int G_OFF = CC * 3 * P::E_SIZE;  // natural-order exchange for the 3-pt DFT
@@ -795,7 +837,7 @@ struct CRowsInvParams {
 struct IntensityEpilogue {
     float2* U;          // [3][N][N]
     float* I;           // [3][N][N]
-    float* partial;     // [3][N/ROWS]
+    float* partial;     // [3][N/CROWS]
     int N;
     B200_HD float operator()(int l, int y, int x, float2 v) const {
         const size_t i = (static_cast<size_t>(l) * N + y) * N + x;
@@ -827,14 +869,14 @@ B200_HD void crows_inv_body(Exec& ex, const CRowsInvParams& p, const Epi& epi, f
     using T = Tile<N>;
     using S = CRowsSmem<N>;
     const int tile = ex.bx(), l = ex.by();
-    const int y0 = tile * T::ROWS;
+    const int y0 = tile * T::CROWS;
     float2* E = smem + S::E_OFF;
     float2* F = smem + S::F_OFF;
     float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
     ex.phase([&](int tid) {
-        for (int w = tid; w < T::ROWS * N; w += S::THREADS) {
-            const int u = w / T::ROWS, j = w % T::ROWS;
-            F[j * T::FP_ROW + u] = ld_ro(p.st + (static_cast<size_t>(l) * N + u) * N + y0 + j);
+        for (int w = tid; w < T::CROWS * N; w += S::THREADS) {
+            const int u = w / T::CROWS, j = w % T::CROWS;
+            F[j * T::FP_CROW + u] = ld_ro(p.st + (static_cast<size_t>(l) * N + u) * N + y0 + j);
         }
     });
     ex.phase([&](int tid) {
@@ -842,7 +884,7 @@ B200_HD void crows_inv_body(Exec& ex, const CRowsInvParams& p, const Epi& epi, f
         if (b < P::R1) {
             float2 v[P::R2];
 #pragma unroll
-            for (int i = 0; i < P::R2; ++i) v[i] = F[j * T::FP_ROW + b + P::R1 * i];
+            for (int i = 0; i < P::R2; ++i) v[i] = F[j * T::FP_CROW + b + P::R1 * i];
             P::stepC(v, b, E + j * P::E_SIZE, p.tw);
         }
     });
@@ -861,7 +903,7 @@ B200_HD void crows_inv_body(Exec& ex, const CRowsInvParams& p, const Epi& epi, f
         if (tid == 0) {
             float s = 0.f;
             for (int t = 0; t < S::THREADS; ++t) s += red[t];
-            epi.finish(l, tile, N / T::ROWS, s);
+            epi.finish(l, tile, N / T::CROWS, s);
         }
     });
 }

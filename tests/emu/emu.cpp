@@ -108,7 +108,7 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
         cols_accum_body<N>(ex, ColsAccumParams{stx.data(), stg.data(), partial.data(), tw.data(), img_max, B, chunk},
                            smem.data(), states.data());
     });
-    grid2(colgroups, 1, ColsSmem<N>::THREADS, [&](HostExec& ex) {
+    grid2((3 * T::NC + T::RCOLS - 1) / T::RCOLS, 1, T::RCOLS * Plan<N>::LANES, [&](HostExec& ex) {
         cols_reduce_inv_body<N>(ex, ColsReduceInvParams{partial.data(), stp.data(), tw.data(), used_chunks,
                                                         1.0f / (static_cast<float>(N) * N)}, smem.data());
     });
@@ -117,7 +117,11 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
     });
     TieTermParams tp{grad_psf, img, img_max, tie_count, tie_pos, dot_partial.data(), coef.data(), B, N, tiles};
     grid2((B + EW_THREADS - 1) / EW_THREADS, 1, EW_THREADS, [&](HostExec& ex) { tie_coef_body(ex, tp, 1); });
-    grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) { tie_term_body(ex, tp, EW_GRID); });
+    std::vector<float> s_coef(TIE_PASS * MAX_TIES);
+    std::vector<int> s_meta(3 * TIE_PASS * MAX_TIES), s_cnt(TIE_PASS + 1);
+    grid2(EW_GRID, 3, EW_THREADS, [&](HostExec& ex) {
+        tie_term_body(ex, tp, EW_GRID, s_coef.data(), s_meta.data(), s_cnt.data());
+    });
     if (grad_img != nullptr) {
         const int total = planes * T::NC;
         grid2((total + T::COLS - 1) / T::COLS, 1, ColsSmem<N>::THREADS, [&](HostExec& ex) {
@@ -149,18 +153,18 @@ int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const float*
     std::vector<float2> smem(CRowsSmem<N>::FLOAT2S > CColsSmem<N>::FLOAT2S ? CRowsSmem<N>::FLOAT2S : CColsSmem<N>::FLOAT2S);
     std::vector<float> red(3 * EW_THREADS);
     PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
-    grid2(N / T::ROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
+    grid2(N / T::CROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
         crows_fwd_body<N>(ex, CRowsFwdParams{ws.st.data(), tw.data()}, load, smem.data());
     });
     grid2((N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, 1, CColsSmem<N>::THREADS, [&](HostExec& ex) {
         ccols_mix_body<N>(ex, CColsMixParams{ws.st.data(), Ht, tw.data(), 0, 1.0f / (3.0f * N * N)}, smem.data());
     });
     IntensityEpilogue epi{field, ws.I.data(), ws.part_rows.data(), N};
-    grid2(N / T::ROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
+    grid2(N / T::CROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
         crows_inv_body<N>(ex, CRowsInvParams{ws.st.data(), tw.data()}, epi, smem.data());
     });
     grid2(1, 1, EW_THREADS, [&](HostExec& ex) {
-        reduce_body(ex, ReduceParams{ws.part_rows.data(), stats, 3 * (N / T::ROWS), 0, N}, red.data());
+        reduce_body(ex, ReduceParams{ws.part_rows.data(), stats, 3 * (N / T::CROWS), 0, N}, red.data());
     });
     grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) {
         psf_finalise_body(ex, PsfFinaliseParams{ws.I.data(), rho, stats, psf, ws.part_ew.data(), N}, EW_GRID, red.data());
@@ -188,14 +192,14 @@ int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, const fl
         reduce_body(ex, ReduceParams{ws.part_ew.data(), stats, EW_GRID, 2, N}, red.data());
     });
     GradFieldLoad load{field, ws.gtot.data(), stats, N};
-    grid2(N / T::ROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
+    grid2(N / T::CROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
         crows_fwd_body<N>(ex, CRowsFwdParams{ws.st.data(), tw.data()}, load, smem.data());
     });
     grid2((N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, 1, CColsSmem<N>::THREADS, [&](HostExec& ex) {
         ccols_mix_body<N>(ex, CColsMixParams{ws.st.data(), Ht, tw.data(), 1, 1.0f / (3.0f * N * N)}, smem.data());
     });
     HeightGradEpilogue epi{PupilLoad{A, h, {kappa[0], kappa[1], kappa[2]}, N}, ws.gh3.data(), N};
-    grid2(N / T::ROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
+    grid2(N / T::CROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
         crows_inv_body<N>(ex, CRowsInvParams{ws.st.data(), tw.data()}, epi, smem.data());
     });
     grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) { sum3_body(ex, Sum3Params{ws.gh3.data(), grad_h, N * N}, EW_GRID); });
