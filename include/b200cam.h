@@ -46,6 +46,8 @@ int b200cam_init(int N);
 size_t b200cam_otf_bytes(int N);                                   /* 3*(N/2+1)*N complex */
 size_t b200cam_psf_workspace_bytes(int N);
 size_t b200cam_sensor_workspace_bytes(int N, int B, int want_img_grad);
+/* size of the optional saved forward spectrum (0 when the fused N=256 path is not in use) */
+size_t b200cam_spectrum_bytes(int N, int B);
 
 /* PSF synthesis, forward.  Replaces Camera.get_psf + the regularisers
  * (Face-DeId/Camera/Optics.py:89-120 and :124-125):
@@ -79,9 +81,12 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const floa
  *   img_max  [B]                       out: the per-image maximum before division
  *   tie_count[B], tie_pos[B][MAX_TIES] out: how many positions attain the maximum, and the first
  *                                      MAX_TIES of them as flat indices into (3,N,N)
- *   otf      b200cam_otf_bytes(N)      out: rfft2(roll(psf))/N^2 in the library's transposed layout */
+ *   otf      b200cam_otf_bytes(N)      out: rfft2(roll(psf))/N^2 in the library's transposed layout
+ *   spectrum b200cam_spectrum_bytes(N,B) or NULL  out: rfft2(img) in the fused kernel's register order,
+ *                                      kept for b200cam_sensor_bwd (what autograd would save, Utils.py:8);
+ *                                      NULL (inference) skips the store */
 int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float* img_max,
-                       int* tie_count, int* tie_pos, float* otf,
+                       int* tie_count, int* tie_pos, float* otf, float* spectrum,
                        void* workspace, size_t workspace_bytes, int B, int N, void* stream);
 
 /* Sensor image, backward (autograd through Optics.py:126-128 in closed form, incl. the amax term).

@@ -4,9 +4,11 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "../../include/b200cam.h"
+#include "fused256.cuh"
 #include "kernels.cuh"
 
 namespace b200cam {
@@ -101,6 +103,15 @@ __global__ void __launch_bounds__(EW_THREADS) k_sum3(Sum3Params p) {
     DeviceExec ex;
     sum3_body(ex, p, gridDim.x);
 }
+__global__ void __launch_bounds__(EW_THREADS) k_f256_prep(f256::PrepParams p) {
+    DeviceExec ex;
+    f256::prep_body(ex, p, gridDim.x);
+}
+__global__ void __launch_bounds__(f256::THREADS, 1) k_f256_fwd(f256::FwdParams p) {
+    DeviceExec ex;
+    f256::FState st;
+    f256::fwd_body(ex, p, SMEM2, gridDim.x, &st);
+}
 __global__ void k_fill_twiddle(float2* tw, int N) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < N) {
@@ -117,9 +128,19 @@ constexpr int MAX_DEV = 64;
 constexpr int EW_GRID = 296;   // 2 x 148 SMs for the element-wise / reduction kernels
 
 inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
-struct DeviceState { float2* tw[11] = {nullptr}; };
+struct DeviceState { float2* tw[11] = {nullptr}; int sms = 0; };
 static DeviceState g_state[MAX_DEV];
 static std::mutex g_mutex;
+
+static int sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 0;
+    return g_state[dev].sms;
+}
+static bool fused_enabled() {
+    static const bool on = [] { const char* e = getenv("B200CAM_FUSED"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 static const float2* twiddle(int N) {
     int dev = 0;
@@ -188,11 +209,22 @@ struct PsfWs {
     }
 };
 
+constexpr int FUSED_MAX_GRID = 256;   // upper bound on resident CTAs (SMs) the parking area is sized for
+
 struct SensorWs {
     float2* stx; float2* stg; float2* partial; float2* stp; float* dot_partial; float* coef;
+    float2* kf; float2* kq; float* park; int* done;
     size_t bytes;
     SensorWs(void* p, int N, int B, bool backward) {
         Carver c(p);
+        if (N == 256) {
+            kf = c.take<float2>(f256::KF_ELEMS);
+            kq = c.take<float2>(f256::KQ_ELEMS);
+            park = c.take<float>(static_cast<size_t>(FUSED_MAX_GRID) * 64 * f256::THREADS);
+            done = c.take<int>(B);
+        } else {
+            kf = kq = nullptr; park = nullptr; done = nullptr;
+        }
         const size_t plane = static_cast<size_t>(N / 2 + 1) * N;
         stx = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
         if (backward) {
@@ -291,13 +323,24 @@ static int otf_impl(const float* psf, float2* otf, const float2* tw, cudaStream_
 
 template <int N>
 static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
-                           int* tie_pos, float2* otf, void* ws_ptr, int B, cudaStream_t s) {
+                           int* tie_pos, float2* otf, float2* spectrum, void* ws_ptr, int B, cudaStream_t s) {
     using T = Tile<N>;
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     int rc = otf_impl<N>(psf, otf, tw, s);
     if (rc) return rc;
     SensorWs ws(ws_ptr, N, B, false);
+    if (N == 256 && fused_enabled()) {
+        k_f256_prep<<<148, EW_THREADS, 0, s>>>(f256::PrepParams{otf, ws.kf, ws.kq, ws.done, img_max, tie_count, B});
+        LAUNCH_CHECK();
+        int grid = sm_count();
+        if (grid <= 0 || grid > FUSED_MAX_GRID) return B200CAM_E_NOT_INIT;
+        if (grid > 3 * B) grid = 3 * B;
+        k_f256_fwd<<<grid, f256::THREADS, f256::SMEM_BYTES, s>>>(f256::FwdParams{
+            img, sensor, ws.kf, ws.kq, tw, spectrum, ws.park, img_max, ws.done, tie_count, tie_pos, 3 * B, MAX_TIES});
+        LAUNCH_CHECK();
+        return 0;
+    }
     const int planes = 3 * B;
     const dim3 rgrid(N / T::ROWS, planes);
     k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
@@ -426,6 +469,8 @@ int b200cam_init(int N) {
         case 512: e = init_kernels<512>(); break;
         case 1024: e = init_kernels<1024>(); break;
     }
+    if (e == cudaSuccess && N == 256) e = optin(k_f256_fwd, f256::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_state[dev].sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) { cudaFree(tw); return static_cast<int>(e); }
     g_state[dev].tw[l] = tw;
     return 0;
@@ -471,17 +516,24 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const floa
                                      reinterpret_cast<const float2*>(field), stats, grad_h, workspace, s)));
 }
 
+size_t b200cam_spectrum_bytes(int N, int B) {
+    if (N != 256 || B < 1 || !fused_enabled()) return 0;
+    return static_cast<size_t>(3) * B * f256::XS_PLANE * sizeof(float2);
+}
+
 int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
-                       int* tie_pos, float* otf, void* workspace, size_t workspace_bytes, int B, int N,
-                       void* stream) {
+                       int* tie_pos, float* otf, float* spectrum, void* workspace, size_t workspace_bytes, int B,
+                       int N, void* stream) {
     if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
     if (!img || !psf || !sensor || !img_max || !tie_count || !tie_pos || !otf || !workspace) return B200CAM_E_NULL;
     if (workspace_bytes < b200cam_sensor_workspace_bytes(N, B, 0)) return B200CAM_E_WORKSPACE;
     if (!aligned16(img) || !aligned16(sensor) || !aligned16(otf) || !aligned16(workspace) || !aligned16(psf))
         return B200CAM_E_ALIGN;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (spectrum != nullptr && !aligned16(spectrum)) return B200CAM_E_ALIGN;
     DISPATCH_N(N, (sensor_fwd_impl<NN_>(img, psf, sensor, img_max, tie_count, tie_pos,
-                                        reinterpret_cast<float2*>(otf), workspace, B, s)));
+                                        reinterpret_cast<float2*>(otf), reinterpret_cast<float2*>(spectrum), workspace,
+                                        B, s)));
 }
 
 int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* sensor, const float* img_max,

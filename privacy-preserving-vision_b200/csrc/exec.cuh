@@ -23,6 +23,16 @@ struct DeviceExec {
         f(static_cast<int>(threadIdx.x));
         __syncthreads();
     }
+    // a phase whose data exchange stays inside one warp (FFT lane groups never straddle warps)
+    template <class F>
+    __device__ __forceinline__ void warp_phase(F&& f) {
+        f(static_cast<int>(threadIdx.x));
+        __syncwarp();
+    }
+    __device__ __forceinline__ void barrier() { __syncthreads(); }
+    __device__ __forceinline__ void threadfence() { __threadfence(); }
+    __device__ __forceinline__ float load_cg(const float* p) { return __ldcg(p); }
+    __device__ __forceinline__ float4 load_cg4(const float4* p) { return __ldcg(p); }
 };
 #endif
 
@@ -36,6 +46,14 @@ struct HostExec {
     void phase(F&& f) {
         for (int t = 0; t < nthreads_; ++t) f(t);
     }
+    template <class F>
+    void warp_phase(F&& f) {
+        for (int t = 0; t < nthreads_; ++t) f(t);
+    }
+    void barrier() {}
+    void threadfence() {}
+    float load_cg(const float* p) { return *p; }
+    float4 load_cg4(const float4* p) { return *p; }
 };
 
 }  // namespace b200cam

@@ -128,7 +128,7 @@ class SensorConv(torch.autograd.Function):
             with torch.cuda.device(plan.index):
                 _lib.check(plan.lib.b200cam_sensor_fwd(
                     _lib.ptr(x), _lib.ptr(p), _lib.ptr(sensor), _lib.ptr(img_max), _lib.ptr(tie_count),
-                    _lib.ptr(tie_pos), _lib.ptr(otf), _lib.ptr(ws), ws.numel(), B, N, _stream()))
+                    _lib.ptr(tie_pos), _lib.ptr(otf), _lib.ptr(None), _lib.ptr(ws), ws.numel(), B, N, _stream()))
         ctx.plan = plan
         ctx.psf_shape = psf.shape
         ctx.save_for_backward(x, p, sensor, img_max, tie_count, tie_pos, otf)

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../privacy-preserving-vision_b200/csrc/kernels.cuh"
+#include "../../privacy-preserving-vision_b200/csrc/fused256.cuh"
 
 using namespace b200cam;
 
@@ -218,7 +219,32 @@ int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, const fl
         default: return -1;                                    \
     }
 
+// fused N=256 forward: generic OTF -> fused tables -> persistent fused kernel with `grid` emulated CTAs
+int fused_sensor_fwd_impl(int B, int grid, const float* img, const float* psf, float* sensor, float* img_max,
+                          int* tie_count, int* tie_pos, float2* otf, float2* xs) {
+    constexpr int N = 256;
+    auto tw = make_twiddle(N);
+    otf_impl<N>(psf, otf, tw.data());
+    std::vector<float2> kf(f256::KF_ELEMS), kq(f256::KQ_ELEMS);
+    std::vector<int> done(B);
+    f256::PrepParams pp{otf, kf.data(), kq.data(), done.data(), img_max, tie_count, B};
+    grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) { f256::prep_body(ex, pp, EW_GRID); });
+    std::vector<float> park(static_cast<size_t>(grid) * 64 * f256::THREADS);
+    std::vector<float2> smem(f256::SMEM_FLOAT2);
+    std::vector<f256::FState> st(f256::THREADS);
+    f256::FwdParams fp{img, sensor, kf.data(), kq.data(), tw.data(), xs, park.data(), img_max, done.data(),
+                       tie_count, tie_pos, 3 * B, MAX_TIES};
+    grid2(grid, 1, f256::THREADS, [&](HostExec& ex) { f256::fwd_body(ex, fp, smem.data(), grid, st.data()); });
+    return 0;
+}
+
 extern "C" {
+
+int emu_fused_sensor_fwd(int B, int grid, const float* img, const float* psf, float* sensor, float* img_max,
+                         int* tie_count, int* tie_pos, float* otf, float* xs) {
+    return fused_sensor_fwd_impl(B, grid, img, psf, sensor, img_max, tie_count, tie_pos,
+                                 reinterpret_cast<float2*>(otf), reinterpret_cast<float2*>(xs));
+}
 
 int emu_fft(int N, int inverse, const float* in, float* out) {
     // one N-point FFT through stepA..D with 'LANES' emulated lanes; exercises Plan<N> in isolation

@@ -218,7 +218,7 @@ def test_abi_error_codes_on_device():
     i32 = torch.zeros(8, dtype=torch.int32, device="cuda")
     otf = torch.zeros(lib.b200cam_otf_bytes(N) // 4, device="cuda")
     p = _lib.ptr
-    rc = lib.b200cam_sensor_fwd(p(t), p(t), p(t), p(t), p(i32), p(i32), p(otf), p(small), small.numel(), B, N,
+    rc = lib.b200cam_sensor_fwd(p(t), p(t), p(t), p(t), p(i32), p(i32), p(otf), p(None), p(small), small.numel(), B, N,
                                 ctypes.c_void_p(0))
     assert rc == -3                                                   # B200CAM_E_WORKSPACE
     with pytest.raises(TypeError):

@@ -48,7 +48,7 @@ def test_abi_rejects_bad_arguments_before_touching_the_gpu(library):
     kappa = (ctypes.c_float * 3)(1, 2, 3)
     assert library.b200cam_psf_fwd(null, null, null, null, kappa, null, null, null, null, 0, 100, null) == -1
     assert library.b200cam_psf_fwd(null, null, null, null, kappa, null, null, null, null, 0, 256, null) == -2
-    assert library.b200cam_sensor_fwd(null, null, null, null, null, null, null, null, 0, 0, 256, null) == -1
+    assert library.b200cam_sensor_fwd(null, null, null, null, null, null, null, null, null, 0, 0, 256, null) == -1
 
 
 def test_no_cpu_fallback():
