@@ -46,7 +46,7 @@ int b200cam_init(int N);
 size_t b200cam_otf_bytes(int N);                                   /* 3*(N/2+1)*N complex */
 size_t b200cam_psf_workspace_bytes(int N);
 size_t b200cam_sensor_workspace_bytes(int N, int B, int want_img_grad);
-/* size of the optional saved forward spectrum (0 when the fused N=256 path is not in use) */
+/* size of the optional saved forward spectrum (row-transformed rfft of every image plane) */
 size_t b200cam_spectrum_bytes(int N, int B);
 
 /* PSF synthesis, forward.  Replaces Camera.get_psf + the regularisers
@@ -82,21 +82,22 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const floa
  *   tie_count[B], tie_pos[B][MAX_TIES] out: how many positions attain the maximum, and the first
  *                                      MAX_TIES of them as flat indices into (3,N,N)
  *   otf      b200cam_otf_bytes(N)      out: rfft2(roll(psf))/N^2 in the library's transposed layout
- *   spectrum b200cam_spectrum_bytes(N,B) or NULL  out: rfft2(img) in the fused kernel's register order,
- *                                      kept for b200cam_sensor_bwd (what autograd would save, Utils.py:8);
- *                                      NULL (inference) skips the store */
+ *   spectrum b200cam_spectrum_bytes(N,B) or NULL  out: the row-transformed spectra of img (library layout),
+ *                                      kept for b200cam_sensor_bwd (autograd would save rfftn(img), Utils.py:8);
+ *                                      NULL (inference): nothing is kept, the backward recomputes them */
 int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float* img_max,
                        int* tie_count, int* tie_pos, float* otf, float* spectrum,
                        void* workspace, size_t workspace_bytes, int B, int N, void* stream);
 
 /* Sensor image, backward (autograd through Optics.py:126-128 in closed form, incl. the amax term).
  *   grad_sensor [B][3][N][N]   dL/dsensor
- *   sensor, img_max, tie_count, tie_pos, otf: the outputs of b200cam_sensor_fwd on the same img/psf
+ *   sensor, img_max, tie_count, tie_pos, otf, spectrum (or NULL): outputs of b200cam_sensor_fwd on the same img/psf
  *   grad_psf    [3][N][N]      out: dL/dpsf (centred frame), summed over the batch
  *   grad_img    [B][3][N][N]   out or NULL (no reference caller needs it) */
 int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* sensor,
                        const float* img_max, const int* tie_count, const int* tie_pos,
-                       const float* psf, const float* otf, float* grad_psf, float* grad_img,
+                       const float* psf, const float* otf, const float* spectrum,
+                       float* grad_psf, float* grad_img,
                        void* workspace, size_t workspace_bytes, int B, int N, void* stream);
 
 #ifdef __cplusplus

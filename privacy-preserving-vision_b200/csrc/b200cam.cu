@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_r2c(RowsR2CPar
 template <int N>
 __global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_conv(ColsConvParams p) {
     DeviceExec ex;
-    cols_conv_body<N>(ex, p, SMEM2);
+    ConvState<N> st;
+    cols_conv_body<N>(ex, p, SMEM2, &st);
 }
 template <int N>
 __global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_fwd(ColsFwdParams p) {
@@ -138,7 +139,7 @@ static int sm_count() {
     return g_state[dev].sms;
 }
 static bool fused_enabled() {
-    static const bool on = [] { const char* e = getenv("B200CAM_FUSED"); return !(e && e[0] == '0'); }();
+    static const bool on = [] { const char* e = getenv("B200CAM_FUSED"); return e && e[0] == '1'; }();   // experimental, off by default
     return on;
 }
 
@@ -193,6 +194,13 @@ static int accum_chunks(int N, int B) {
     return n;
 }
 
+static int conv_chunk(int N, int B) {      // images per CTA of the persistent column-convolution kernel
+    const int colgroups = (3 * (N / 2 + 1) + 7) / 8;
+    int nchunks = (148 * 5 + colgroups - 1) / colgroups;      // ~5 CTAs per SM
+    if (nchunks > B) nchunks = B;
+    return (B + nchunks - 1) / nchunks;
+}
+
 struct PsfWs {
     float2* st; float* I; float* gtot; float* gh3; float* part_rows; float* part_ew;
     size_t bytes;
@@ -213,7 +221,7 @@ constexpr int FUSED_MAX_GRID = 256;   // upper bound on resident CTAs (SMs) the 
 
 struct SensorWs {
     float2* stx; float2* stg; float2* partial; float2* stp; float* dot_partial; float* coef;
-    float2* kf; float2* kq; float* park; int* done;
+    float2* kf; float2* kq; float* park; int* done; float2* st2; int* arrive;
     size_t bytes;
     SensorWs(void* p, int N, int B, bool backward) {
         Carver c(p);
@@ -227,6 +235,8 @@ struct SensorWs {
         }
         const size_t plane = static_cast<size_t>(N / 2 + 1) * N;
         stx = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
+        st2 = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
+        arrive = c.take<int>(B);
         if (backward) {
             stg = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
             partial = c.take<float2>(static_cast<size_t>(accum_chunks(N, B)) * 3 * plane);
@@ -312,7 +322,7 @@ template <int N>
 static int otf_impl(const float* psf, float2* otf, const float2* tw, cudaStream_t s) {
     using T = Tile<N>;
     k_rows_r2c<N><<<dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsR2CParams{psf, otf, tw, nullptr, nullptr, nullptr, nullptr});
+        RowsR2CParams{psf, otf, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
     LAUNCH_CHECK();
     const int total = 3 * T::NC;
     k_cols_fwd<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
@@ -343,15 +353,17 @@ static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, fl
     }
     const int planes = 3 * B;
     const dim3 rgrid(N / T::ROWS, planes);
+    float2* srow = spectrum != nullptr ? spectrum : ws.stx;      // row spectra: kept for the backward when asked
     k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsR2CParams{img, ws.stx, tw, nullptr, nullptr, img_max, tie_count});
+        RowsR2CParams{img, srow, tw, nullptr, nullptr, img_max, tie_count, nullptr, nullptr, nullptr, nullptr});
     LAUNCH_CHECK();
-    const int total = planes * T::NC;
-    k_cols_conv<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsConvParams{ws.stx, ws.stx, otf, tw, nullptr, total, 0});
+    const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
+    const int chunk = conv_chunk(N, B);
+    k_cols_conv<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, chunk, 0});
     LAUNCH_CHECK();
     k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsC2RParams{ws.stx, sensor, tw, img_max, 1.0f});
+        RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f});
     LAUNCH_CHECK();
     const long long n4 = static_cast<long long>(planes) * N * N / 4;
     const int grid = static_cast<int>(n4 / EW_THREADS < 148 * 8 ? (n4 + EW_THREADS - 1) / EW_THREADS : 148 * 8);
@@ -362,25 +374,31 @@ static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, fl
 
 template <int N>
 static int sensor_bwd_impl(const float* g, const float* img, const float* sensor, const float* img_max,
-                           const int* tie_count, const int* tie_pos, const float* psf, const float2* otf, float* grad_psf,
-                           float* grad_img, void* ws_ptr, int B, cudaStream_t s) {
+                           const int* tie_count, const int* tie_pos, const float* psf, const float2* otf,
+                           const float2* spectrum, float* grad_psf, float* grad_img, void* ws_ptr, int B,
+                           cudaStream_t s) {
     using T = Tile<N>;
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     SensorWs ws(ws_ptr, N, B, true);
     const int planes = 3 * B, tiles = N / T::ROWS;
     const dim3 rgrid(tiles, planes);
+    const float2* srow = spectrum;
+    if (srow == nullptr) {                       // forward did not keep the row spectra: recompute them
+        k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+            RowsR2CParams{img, ws.stx, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
+        LAUNCH_CHECK();
+        srow = ws.stx;
+    }
+    CK(cudaMemsetAsync(ws.arrive, 0, sizeof(int) * B, s));
     k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsR2CParams{img, ws.stx, tw, nullptr, nullptr, nullptr, nullptr});
-    LAUNCH_CHECK();
-    k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsR2CParams{g, ws.stg, tw, sensor, ws.dot_partial, nullptr, nullptr});
+        RowsR2CParams{g, ws.stg, tw, sensor, ws.dot_partial, nullptr, nullptr, ws.arrive, ws.coef, img_max, tie_count});
     LAUNCH_CHECK();
     const int nchunks = accum_chunks(N, B);
     const int chunk = (B + nchunks - 1) / nchunks;
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     k_cols_accum<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsAccumParams{ws.stx, ws.stg, ws.partial, tw, img_max, B, chunk});
+        ColsAccumParams{srow, ws.stg, ws.partial, tw, img_max, ws.coef, tie_count, tie_pos, B, chunk});
     LAUNCH_CHECK();
     k_cols_reduce_inv<N><<<(3 * T::NC + T::RCOLS - 1) / T::RCOLS, T::RCOLS * Plan<N>::LANES, ColsSmem<N>::BYTES, s>>>(
         ColsReduceInvParams{ws.partial, ws.stp, tw, (B + chunk - 1) / chunk, 1.0f / (static_cast<float>(N) * N)});
@@ -388,15 +406,10 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
         RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
     LAUNCH_CHECK();
-    TieTermParams tp{grad_psf, img, img_max, tie_count, tie_pos, ws.dot_partial, ws.coef, B, N, tiles};
-    k_tie_coef<<<(B + EW_THREADS - 1) / EW_THREADS, EW_THREADS, 0, s>>>(tp);
-    LAUNCH_CHECK();
-    k_tie_term<<<dim3((N * N / 4 + EW_THREADS - 1) / EW_THREADS, 3), EW_THREADS, 0, s>>>(tp);
-    LAUNCH_CHECK();
     if (grad_img != nullptr) {
-        const int total = planes * T::NC;
-        k_cols_conv<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, total, 1});
+        const int cchunk = conv_chunk(N, B);
+        k_cols_conv<N><<<dim3(colgroups, (B + cchunk - 1) / cchunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunk, 1});
         LAUNCH_CHECK();
         k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
             RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
@@ -517,8 +530,9 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const floa
 }
 
 size_t b200cam_spectrum_bytes(int N, int B) {
-    if (N != 256 || B < 1 || !fused_enabled()) return 0;
-    return static_cast<size_t>(3) * B * f256::XS_PLANE * sizeof(float2);
+    if (!b200cam_supported(N) || B < 1) return 0;
+    if (N == 256 && fused_enabled()) return static_cast<size_t>(3) * B * f256::XS_PLANE * sizeof(float2);
+    return static_cast<size_t>(3) * B * (N / 2 + 1) * N * sizeof(float2);
 }
 
 int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
@@ -538,8 +552,8 @@ int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float*
 
 int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* sensor, const float* img_max,
                        const int* tie_count, const int* tie_pos, const float* psf, const float* otf,
-                       float* grad_psf, float* grad_img, void* workspace, size_t workspace_bytes, int B, int N,
-                       void* stream) {
+                       const float* spectrum, float* grad_psf, float* grad_img, void* workspace,
+                       size_t workspace_bytes, int B, int N, void* stream) {
     if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
     if (!grad_sensor || !img || !sensor || !img_max || !tie_count || !tie_pos || !psf || !otf || !grad_psf || !workspace)
         return B200CAM_E_NULL;
@@ -548,8 +562,10 @@ int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* 
         !aligned16(grad_psf) || (grad_img && !aligned16(grad_img)))
         return B200CAM_E_ALIGN;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const float2* spec = (N == 256 && fused_enabled()) ? nullptr : reinterpret_cast<const float2*>(spectrum);
     DISPATCH_N(N, (sensor_bwd_impl<NN_>(grad_sensor, img, sensor, img_max, tie_count, tie_pos, psf,
-                                        reinterpret_cast<const float2*>(otf), grad_psf, grad_img, workspace, B, s)));
+                                        reinterpret_cast<const float2*>(otf), spec, grad_psf, grad_img, workspace,
+                                        B, s)));
 }
 
 }  // extern "C"

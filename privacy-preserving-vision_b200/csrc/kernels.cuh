@@ -45,6 +45,12 @@ struct RowsR2CParams {
     float* dot_partial;      // [planes][N/ROWS]
     float* init_max;         // nullable, [planes/3]
     int* init_count;         // nullable, [planes/3]
+    // with dot_with: the last CTA of an image to finish turns the partials into
+    //   coef[b] = sum(g*y) / (n_ties * max)      (the weight of the arg-max term of the amax backward)
+    int* arrive;             // [planes/3], zeroed by the caller before the launch
+    float* coef;             // [planes/3]
+    const float* img_max;    // [planes/3]
+    const int* tie_count;    // [planes/3]
 };
 
 template <int N>
@@ -54,7 +60,7 @@ struct RowsR2CSmem {
     static constexpr int E_OFF = 0;
     static constexpr int F_OFF = T::NP * P::E_SIZE;
     static constexpr int RED_OFF = F_OFF + T::NP * T::FP_PAIR;            // float2 units
-    static constexpr int FLOAT2S = RED_OFF + (T::NP * P::LANES + 1) / 2;  // reduction scratch (floats)
+    static constexpr int FLOAT2S = RED_OFF + (T::NP * P::LANES + 2) / 2 + 1;  // reduction scratch (floats) + flag
     static constexpr int BYTES = FLOAT2S * 8;
     static constexpr int THREADS = T::NP * P::LANES;
 };
@@ -106,9 +112,19 @@ B200_HD void rows_r2c_body(Exec& ex, const RowsR2CParams& p, float2* smem) {
             float s = 0.f;
             for (int t = 0; t < S::THREADS; ++t) s += red[t];
             p.dot_partial[plane * (N / T::ROWS) + tile] = s;
+            ex.threadfence();
+            const int old = atomic_add_int(p.arrive + plane / 3, 1);
+            red[S::THREADS] = (old == 3 * (N / T::ROWS) - 1) ? 1.f : 0.f;     // this CTA completes the image
         }
     });
     ex.phase([&](int tid) {
+        if (p.dot_with != nullptr && red[S::THREADS] != 0.f && tid < 32) {
+            ex.threadfence();
+            float s = 0.f;                                                          // fixed order: deterministic
+            for (int t = tid; t < 3 * (N / T::ROWS); t += 32)
+                s += ex.load_cg(p.dot_partial + (plane / 3) * 3 * (N / T::ROWS) + t);
+            red[tid] = s;
+        }
         // unpack the pair spectrum Z = FFT(row_even + i*row_odd) into the two Hermitian halves
         for (int w = tid; w < T::NP * T::NC; w += S::THREADS) {
             const int u = w / T::NP, j = w % T::NP;
@@ -119,6 +135,17 @@ B200_HD void rows_r2c_body(Exec& ex, const RowsR2CParams& p, float2* smem) {
             *reinterpret_cast<float4*>(p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0 + 2 * j) = o;
         }
     });
+    if (p.dot_with != nullptr) {
+        ex.phase([&](int tid) {
+            if (tid == 0 && red[S::THREADS] != 0.f) {
+                float s = 0.f;
+                for (int t = 0; t < 32; ++t) s += red[t];
+                const int b = plane / 3;
+                const int n = p.tie_count[b] > 0 ? p.tie_count[b] : 1;
+                p.coef[b] = s / (static_cast<float>(n) * p.img_max[b]);
+            }
+        });
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -129,12 +156,13 @@ B200_HD void rows_r2c_body(Exec& ex, const RowsR2CParams& p, float2* smem) {
 //      col_scale (nullable, [planes/3]): extra per-image factor (1/max for the backward).
 // ---------------------------------------------------------------------------------------------
 struct ColsConvParams {
-    const float2* in;        // [planes][NC][N]
+    const float2* in;        // [B*3][NC][N]
     float2* out;             // same layout (may alias in)
     const float2* otf;       // [3][NC][N]
     const float2* tw;
     const float* img_scale;  // nullable: per image multiplier is 1/img_scale[b]
-    int total_cols;          // planes*NC
+    int B;
+    int chunk;               // images per CTA (gridDim.y = ceil(B/chunk))
     int conj_otf;
 };
 
@@ -147,55 +175,81 @@ struct ColsSmem {
     static constexpr int BYTES = FLOAT2S * 8;
 };
 
+template <int N>
+struct ConvState {
+    float2 k[Plan<N>::R2];   // this lane's OTF values, loaded once per CTA
+    float2 v[Plan<N>::R2 > Plan<N>::R1 ? Plan<N>::R2 : Plan<N>::R1];
+};
+
+// grid (ceil(3*NC/COLS), ceil(B/chunk)), block COLS*LANES.  A CTA owns COLS columns of one channel
+// (flat index cu over [3][NC]) and walks its chunk of images, so the OTF is read once per CTA.
 template <int N, class Exec>
-B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem) {
+B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem, ConvState<N>* st) {
     using P = Plan<N>;
     using T = Tile<N>;
     using S = ColsSmem<N>;
     float2* E1 = smem;
     float2* E2 = smem + S::COLS * P::E_SIZE;
-    const int col0 = ex.bx() * S::COLS;
+    constexpr int TOTAL = 3 * T::NC;
+    const int cu0 = ex.bx() * S::COLS;
+    const int b0 = ex.by() * p.chunk;
+    const int b1 = (b0 + p.chunk < p.B) ? b0 + p.chunk : p.B;
 
-    ex.phase([&](int tid) {
-        const int jc = tid / P::LANES, a = tid % P::LANES;
-        const int col = col0 + jc;
-        if (col < p.total_cols && a < P::R2) {
-            const float2* src = p.in + static_cast<size_t>(col) * N;   // may alias p.out: plain loads
-            float2 v[P::R1];
-#pragma unroll
-            for (int i = 0; i < P::R1; ++i) v[i] = src[P::R2 * i + a];
-            P::stepA(v, a, E1 + jc * P::E_SIZE, p.tw);
-        }
-    });
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, b = tid % P::LANES;
-        const int col = col0 + jc;
-        if (col < p.total_cols && b < P::R1) {
-            const int plane = col / T::NC, u = col % T::NC, c = plane % 3;
-            const float2* k = p.otf + (static_cast<size_t>(c) * T::NC + u) * N;
-            const float s = p.img_scale != nullptr ? 1.0f / ld_ro(p.img_scale + plane / 3) : 1.0f;
-            float2 v[P::R2];
-            P::stepB(v, b, E1 + jc * P::E_SIZE);
+        const int cu = cu0 + jc;
+        if (cu < TOTAL && b < P::R1) {
+            ConvState<N>& s = st[ex.slot(tid)];
+            const float2* k = p.otf + static_cast<size_t>(cu) * N;
 #pragma unroll
             for (int i = 0; i < P::R2; ++i) {
                 const float2 kk = ld_ro(k + b + P::R1 * i);
-                v[i] = p.conj_otf ? cmulc(v[i], kk) : cmul(v[i], kk);
-                if (p.img_scale != nullptr) v[i] = cscale(v[i], s);
+                s.k[i] = p.conj_otf ? cconj(kk) : kk;
             }
-            P::stepC(v, b, E2 + jc * P::E_SIZE, p.tw);
         }
     });
-    ex.phase([&](int tid) {
-        const int jc = tid / P::LANES, a = tid % P::LANES;
-        const int col = col0 + jc;
-        if (col < p.total_cols && a < P::R2) {
-            float2 v[P::R1];
-            P::stepD(v, a, E2 + jc * P::E_SIZE);
-            float2* dst = p.out + static_cast<size_t>(col) * N;
+    for (int img = b0; img < b1; ++img) {
+        ex.warp_phase([&](int tid) {
+            const int jc = tid / P::LANES, a = tid % P::LANES;
+            const int cu = cu0 + jc;
+            if (cu < TOTAL && a < P::R2) {
+                const int c = cu / T::NC, u = cu % T::NC;
+                const float2* src = p.in + (static_cast<size_t>(img * 3 + c) * T::NC + u) * N;   // may alias out: plain loads
+                float2 v[P::R1];
 #pragma unroll
-            for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = v[i];
-        }
-    });
+                for (int i = 0; i < P::R1; ++i) v[i] = src[P::R2 * i + a];
+                P::stepA(v, a, E1 + jc * P::E_SIZE, p.tw);
+            }
+        });
+        ex.warp_phase([&](int tid) {
+            const int jc = tid / P::LANES, b = tid % P::LANES;
+            const int cu = cu0 + jc;
+            if (cu < TOTAL && b < P::R1) {
+                const ConvState<N>& s = st[ex.slot(tid)];
+                const float sc = p.img_scale != nullptr ? 1.0f / ld_ro(p.img_scale + img) : 1.0f;
+                float2 v[P::R2];
+                P::stepB(v, b, E1 + jc * P::E_SIZE);
+#pragma unroll
+                for (int i = 0; i < P::R2; ++i) {
+                    v[i] = cmul(v[i], s.k[i]);
+                    if (p.img_scale != nullptr) v[i] = cscale(v[i], sc);
+                }
+                P::stepC(v, b, E2 + jc * P::E_SIZE, p.tw);
+            }
+        });
+        ex.warp_phase([&](int tid) {
+            const int jc = tid / P::LANES, a = tid % P::LANES;
+            const int cu = cu0 + jc;
+            if (cu < TOTAL && a < P::R2) {
+                const int c = cu / T::NC, u = cu % T::NC;
+                float2 v[P::R1];
+                P::stepD(v, a, E2 + jc * P::E_SIZE);
+                float2* dst = p.out + (static_cast<size_t>(img * 3 + c) * T::NC + u) * N;
+#pragma unroll
+                for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = v[i];
+            }
+        });
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -217,7 +271,7 @@ B200_HD void cols_fwd_body(Exec& ex, const ColsFwdParams& p, float2* smem) {
     using S = ColsSmem<N>;
     float2* E1 = smem;
     const int col0 = ex.bx() * S::COLS;
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, a = tid % P::LANES;
         const int col = col0 + jc;
         if (col < p.total_cols && a < P::R2) {
@@ -228,7 +282,7 @@ B200_HD void cols_fwd_body(Exec& ex, const ColsFwdParams& p, float2* smem) {
             P::stepA(v, a, E1 + jc * P::E_SIZE, p.tw);
         }
     });
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, b = tid % P::LANES;
         const int col = col0 + jc;
         if (col < p.total_cols && b < P::R1) {
@@ -374,6 +428,11 @@ struct ColsAccumParams {
     float2* partial;        // [nchunks][3][NC][N]
     const float2* tw;
     const float* img_max;   // [B]
+    // arg-max term of the amax backward, applied as  G' = G/m - coef * sum_t exp(-2 pi i (v ty + u tx)/N)
+    // on the channel that holds the tie (nullable: term left to the spatial tie_term kernel)
+    const float* coef;      // [B]
+    const int* tie_count;   // [B]
+    const int* tie_pos;     // [B][MAX_TIES]
     int B;
     int chunk;              // images per chunk
 };
@@ -395,13 +454,13 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
     const int b1 = (b0 + p.chunk < p.B) ? b0 + p.chunk : p.B;
     constexpr int TOTAL = 3 * T::NC;
 
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
         AccumState<N>& s = st[ex.slot(tid)];
 #pragma unroll
         for (int i = 0; i < P::R2; ++i) s.acc[i] = make_float2(0.f, 0.f);
     });
     for (int b = b0; b < b1; ++b) {
-        ex.phase([&](int tid) {
+        ex.warp_phase([&](int tid) {
             const int jc = tid / P::LANES, a = tid % P::LANES;
             const int cu = cu0 + jc;
             if (cu < TOTAL && a < P::R2) {
@@ -416,7 +475,7 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
                 P::stepA(v, a, Eg + jc * P::E_SIZE, p.tw);
             }
         });
-        ex.phase([&](int tid) {
+        ex.warp_phase([&](int tid) {
             const int jc = tid / P::LANES, bb = tid % P::LANES;
             const int cu = cu0 + jc;
             if (cu < TOTAL && bb < P::R1) {
@@ -426,15 +485,33 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
                 P::stepB(vx, bb, Ex + jc * P::E_SIZE);
                 P::stepB(vg, bb, Eg + jc * P::E_SIZE);
 #pragma unroll
+                for (int i = 0; i < P::R2; ++i) vg[i] = cscale(vg[i], inv_m);
+                if (p.coef != nullptr) {
+                    const int c = cu / T::NC, u = cu % T::NC;
+                    const int nt = p.tie_count[b] < MAX_TIES ? p.tie_count[b] : MAX_TIES;
+                    const float cf = ld_ro(p.coef + b);
+                    for (int t = 0; t < nt; ++t) {
+                        const int pos = p.tie_pos[b * MAX_TIES + t];
+                        if (pos / (N * N) != c) continue;
+                        const int ty = (pos % (N * N)) / N, tx = pos % N;
+                        const float2 pu = cscale(ld_ro(p.tw + ((u * tx) & (N - 1))), cf);
+#pragma unroll
+                        for (int i = 0; i < P::R2; ++i) {
+                            const int v = bb + P::R1 * i;
+                            vg[i] = csub(vg[i], cmul(pu, ld_ro(p.tw + ((v * ty) & (N - 1)))));
+                        }
+                    }
+                }
+#pragma unroll
                 for (int i = 0; i < P::R2; ++i) {
-                    const float2 t = cmulc(vg[i], vx[i]);   // G * conj(X)
-                    s.acc[i].x += t.x * inv_m;
-                    s.acc[i].y += t.y * inv_m;
+                    const float2 t = cmulc(vg[i], vx[i]);   // G' * conj(X)
+                    s.acc[i].x += t.x;
+                    s.acc[i].y += t.y;
                 }
             }
         });
     }
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, bb = tid % P::LANES;
         const int cu = cu0 + jc;
         if (cu < TOTAL && bb < P::R1) {
@@ -467,7 +544,7 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
     float2* E = smem;
     const int cu0 = ex.bx() * T::RCOLS;
     constexpr int TOTAL = 3 * T::NC;
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, b = tid % P::LANES;
         const int cu = cu0 + jc;
         if (cu < TOTAL && b < P::R1) {
@@ -488,7 +565,7 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
             P::stepC(v, b, E + jc * P::E_SIZE, p.tw);
         }
     });
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, a = tid % P::LANES;
         const int cu = cu0 + jc;
         if (cu < TOTAL && a < P::R2) {

@@ -123,14 +123,19 @@ class SensorConv(torch.autograd.Function):
         tie_count = torch.empty(B, dtype=torch.int32, device=plan.device)
         tie_pos = torch.empty(B, 8, dtype=torch.int32, device=plan.device)
         otf = torch.empty(plan.otf_floats, dtype=torch.float32, device=plan.device)
+        # keep the image spectra for the backward (what autograd would save) only when a gradient is wanted
+        spectrum = None
+        if B > 0 and any(ctx.needs_input_grad[:2]):
+            spectrum = torch.empty(plan.lib.b200cam_spectrum_bytes(N, B) // 4, dtype=torch.float32, device=plan.device)
         if B > 0:
             ws = plan.sensor_workspace(B)
             with torch.cuda.device(plan.index):
                 _lib.check(plan.lib.b200cam_sensor_fwd(
                     _lib.ptr(x), _lib.ptr(p), _lib.ptr(sensor), _lib.ptr(img_max), _lib.ptr(tie_count),
-                    _lib.ptr(tie_pos), _lib.ptr(otf), _lib.ptr(None), _lib.ptr(ws), ws.numel(), B, N, _stream()))
+                    _lib.ptr(tie_pos), _lib.ptr(otf), _lib.ptr(spectrum), _lib.ptr(ws), ws.numel(), B, N, _stream()))
         ctx.plan = plan
         ctx.psf_shape = psf.shape
+        ctx.spectrum = spectrum
         ctx.save_for_backward(x, p, sensor, img_max, tie_count, tie_pos, otf)
         return sensor
 
@@ -149,7 +154,8 @@ class SensorConv(torch.autograd.Function):
             with torch.cuda.device(plan.index):
                 _lib.check(plan.lib.b200cam_sensor_bwd(
                     _lib.ptr(gc), _lib.ptr(x), _lib.ptr(sensor), _lib.ptr(img_max), _lib.ptr(tie_count),
-                    _lib.ptr(tie_pos), _lib.ptr(p), _lib.ptr(otf), _lib.ptr(grad_psf), _lib.ptr(grad_img),
+                    _lib.ptr(tie_pos), _lib.ptr(p), _lib.ptr(otf), _lib.ptr(ctx.spectrum), _lib.ptr(grad_psf),
+                    _lib.ptr(grad_img),
                     _lib.ptr(ws), ws.numel(), B, N, _stream()))
         return grad_img, grad_psf.reshape(ctx.psf_shape), None
 

@@ -48,7 +48,7 @@ void otf_impl(const float* psf, float2* otf, const float2* tw) {
     using T = Tile<N>;
     std::vector<float2> smem(RowsR2CSmem<N>::FLOAT2S > ColsSmem<N>::FLOAT2S ? RowsR2CSmem<N>::FLOAT2S : ColsSmem<N>::FLOAT2S);
     grid2(N / T::ROWS, 3, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_r2c_body<N>(ex, RowsR2CParams{psf, otf, tw, nullptr, nullptr, nullptr, nullptr}, smem.data());
+        rows_r2c_body<N>(ex, RowsR2CParams{psf, otf, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, smem.data());
     });
     const int total = 3 * T::NC;
     grid2((total + T::COLS - 1) / T::COLS, 1, ColsSmem<N>::THREADS, [&](HostExec& ex) {
@@ -56,24 +56,35 @@ void otf_impl(const float* psf, float2* otf, const float2* tw) {
     });
 }
 
+int conv_chunk(int N, int B) {
+    const int colgroups = (3 * (N / 2 + 1) + 7) / 8;
+    int nchunks = (148 * 5 + colgroups - 1) / colgroups;
+    if (nchunks > B) nchunks = B;
+    return (B + nchunks - 1) / nchunks;
+}
+
 template <int N>
 int sensor_fwd_impl(int B, const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
-                    int* tie_pos, float2* otf) {
+                    int* tie_pos, float2* otf, float2* spectrum) {
     using T = Tile<N>;
     auto tw = make_twiddle(N);
     otf_impl<N>(psf, otf, tw.data());
     const int planes = 3 * B;
-    std::vector<float2> st(static_cast<size_t>(planes) * T::NC * N);
+    std::vector<float2> stx(static_cast<size_t>(planes) * T::NC * N), st2(static_cast<size_t>(planes) * T::NC * N);
+    float2* srow = spectrum != nullptr ? spectrum : stx.data();
     std::vector<float2> smem(RowsR2CSmem<N>::FLOAT2S > ColsSmem<N>::FLOAT2S ? RowsR2CSmem<N>::FLOAT2S : ColsSmem<N>::FLOAT2S);
     grid2(N / T::ROWS, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_r2c_body<N>(ex, RowsR2CParams{img, st.data(), tw.data(), nullptr, nullptr, img_max, tie_count}, smem.data());
+        rows_r2c_body<N>(ex, RowsR2CParams{img, srow, tw.data(), nullptr, nullptr, img_max, tie_count, nullptr, nullptr,
+                                           nullptr, nullptr}, smem.data());
     });
-    const int total = planes * T::NC;
-    grid2((total + T::COLS - 1) / T::COLS, 1, ColsSmem<N>::THREADS, [&](HostExec& ex) {
-        cols_conv_body<N>(ex, ColsConvParams{st.data(), st.data(), otf, tw.data(), nullptr, total, 0}, smem.data());
+    const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
+    const int chunk = conv_chunk(N, B);
+    std::vector<ConvState<N>> cst(ColsSmem<N>::THREADS);
+    grid2(colgroups, (B + chunk - 1) / chunk, ColsSmem<N>::THREADS, [&](HostExec& ex) {
+        cols_conv_body<N>(ex, ColsConvParams{srow, st2.data(), otf, tw.data(), nullptr, B, chunk, 0}, smem.data(), cst.data());
     });
     grid2(N / T::ROWS, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_c2r_body<N>(ex, RowsC2RParams{st.data(), sensor, tw.data(), img_max, 1.0f}, smem.data());
+        rows_c2r_body<N>(ex, RowsC2RParams{st2.data(), sensor, tw.data(), img_max, 1.0f}, smem.data());
     });
     const long long n4 = static_cast<long long>(planes) * N * N / 4;
     grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) {
@@ -84,8 +95,8 @@ int sensor_fwd_impl(int B, const float* img, const float* psf, float* sensor, fl
 
 template <int N>
 int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor, const float* img_max,
-                    const int* tie_count, const int* tie_pos, const float* psf, const float2* otf, float* grad_psf,
-                    float* grad_img) {
+                    const int* tie_count, const int* tie_pos, const float* psf, const float2* otf,
+                    const float2* spectrum, float* grad_psf, float* grad_img) {
     using T = Tile<N>;
     auto tw = make_twiddle(N);
     const int planes = 3 * B, tiles = N / T::ROWS;
@@ -96,18 +107,25 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
     const int used_chunks = (B + chunk - 1) / chunk;
     std::vector<float2> partial(static_cast<size_t>(nchunks) * 3 * plane_sz);
     std::vector<float> dot_partial(static_cast<size_t>(planes) * N), coef(B);
+    std::vector<int> arrive(B, 0);
     std::vector<float2> smem(RowsR2CSmem<N>::FLOAT2S > ColsSmem<N>::FLOAT2S ? RowsR2CSmem<N>::FLOAT2S : ColsSmem<N>::FLOAT2S);
+    const float2* srow = spectrum;
+    if (srow == nullptr) {
+        grid2(tiles, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
+            rows_r2c_body<N>(ex, RowsR2CParams{img, stx.data(), tw.data(), nullptr, nullptr, nullptr, nullptr, nullptr,
+                                               nullptr, nullptr, nullptr}, smem.data());
+        });
+        srow = stx.data();
+    }
     grid2(tiles, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_r2c_body<N>(ex, RowsR2CParams{img, stx.data(), tw.data(), nullptr, nullptr, nullptr, nullptr}, smem.data());
-    });
-    grid2(tiles, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_r2c_body<N>(ex, RowsR2CParams{g, stg.data(), tw.data(), sensor, dot_partial.data(), nullptr, nullptr}, smem.data());
+        rows_r2c_body<N>(ex, RowsR2CParams{g, stg.data(), tw.data(), sensor, dot_partial.data(), nullptr, nullptr,
+                                           arrive.data(), coef.data(), img_max, tie_count}, smem.data());
     });
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     std::vector<AccumState<N>> states(ColsSmem<N>::THREADS);
     grid2(colgroups, used_chunks, ColsSmem<N>::THREADS, [&](HostExec& ex) {
-        cols_accum_body<N>(ex, ColsAccumParams{stx.data(), stg.data(), partial.data(), tw.data(), img_max, B, chunk},
-                           smem.data(), states.data());
+        cols_accum_body<N>(ex, ColsAccumParams{srow, stg.data(), partial.data(), tw.data(), img_max, coef.data(),
+                                               tie_count, tie_pos, B, chunk}, smem.data(), states.data());
     });
     grid2((3 * T::NC + T::RCOLS - 1) / T::RCOLS, 1, T::RCOLS * Plan<N>::LANES, [&](HostExec& ex) {
         cols_reduce_inv_body<N>(ex, ColsReduceInvParams{partial.data(), stp.data(), tw.data(), used_chunks,
@@ -116,17 +134,12 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
     grid2(tiles, 3, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
         rows_c2r_body<N>(ex, RowsC2RParams{stp.data(), grad_psf, tw.data(), nullptr, 1.0f}, smem.data());
     });
-    TieTermParams tp{grad_psf, img, img_max, tie_count, tie_pos, dot_partial.data(), coef.data(), B, N, tiles};
-    grid2((B + EW_THREADS - 1) / EW_THREADS, 1, EW_THREADS, [&](HostExec& ex) { tie_coef_body(ex, tp, 1); });
-    std::vector<float> s_coef(TIE_PASS * MAX_TIES);
-    std::vector<int> s_meta(3 * TIE_PASS * MAX_TIES), s_cnt(TIE_PASS + 1);
-    grid2(EW_GRID, 3, EW_THREADS, [&](HostExec& ex) {
-        tie_term_body(ex, tp, EW_GRID, s_coef.data(), s_meta.data(), s_cnt.data());
-    });
     if (grad_img != nullptr) {
-        const int total = planes * T::NC;
-        grid2((total + T::COLS - 1) / T::COLS, 1, ColsSmem<N>::THREADS, [&](HostExec& ex) {
-            cols_conv_body<N>(ex, ColsConvParams{stg.data(), stg.data(), otf, tw.data(), img_max, total, 1}, smem.data());
+        const int cchunk = conv_chunk(N, B);
+        std::vector<ConvState<N>> cst(ColsSmem<N>::THREADS);
+        grid2(colgroups, (B + cchunk - 1) / cchunk, ColsSmem<N>::THREADS, [&](HostExec& ex) {
+            cols_conv_body<N>(ex, ColsConvParams{stg.data(), stg.data(), otf, tw.data(), img_max, B, cchunk, 1}, smem.data(),
+                              cst.data());
         });
         grid2(tiles, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
             rows_c2r_body<N>(ex, RowsC2RParams{stg.data(), grad_img, tw.data(), nullptr, 1.0f}, smem.data());
@@ -305,15 +318,17 @@ int emu_psf_bwd(int N, const float* gpsf, const float* gscal, const float* h, co
 }
 
 int emu_sensor_fwd(int N, int B, const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
-                   int* tie_pos, float* otf) {
-    DISPATCH_N(N, (sensor_fwd_impl<NN_>(B, img, psf, sensor, img_max, tie_count, tie_pos, reinterpret_cast<float2*>(otf))));
+                   int* tie_pos, float* otf, float* spectrum) {
+    DISPATCH_N(N, (sensor_fwd_impl<NN_>(B, img, psf, sensor, img_max, tie_count, tie_pos, reinterpret_cast<float2*>(otf),
+                                        reinterpret_cast<float2*>(spectrum))));
 }
 
 int emu_sensor_bwd(int N, int B, const float* g, const float* img, const float* sensor, const float* img_max,
-                   const int* tie_count, const int* tie_pos, const float* psf, const float* otf, float* grad_psf,
-                   float* grad_img) {
+                   const int* tie_count, const int* tie_pos, const float* psf, const float* otf, const float* spectrum,
+                   float* grad_psf, float* grad_img) {
     DISPATCH_N(N, (sensor_bwd_impl<NN_>(B, g, img, sensor, img_max, tie_count, tie_pos, psf,
-                                        reinterpret_cast<const float2*>(otf), grad_psf, grad_img)));
+                                        reinterpret_cast<const float2*>(otf), reinterpret_cast<const float2*>(spectrum),
+                                        grad_psf, grad_img)));
 }
 
 }  // extern "C"

@@ -73,25 +73,28 @@ def psf_bwd(gpsf, gscal, h, tables, psf, field, stats):
     return gh
 
 
-def sensor_fwd(img, psf):
+def sensor_fwd(img, psf, save_spectrum=False):
     B, _, N, _ = img.shape
     sensor = torch.empty_like(img)
     img_max = torch.empty(B)
     tie_count = torch.zeros(B, dtype=torch.int32)
     tie_pos = torch.zeros(B, 8, dtype=torch.int32)
     otf = torch.empty(3, N // 2 + 1, N, 2)
+    spectrum = torch.empty(3 * B, N // 2 + 1, N, 2) if save_spectrum else None
     rc = lib().emu_sensor_fwd(N, B, _p(img.contiguous()), _p(psf.contiguous()), _p(sensor), _p(img_max),
-                              _p(tie_count), _p(tie_pos), _p(otf))
+                              _p(tie_count), _p(tie_pos), _p(otf), _p(spectrum))
     assert rc == 0
+    if save_spectrum:
+        return sensor, img_max, tie_count, tie_pos, otf, spectrum
     return sensor, img_max, tie_count, tie_pos, otf
 
 
-def sensor_bwd(g, img, sensor, img_max, tie_count, tie_pos, psf, otf, want_img_grad=False):
+def sensor_bwd(g, img, sensor, img_max, tie_count, tie_pos, psf, otf, want_img_grad=False, spectrum=None):
     B, _, N, _ = img.shape
     gpsf = torch.empty(3, N, N)
     gimg = torch.empty_like(img) if want_img_grad else None
     rc = lib().emu_sensor_bwd(N, B, _p(g.contiguous()), _p(img.contiguous()), _p(sensor), _p(img_max), _p(tie_count),
-                              _p(tie_pos), _p(psf.contiguous()), _p(otf), _p(gpsf), _p(gimg))
+                              _p(tie_pos), _p(psf.contiguous()), _p(otf), _p(spectrum), _p(gpsf), _p(gimg))
     assert rc == 0
     return gpsf, gimg
 

@@ -28,10 +28,12 @@ def test_emulated_pipeline_matches_golden(name):
     assert rel_l2(psf, gold["psf"][0]) <= 1e-5
     assert abs(stats[1].item() - gold["loss_rad"].item()) <= 1e-5 * gold["loss_rad"].item()
     assert abs(stats[2].item() - gold["centering_loss"].item()) <= 1e-4 * gold["centering_loss"].item()
-    sensor, m, tc, tp, otf = emu.sensor_fwd(gold["img"], psf)
+    sensor, m, tc, tp, otf, spec = emu.sensor_fwd(gold["img"], psf, save_spectrum=True)
     assert rel_l2(sensor, gold["sensor"]) <= 1e-5
     assert tc.tolist() == [1] * gold["B"]
-    gpsf, _ = emu.sensor_bwd(gold["w"], gold["img"], sensor, m, tc, tp, psf, otf)
+    gpsf, _ = emu.sensor_bwd(gold["w"], gold["img"], sensor, m, tc, tp, psf, otf, spectrum=spec)   # saved row spectra
+    gpsf2, _ = emu.sensor_bwd(gold["w"], gold["img"], sensor, m, tc, tp, psf, otf)                # recomputed
+    assert rel_l2(gpsf2, gpsf) <= 1e-6
     gh = emu.psf_bwd(gpsf, torch.tensor([1.0, 1.0]), gold["h"][0], T, psf, field, stats)
     assert rel_l2(gh, gold["grad_h"][0]) <= 1e-4
 
