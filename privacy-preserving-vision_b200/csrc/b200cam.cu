@@ -1,5 +1,6 @@
 // b200cam: __global__ wrappers, launch sequencing and the C ABI (include/b200cam.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -90,8 +91,13 @@ __global__ void __launch_bounds__(EW_THREADS) k_reduce(ReduceParams p) {
     DeviceExec ex;
     reduce_body(ex, p, red);
 }
+template <int N>
+__global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad(CRowsInvParams p, PupilLoad pupil, float* gh) {
+    DeviceExec ex;
+    crows_inv_hgrad_body<N>(ex, p, pupil, gh, SMEM2);
+}
 __global__ void __launch_bounds__(EW_THREADS) k_psf_finalise(PsfFinaliseParams p) {
-    __shared__ float red[3 * EW_THREADS];
+    __shared__ float red[3 * EW_THREADS + 2];
     DeviceExec ex;
     psf_finalise_body(ex, p, gridDim.x, red);
 }
@@ -113,6 +119,91 @@ __global__ void __launch_bounds__(f256::THREADS, 1) k_f256_fwd(f256::FwdParams p
     f256::FState st;
     f256::fwd_body(ex, p, SMEM2, gridDim.x, &st);
 }
+// ------------------------------------------------------------------------------------------
+// PSF chain as ONE cooperative launch per direction: the same bodies, run as virtual blocks, with
+// grid-wide barriers where the multi-kernel version had kernel boundaries.
+// ------------------------------------------------------------------------------------------
+constexpr int COOP_THREADS = 384;   // >= the widest body (3 wavelength groups of the N=1024 row pass)
+
+struct PsfFwdArgs {
+    CRowsFwdParams rows_fwd; PupilLoad pupil;
+    CColsMixParams mix;
+    CRowsInvParams rows_inv; IntensityEpilogue inten;
+    PsfFinaliseParams fin;
+};
+
+template <int N>
+__global__ void __launch_bounds__(COOP_THREADS) k_psf_fwd_coop(PsfFwdArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float red[3 * EW_THREADS + 2];
+    using T = Tile<N>;
+    const int G = gridDim.x;
+    for (int vb = blockIdx.x; vb < 3 * (N / T::CROWS); vb += G) {
+        VirtualExec ex{vb % (N / T::CROWS), vb / (N / T::CROWS), CRowsSmem<N>::THREADS};
+        crows_fwd_body<N>(ex, a.rows_fwd, a.pupil, SMEM2);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < (N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC; vb += G) {
+        VirtualExec ex{vb, 0, CColsSmem<N>::THREADS};
+        ccols_mix_body<N>(ex, a.mix, SMEM2);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < 3 * (N / T::CROWS); vb += G) {
+        VirtualExec ex{vb % (N / T::CROWS), vb / (N / T::CROWS), CRowsSmem<N>::THREADS};
+        crows_inv_body<N>(ex, a.rows_inv, a.inten, SMEM2);
+    }
+    grid.sync();
+    {
+        VirtualExec ex{static_cast<int>(blockIdx.x), 0, EW_THREADS};
+        psf_finalise_body(ex, a.fin, G, red);
+    }
+}
+
+struct PsfBwdArgs {
+    PsfGradPrepParams prep;
+    CRowsFwdParams rows_fwd; GradFieldLoad gload;
+    CColsMixParams mix;
+    CRowsInvParams rows_inv; PupilLoad pupil; float* gh;
+};
+
+template <int N>
+__global__ void __launch_bounds__(COOP_THREADS) k_psf_bwd_coop(PsfBwdArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float red[3 * EW_THREADS + 2];
+    using T = Tile<N>;
+    const int G = gridDim.x;
+    {
+        VirtualExec ex{static_cast<int>(blockIdx.x), 0, EW_THREADS};
+        psf_grad_prepare_body(ex, a.prep, G, red);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < 3 * (N / T::CROWS); vb += G) {
+        VirtualExec ex{vb % (N / T::CROWS), vb / (N / T::CROWS), CRowsSmem<N>::THREADS};
+        crows_fwd_body<N>(ex, a.rows_fwd, a.gload, SMEM2);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < (N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC; vb += G) {
+        VirtualExec ex{vb, 0, CColsSmem<N>::THREADS};
+        ccols_mix_body<N>(ex, a.mix, SMEM2);
+    }
+    grid.sync();
+    for (int vb = blockIdx.x; vb < N / T::CROWS; vb += G) {
+        VirtualExec ex{vb, 0, HGradSmem<N>::THREADS};
+        crows_inv_hgrad_body<N>(ex, a.rows_inv, a.pupil, a.gh, SMEM2);
+    }
+}
+
+template <int N>
+constexpr int coop_smem_bytes() {
+    return HGradSmem<N>::BYTES > CColsSmem<N>::BYTES ? HGradSmem<N>::BYTES : CColsSmem<N>::BYTES;
+}
+static_assert(HGradSmem<1024>::BYTES <= 227 * 1024 && HGradSmem<512>::BYTES <= 227 * 1024 && CColsSmem<1024>::BYTES <= 227 * 1024,
+              "shared memory budget");
+static_assert(HGradSmem<1024>::THREADS <= COOP_THREADS && HGradSmem<512>::THREADS <= COOP_THREADS && CColsSmem<1024>::THREADS <= COOP_THREADS && EW_THREADS <= COOP_THREADS,
+              "cooperative block too small for a body");
+
 __global__ void k_fill_twiddle(float2* tw, int N) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < N) {
@@ -129,7 +220,7 @@ constexpr int MAX_DEV = 64;
 constexpr int EW_GRID = 296;   // 2 x 148 SMs for the element-wise / reduction kernels
 
 inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
-struct DeviceState { float2* tw[11] = {nullptr}; int sms = 0; };
+struct DeviceState { float2* tw[11] = {nullptr}; int sms = 0; int coop_grid[11] = {0}; };
 static DeviceState g_state[MAX_DEV];
 static std::mutex g_mutex;
 
@@ -137,6 +228,21 @@ static int sm_count() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 0;
     return g_state[dev].sms;
+}
+// The PSF chain is a dozen tiny dependent kernels.  Launched eagerly, one cooperative kernel with grid-wide
+// barriers is faster (measured 346 vs 405 us per step); replayed from a CUDA graph the kernel boundaries are
+// cheaper than the grid barriers (284 vs 314 us).  So: cooperative unless the stream is being captured.
+// B200CAM_COOP=0/1 forces one or the other.
+static int coop_grid(int N, cudaStream_t s) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 0;
+    static const int mode = [] { const char* e = getenv("B200CAM_COOP"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    if (mode == 0) return 0;
+    if (mode < 0) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return 0;
+    }
+    return g_state[dev].coop_grid[log2i(N)];
 }
 static bool fused_enabled() {
     static const bool on = [] { const char* e = getenv("B200CAM_FUSED"); return e && e[0] == '1'; }();   // experimental, off by default
@@ -166,8 +272,26 @@ static cudaError_t init_kernels() {
     if ((e = optin(k_crows_fwd<N, PupilLoad>, CRowsSmem<N>::BYTES))) return e;
     if ((e = optin(k_crows_fwd<N, GradFieldLoad>, CRowsSmem<N>::BYTES))) return e;
     if ((e = optin(k_crows_inv<N, IntensityEpilogue>, CRowsSmem<N>::BYTES))) return e;
-    if ((e = optin(k_crows_inv<N, HeightGradEpilogue>, CRowsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_crows_inv_hgrad<N>, HGradSmem<N>::BYTES))) return e;
     if ((e = optin(k_ccols_mix<N>, CColsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_psf_fwd_coop<N>, coop_smem_bytes<N>()))) return e;
+    if ((e = optin(k_psf_bwd_coop<N>, coop_smem_bytes<N>()))) return e;
+    return cudaSuccess;
+}
+
+// largest co-resident grid of the cooperative PSF kernels, capped at the useful number of virtual blocks
+template <int N>
+static cudaError_t coop_grid_size(int dev, int sms, int* out) {
+    int coop = 0, nb_f = 0, nb_b = 0;
+    cudaError_t e;
+    if ((e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev))) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_f, k_psf_fwd_coop<N>, COOP_THREADS, coop_smem_bytes<N>()))) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_b, k_psf_bwd_coop<N>, COOP_THREADS, coop_smem_bytes<N>()))) return e;
+    const int nb = nb_f < nb_b ? nb_f : nb_b;
+    int g = coop ? sms * nb : 0;
+    const int useful = 3 * (N / Tile<N>::CROWS);
+    if (g > useful) g = useful;
+    *out = g;
     return cudaSuccess;
 }
 
@@ -202,7 +326,7 @@ static int conv_chunk(int N, int B) {      // images per CTA of the persistent c
 }
 
 struct PsfWs {
-    float2* st; float* I; float* gtot; float* gh3; float* part_rows; float* part_ew;
+    float2* st; float* I; float* gtot; float* gh3; float* part_rows; float* part_ew; int* arrive;
     size_t bytes;
     PsfWs(void* p, int N) {
         Carver c(p);
@@ -212,7 +336,8 @@ struct PsfWs {
         gtot = c.take<float>(3 * NN);
         gh3 = c.take<float>(3 * NN);
         part_rows = c.take<float>(3 * N);
-        part_ew = c.take<float>(3 * EW_GRID);
+        part_ew = c.take<float>(3 * 1024);          // element-wise partials: grid <= 1024 CTAs
+        arrive = c.take<int>(1);
         bytes = c.off;
     }
 };
@@ -273,20 +398,28 @@ static int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     PsfWs ws(ws_ptr, N);
     PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
+    const int nrow = 3 * (N / T::CROWS);
+    CRowsFwdParams rf{ws.st, tw};
+    CColsMixParams mix{ws.st, Ht, tw, 0, 1.0f / (3.0f * N * N)};
+    CRowsInvParams ri{ws.st, tw};
+    IntensityEpilogue epi{field, ws.I, ws.part_rows, ws.arrive, N};
+    PsfFinaliseParams fin{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, nrow, N};
+    if (const int G = coop_grid(N, s)) {
+        PsfFwdArgs args{rf, load, mix, ri, epi, fin};
+        void* kargs[] = {&args};
+        CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_psf_fwd_coop<N>), dim3(G), dim3(COOP_THREADS), kargs,
+                                       coop_smem_bytes<N>(), s));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     const dim3 rgrid(N / T::CROWS, 3);
-    k_crows_fwd<N, PupilLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsFwdParams{ws.st, tw}, load);
+    k_crows_fwd<N, PupilLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(rf, load);
     LAUNCH_CHECK();
-    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(
-        CColsMixParams{ws.st, Ht, tw, 0, 1.0f / (3.0f * N * N)});
+    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(mix);
     LAUNCH_CHECK();
-    IntensityEpilogue epi{field, ws.I, ws.part_rows, N};
-    k_crows_inv<N, IntensityEpilogue><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsInvParams{ws.st, tw}, epi);
+    k_crows_inv<N, IntensityEpilogue><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(ri, epi);
     LAUNCH_CHECK();
-    k_reduce<<<1, EW_THREADS, 0, s>>>(ReduceParams{ws.part_rows, stats, 3 * (N / T::CROWS), 0, N});
-    LAUNCH_CHECK();
-    k_psf_finalise<<<EW_GRID, EW_THREADS, 0, s>>>(PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, N});
-    LAUNCH_CHECK();
-    k_reduce<<<1, EW_THREADS, 0, s>>>(ReduceParams{ws.part_ew, stats, EW_GRID, 1, N});
+    k_psf_finalise<<<EW_GRID, EW_THREADS, 0, s>>>(fin);
     LAUNCH_CHECK();
     return 0;
 }
@@ -299,21 +432,27 @@ static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, c
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     PsfWs ws(ws_ptr, N);
+    PupilLoad pupil{A, h, {kappa[0], kappa[1], kappa[2]}, N};
+    CRowsFwdParams rf{ws.st, tw};
+    CColsMixParams mix{ws.st, Ht, tw, 1, 1.0f / (3.0f * N * N)};
+    CRowsInvParams ri{ws.st, tw};
+    if (const int G = coop_grid(N, s)) {
+        PsfBwdArgs args{PsfGradPrepParams{gpsf, gscal, psf, rho, stats, ws.gtot, ws.part_ew, N}, rf,
+                        GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, G, N}, mix, ri, pupil, grad_h};
+        void* kargs[] = {&args};
+        CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_psf_bwd_coop<N>), dim3(G), dim3(COOP_THREADS), kargs,
+                                       coop_smem_bytes<N>(), s));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     k_psf_grad_prepare<<<EW_GRID, EW_THREADS, 0, s>>>(PsfGradPrepParams{gpsf, gscal, psf, rho, stats, ws.gtot, ws.part_ew, N});
     LAUNCH_CHECK();
-    k_reduce<<<1, EW_THREADS, 0, s>>>(ReduceParams{ws.part_ew, stats, EW_GRID, 2, N});
+    k_crows_fwd<N, GradFieldLoad><<<dim3(N / T::CROWS, 3), CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(
+        rf, GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, EW_GRID, N});
     LAUNCH_CHECK();
-    const dim3 rgrid(N / T::CROWS, 3);
-    GradFieldLoad load{field, ws.gtot, stats, N};
-    k_crows_fwd<N, GradFieldLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsFwdParams{ws.st, tw}, load);
+    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(mix);
     LAUNCH_CHECK();
-    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(
-        CColsMixParams{ws.st, Ht, tw, 1, 1.0f / (3.0f * N * N)});
-    LAUNCH_CHECK();
-    HeightGradEpilogue epi{PupilLoad{A, h, {kappa[0], kappa[1], kappa[2]}, N}, ws.gh3, N};
-    k_crows_inv<N, HeightGradEpilogue><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsInvParams{ws.st, tw}, epi);
-    LAUNCH_CHECK();
-    k_sum3<<<EW_GRID, EW_THREADS, 0, s>>>(Sum3Params{ws.gh3, grad_h, N * N});
+    k_crows_inv_hgrad<N><<<N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s>>>(ri, pupil, grad_h);
     LAUNCH_CHECK();
     return 0;
 }
@@ -484,7 +623,21 @@ int b200cam_init(int N) {
     }
     if (e == cudaSuccess && N == 256) e = optin(k_f256_fwd, f256::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_state[dev].sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) { cudaFree(tw); return static_cast<int>(e); }
+    if (e == cudaSuccess) {
+        const int sms = g_state[dev].sms;
+        switch (N) {
+            case 64: e = coop_grid_size<64>(dev, sms, &g_state[dev].coop_grid[l]); break;
+            case 128: e = coop_grid_size<128>(dev, sms, &g_state[dev].coop_grid[l]); break;
+            case 256: e = coop_grid_size<256>(dev, sms, &g_state[dev].coop_grid[l]); break;
+            case 512: e = coop_grid_size<512>(dev, sms, &g_state[dev].coop_grid[l]); break;
+            case 1024: e = coop_grid_size<1024>(dev, sms, &g_state[dev].coop_grid[l]); break;
+        }
+    }
+    if (e != cudaSuccess) {
+        cudaFree(tw);
+        (void)cudaGetLastError();          // do not leave a sticky error behind for later launches
+        return static_cast<int>(e);
+    }
     g_state[dev].tw[l] = tw;
     return 0;
 }

@@ -34,6 +34,29 @@ struct DeviceExec {
     __device__ __forceinline__ float load_cg(const float* p) { return __ldcg(p); }
     __device__ __forceinline__ float4 load_cg4(const float4* p) { return __ldcg(p); }
 };
+// A "virtual block" of a cooperative kernel: the CTA plays block (vbx, vby) of a body written for
+// `nthr` threads; surplus threads only take part in the barriers.
+struct VirtualExec {
+    int vbx, vby, nthr;
+    __device__ __forceinline__ int bx() const { return vbx; }
+    __device__ __forceinline__ int by() const { return vby; }
+    __device__ __forceinline__ int nthreads() const { return nthr; }
+    __device__ __forceinline__ int slot(int) const { return 0; }
+    template <class F>
+    __device__ __forceinline__ void phase(F&& f) {
+        if (static_cast<int>(threadIdx.x) < nthr) f(static_cast<int>(threadIdx.x));
+        __syncthreads();
+    }
+    template <class F>
+    __device__ __forceinline__ void warp_phase(F&& f) {
+        if (static_cast<int>(threadIdx.x) < nthr) f(static_cast<int>(threadIdx.x));
+        __syncwarp();
+    }
+    __device__ __forceinline__ void barrier() { __syncthreads(); }
+    __device__ __forceinline__ void threadfence() { __threadfence(); }
+    __device__ __forceinline__ float load_cg(const float* p) { return __ldcg(p); }
+    __device__ __forceinline__ float4 load_cg4(const float4* p) { return __ldcg(p); }
+};
 #endif
 
 struct HostExec {

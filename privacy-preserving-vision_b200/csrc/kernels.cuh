@@ -25,7 +25,7 @@ struct Tile {
     static constexpr int FP_PAIR = N + 16 / NP;        // natural-order smem row pitch (float2)
     static constexpr int FP_ROW = N + 16 / ROWS;
     static constexpr int COLS = 8;                     // spectral columns per CTA in column passes
-    static constexpr int CROWS = 4;                    // rows per CTA in the complex (PSF chain) row passes
+    static constexpr int CROWS = (N >= 1024) ? 2 : 4;  // rows per CTA in the complex (PSF chain) row passes
     static constexpr int FP_CROW = N + 16 / CROWS;
     static constexpr int RCOLS = 2;                    // columns per CTA in the small batch-independent column passes
 };
@@ -716,6 +716,9 @@ struct PupilLoad {     // V = A * exp(i*kappa_l*h)   (Optics.py:89-100)
     const float* h;    // [N][N]
     float kappa[3];
     int N;
+    B200_HD void bind(float*) {}
+    template <class Exec>
+    B200_HD void prologue(Exec&, float*) const {}
     B200_HD float2 operator()(int l, int y, int x) const {
         const size_t i = static_cast<size_t>(y) * N + x;
         const float phi = kappa[l] * ld_ro(h + i);
@@ -730,13 +733,33 @@ struct PupilLoad {     // V = A * exp(i*kappa_l*h)   (Optics.py:89-100)
 };
 
 struct GradFieldLoad {  // GU = 2 * (gtot - dot)/S * U      (adjoint of |U|^2 / sum, Optics.py:109-110)
-    const float2* U;    // [3][N][N]
-    const float* gtot;  // [3][N][N]
-    const float* scal;  // device scalars: [0]=S, [3]=dot
+    const float2* U;       // [3][N][N]
+    const float* gtot;     // [3][N][N]
+    const float* scal;     // device scalars: [0]=S
+    const float* partial;  // [npartial] partial sums of gtot*psf written by psf_grad_prepare
+    float* dot_smem;       // one float of shared memory: dot = sum(partial), reduced by every CTA in the same order
+    int npartial;
     int N;
+    B200_HD void bind(float* scratch) { dot_smem = scratch; }
+    template <class Exec>
+    B200_HD void prologue(Exec& ex, float* red) const {
+        const int nt = ex.nthreads();
+        ex.phase([&](int tid) {
+            float acc = 0.f;
+            for (int i = tid; i < npartial; i += nt) acc += partial[i];
+            red[tid] = acc;
+        });
+        ex.phase([&](int tid) {
+            if (tid == 0) {
+                float s = 0.f;
+                for (int t = 0; t < nt; ++t) s += red[t];
+                *dot_smem = s;
+            }
+        });
+    }
     B200_HD float2 operator()(int l, int y, int x) const {
         const size_t i = (static_cast<size_t>(l) * N + y) * N + x;
-        const float gi = 2.0f * (ld_ro(gtot + i) - ld_ro(scal + 3)) / ld_ro(scal + 0);
+        const float gi = 2.0f * (ld_ro(gtot + i) - *dot_smem) / ld_ro(scal + 0);
         return cscale(ld_ro(U + i), gi);
     }
 };
@@ -750,7 +773,7 @@ struct CRowsSmem {
     static constexpr int E_OFF = 0;
     static constexpr int F_OFF = T::CROWS * P::E_SIZE;
     static constexpr int RED_OFF = F_OFF + T::CROWS * T::FP_CROW;
-    static constexpr int FLOAT2S = RED_OFF + THREADS;   // 2 floats per thread of scratch
+    static constexpr int FLOAT2S = RED_OFF + THREADS + 2;   // 2 floats per thread of scratch + 2 scalars
     static constexpr int BYTES = FLOAT2S * 8;
 };
 
@@ -760,7 +783,7 @@ struct CRowsFwdParams {
 };
 
 template <int N, class Load, class Exec>
-B200_HD void crows_fwd_body(Exec& ex, const CRowsFwdParams& p, const Load& load, float2* smem) {
+B200_HD void crows_fwd_body(Exec& ex, const CRowsFwdParams& p, Load load, float2* smem) {
     using P = Plan<N>;
     using T = Tile<N>;
     using S = CRowsSmem<N>;
@@ -768,6 +791,8 @@ B200_HD void crows_fwd_body(Exec& ex, const CRowsFwdParams& p, const Load& load,
     const int y0 = tile * T::CROWS;
     float2* E = smem + S::E_OFF;
     float2* F = smem + S::F_OFF;
+    load.bind(reinterpret_cast<float*>(smem + S::RED_OFF) + S::THREADS);
+    load.prologue(ex, reinterpret_cast<float*>(smem + S::RED_OFF));
     ex.phase([&](int tid) {
         const int j = tid / P::LANES, a = tid % P::LANES;
         if (a < P::R2) {
@@ -915,6 +940,7 @@ struct IntensityEpilogue {
     float2* U;          // [3][N][N]
     float* I;           // [3][N][N]
     float* partial;     // [3][N/CROWS]
+    int* arrive;        // counter of psf_finalise, zeroed here (it runs next in the stream)
     int N;
     B200_HD float operator()(int l, int y, int x, float2 v) const {
         const size_t i = (static_cast<size_t>(l) * N + y) * N + x;
@@ -923,7 +949,10 @@ struct IntensityEpilogue {
         I[i] = in;
         return in;
     }
-    B200_HD void finish(int l, int tile, int tiles, float s) const { partial[l * tiles + tile] = s; }
+    B200_HD void finish(int l, int tile, int tiles, float s) const {
+        partial[l * tiles + tile] = s;
+        if (l == 0 && tile == 0) *arrive = 0;
+    }
 };
 
 // backward epilogue: dL/dh contribution of one wavelength: kappa_l * Im(GV * conj(V)), V recomputed
@@ -985,6 +1014,81 @@ B200_HD void crows_inv_body(Exec& ex, const CRowsInvParams& p, const Epi& epi, f
     });
 }
 
+// P3b crows_inv_hgrad : the backward's last stage.  grid (N/CROWS), block 3*CROWS*LANES.  The three
+//      wavelengths of a row tile are three thread groups of one CTA; kappa_l * Im(GV_l conj V_l) is summed
+//      over l through shared memory in fixed order, so dL/dh is written once (sum over wavelengths of
+//      Optics.py:89-90's adjoint) - no per-wavelength planes, no extra pass.
+template <int N>
+struct HGradSmem {
+    using C = CRowsSmem<N>;
+    static constexpr int THREADS = 3 * C::THREADS;
+    static constexpr int PART = C::FLOAT2S;                                 // float2 per wavelength group
+    static constexpr int SUM_OFF = 3 * PART;                                // [2][CROWS][N] floats
+    static constexpr int FLOAT2S = SUM_OFF + Tile<N>::CROWS * N;            // 2 * CROWS*N floats
+    static constexpr int BYTES = FLOAT2S * 8;
+};
+
+template <int N, class Exec>
+B200_HD void crows_inv_hgrad_body(Exec& ex, const CRowsInvParams& p, const PupilLoad& pupil, float* gh, float2* smem) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = CRowsSmem<N>;
+    using H = HGradSmem<N>;
+    const int tile = ex.bx();
+    const int y0 = tile * T::CROWS;
+    float* sum = reinterpret_cast<float*>(smem + H::SUM_OFF);      // partial sums of wavelengths 1 and 2
+    ex.phase([&](int tid) {
+        const int l = tid / S::THREADS, t = tid % S::THREADS;
+        float2* F = smem + l * H::PART + S::F_OFF;
+        for (int w = t; w < T::CROWS * N; w += S::THREADS) {
+            const int u = w / T::CROWS, j = w % T::CROWS;
+            F[j * T::FP_CROW + u] = ld_ro(p.st + (static_cast<size_t>(l) * N + u) * N + y0 + j);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int l = tid / S::THREADS, t = tid % S::THREADS;
+        const int j = t / P::LANES, b = t % P::LANES;
+        float2* F = smem + l * H::PART + S::F_OFF;
+        float2* E = smem + l * H::PART + S::E_OFF;
+        if (b < P::R1) {
+            float2 v[P::R2];
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) v[i] = F[j * T::FP_CROW + b + P::R1 * i];
+            P::stepC(v, b, E + j * P::E_SIZE, p.tw);
+        }
+    });
+    ex.phase([&](int tid) {
+        const int l = tid / S::THREADS, t = tid % S::THREADS;
+        const int j = t / P::LANES, a = t % P::LANES;
+        const float2* E = smem + l * H::PART + S::E_OFF;
+        if (a < P::R2) {
+            float2 v[P::R1];
+            P::stepD(v, a, E + j * P::E_SIZE);
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) {
+                const int x = P::R2 * i + a;
+                const float2 pv = pupil(l, y0 + j, x);
+                const float g = pupil.kappa[l] * cmulc(v[i], pv).y;
+                if (l > 0) sum[((l - 1) * T::CROWS + j) * N + x] = g;
+                else v[i].x = g;
+            }
+            if (l == 0) {
+                // keep wavelength 0 in registers across the barrier through the group's own E buffer
+                float* keep = reinterpret_cast<float*>(smem + S::F_OFF);      // F of group 0 is free now
+#pragma unroll
+                for (int i = 0; i < P::R1; ++i) keep[j * N + P::R2 * i + a] = v[i].x;
+            }
+        }
+    });
+    ex.phase([&](int tid) {
+        const float* keep = reinterpret_cast<const float*>(smem + S::F_OFF);
+        for (int w = tid; w < T::CROWS * N; w += H::THREADS) {
+            const int j = w / N, x = w % N;
+            gh[static_cast<size_t>(y0 + j) * N + x] = (keep[w] + sum[w]) + sum[T::CROWS * N + w];
+        }
+    });
+}
+
 // ---------------------------------------------------------------------------------------------
 // small element-wise / reduction bodies of the PSF chain.  Device scalars `scal`:
 //   [0] S = sum |U|^2   [1] loss_rad   [2] centering_loss   [3] dot = sum(gtot * psf)
@@ -1032,17 +1136,37 @@ B200_HD void reduce_body(Exec& ex, const ReduceParams& p, float* red) {
 struct PsfFinaliseParams {
     const float* I;        // [3][N][N]
     const float* rho;      // [N][N]
-    const float* scal;
+    float* scal;           // out: [0]=S, [1]=loss_rad, [2]=centering_loss
     float* psf;            // [3][N][N]
     float* partial;        // [3 sets][grid]
+    const float* row_partial;  // [nrow] partial sums of |U|^2 from the inverse row pass
+    int* arrive;           // one counter, zero on entry, reset to zero by the last CTA
+    int nrow;
     int N;
 };
 
 template <class Exec>
 B200_HD void psf_finalise_body(Exec& ex, const PsfFinaliseParams& p, int grid_x, float* red) {
     const int N = p.N, NN = N * N, total = 3 * NN;
+    // S = sum |U|^2: every CTA adds the same partials in the same order (deterministic, no extra launch)
     ex.phase([&](int tid) {
-        const float S = p.scal[0];
+        float acc = 0.f;
+        for (int i = tid; i < p.nrow; i += EW_THREADS) acc += p.row_partial[i];
+        red[tid] = acc;
+    });
+    for (int half = EW_THREADS / 2; half > 0; half /= 2) {
+        ex.phase([&](int tid) {
+            if (tid < half) red[tid] += red[tid + half];
+        });
+    }
+    ex.phase([&](int tid) {
+        if (tid == 0) {
+            red[3 * EW_THREADS] = red[0];
+            if (ex.bx() == 0) p.scal[0] = red[0];
+        }
+    });
+    ex.phase([&](int tid) {
+        const float S = red[3 * EW_THREADS];
         float r2 = 0.f, cy = 0.f, cx = 0.f;
         const int stride = grid_x * EW_THREADS;
         for (int idx = ex.bx() * EW_THREADS + tid; idx < total; idx += stride) {
@@ -1067,6 +1191,37 @@ B200_HD void psf_finalise_body(Exec& ex, const PsfFinaliseParams& p, int grid_x,
     ex.phase([&](int tid) {
         if (tid < 3) p.partial[tid * grid_x + ex.bx()] = red[tid * EW_THREADS];
     });
+    // the last CTA to arrive turns the partials into the two regulariser values (Optics.py:113, :124-125)
+    ex.phase([&](int tid) {
+        if (tid == 0) {
+            ex.threadfence();
+            const int old = atomic_add_int(p.arrive, 1);
+            red[3 * EW_THREADS + 1] = (old == grid_x - 1) ? 1.f : 0.f;
+        }
+    });
+    if (red[3 * EW_THREADS + 1] != 0.f) {
+        ex.phase([&](int tid) {
+            ex.threadfence();
+            for (int s = 0; s < 3; ++s) {
+                float acc = 0.f;
+                for (int i = tid; i < grid_x; i += EW_THREADS) acc += ex.load_cg(p.partial + s * grid_x + i);
+                red[s * EW_THREADS + tid] = acc;
+            }
+        });
+        for (int half = EW_THREADS / 2; half > 0; half /= 2) {
+            ex.phase([&](int tid) {
+                if (tid < half)
+                    for (int s = 0; s < 3; ++s) red[s * EW_THREADS + tid] += red[s * EW_THREADS + tid + half];
+            });
+        }
+        ex.phase([&](int tid) {
+            if (tid == 0) {
+                p.scal[1] = sqrtf(red[0]);
+                p.scal[2] = red[EW_THREADS] / (3.0f * N * N) + red[2 * EW_THREADS] / (3.0f * N * N);
+                *p.arrive = 0;
+            }
+        });
+    }
 }
 
 // Q1  psf_grad_prepare: gtot = gpsf + g_rad * d loss_rad/dpsf + g_cen * d centering/dpsf ; partial sum(gtot*psf)

@@ -102,10 +102,8 @@ class PsfSynth(torch.autograd.Function):
                 plan.kappa, _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(grad_h),
                 _lib.ptr(ws), ws.numel(), N, _stream()))
         if plan.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(grad_h, op=dist.ReduceOp.SUM, group=plan.process_group)
-            if plan.average_grads:
-                grad_h /= dist.get_world_size(plan.process_group)
+            from .parallel import allreduce_height_grad
+            allreduce_height_grad(grad_h, plan.process_group, plan.average_grads)
         return grad_h.reshape(ctx.h_shape), None
 
 

@@ -153,9 +153,9 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
 
 struct PsfBuffers {
     std::vector<float2> st;
-    std::vector<float> I, gtot, gh3, part_rows, part_ew;
-    explicit PsfBuffers(int N)
-        : st(3 * N * N), I(3 * N * N), gtot(3 * N * N), gh3(3 * N * N), part_rows(3 * N), part_ew(3 * EW_GRID) {}
+    std::vector<float> I, gtot, part_rows, part_ew;
+    int arrive = 12345;     // deliberately dirty: the pipeline must zero it itself
+    explicit PsfBuffers(int N) : st(3 * N * N), I(3 * N * N), gtot(3 * N * N), part_rows(3 * N), part_ew(3 * 1024) {}
 };
 
 template <int N>
@@ -165,7 +165,7 @@ int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const float*
     auto tw = make_twiddle(N);
     PsfBuffers ws(N);
     std::vector<float2> smem(CRowsSmem<N>::FLOAT2S > CColsSmem<N>::FLOAT2S ? CRowsSmem<N>::FLOAT2S : CColsSmem<N>::FLOAT2S);
-    std::vector<float> red(3 * EW_THREADS);
+    std::vector<float> red(3 * EW_THREADS + 2);
     PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
     grid2(N / T::CROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
         crows_fwd_body<N>(ex, CRowsFwdParams{ws.st.data(), tw.data()}, load, smem.data());
@@ -173,20 +173,14 @@ int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const float*
     grid2((N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, 1, CColsSmem<N>::THREADS, [&](HostExec& ex) {
         ccols_mix_body<N>(ex, CColsMixParams{ws.st.data(), Ht, tw.data(), 0, 1.0f / (3.0f * N * N)}, smem.data());
     });
-    IntensityEpilogue epi{field, ws.I.data(), ws.part_rows.data(), N};
+    IntensityEpilogue epi{field, ws.I.data(), ws.part_rows.data(), &ws.arrive, N};
     grid2(N / T::CROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
         crows_inv_body<N>(ex, CRowsInvParams{ws.st.data(), tw.data()}, epi, smem.data());
     });
-    grid2(1, 1, EW_THREADS, [&](HostExec& ex) {
-        reduce_body(ex, ReduceParams{ws.part_rows.data(), stats, 3 * (N / T::CROWS), 0, N}, red.data());
-    });
-    grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) {
-        psf_finalise_body(ex, PsfFinaliseParams{ws.I.data(), rho, stats, psf, ws.part_ew.data(), N}, EW_GRID, red.data());
-    });
-    grid2(1, 1, EW_THREADS, [&](HostExec& ex) {
-        reduce_body(ex, ReduceParams{ws.part_ew.data(), stats, EW_GRID, 1, N}, red.data());
-    });
-    return 0;
+    PsfFinaliseParams fin{ws.I.data(), rho, stats, psf, ws.part_ew.data(), ws.part_rows.data(), &ws.arrive,
+                          3 * (N / T::CROWS), N};
+    grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) { psf_finalise_body(ex, fin, EW_GRID, red.data()); });
+    return ws.arrive == 0 ? 0 : -7;
 }
 
 template <int N>
@@ -197,26 +191,23 @@ int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, const fl
     auto tw = make_twiddle(N);
     PsfBuffers ws(N);
     std::vector<float2> smem(CRowsSmem<N>::FLOAT2S > CColsSmem<N>::FLOAT2S ? CRowsSmem<N>::FLOAT2S : CColsSmem<N>::FLOAT2S);
-    std::vector<float> red(3 * EW_THREADS);
+    std::vector<float> red(3 * EW_THREADS + 2);
     grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) {
         psf_grad_prepare_body(ex, PsfGradPrepParams{gpsf, gscal, psf, rho, stats, ws.gtot.data(), ws.part_ew.data(), N},
                               EW_GRID, red.data());
     });
-    grid2(1, 1, EW_THREADS, [&](HostExec& ex) {
-        reduce_body(ex, ReduceParams{ws.part_ew.data(), stats, EW_GRID, 2, N}, red.data());
-    });
-    GradFieldLoad load{field, ws.gtot.data(), stats, N};
+    GradFieldLoad load{field, ws.gtot.data(), stats, ws.part_ew.data(), nullptr, EW_GRID, N};
     grid2(N / T::CROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
         crows_fwd_body<N>(ex, CRowsFwdParams{ws.st.data(), tw.data()}, load, smem.data());
     });
     grid2((N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, 1, CColsSmem<N>::THREADS, [&](HostExec& ex) {
         ccols_mix_body<N>(ex, CColsMixParams{ws.st.data(), Ht, tw.data(), 1, 1.0f / (3.0f * N * N)}, smem.data());
     });
-    HeightGradEpilogue epi{PupilLoad{A, h, {kappa[0], kappa[1], kappa[2]}, N}, ws.gh3.data(), N};
-    grid2(N / T::CROWS, 3, CRowsSmem<N>::THREADS, [&](HostExec& ex) {
-        crows_inv_body<N>(ex, CRowsInvParams{ws.st.data(), tw.data()}, epi, smem.data());
+    PupilLoad pupil{A, h, {kappa[0], kappa[1], kappa[2]}, N};
+    std::vector<float2> hsmem(HGradSmem<N>::FLOAT2S);
+    grid2(N / T::CROWS, 1, HGradSmem<N>::THREADS, [&](HostExec& ex) {
+        crows_inv_hgrad_body<N>(ex, CRowsInvParams{ws.st.data(), tw.data()}, pupil, grad_h, hsmem.data());
     });
-    grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) { sum3_body(ex, Sum3Params{ws.gh3.data(), grad_h, N * N}, EW_GRID); });
     return 0;
 }
 

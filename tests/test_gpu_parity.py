@@ -206,7 +206,14 @@ def test_cuda_graph_capture_of_forward_backward():
     h.grad.zero_()
     graph.replay()
     torch.cuda.synchronize()
-    assert torch.equal(h.grad, eager)
+    first = h.grad.clone()
+    # eager launches use the cooperative PSF kernel, captured ones the multi-kernel chain: same maths,
+    # different partial-sum grouping, so compare to rounding; replays themselves are bit-reproducible
+    assert rel_l2(first, eager) <= 1e-5
+    h.grad.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(h.grad, first)
 
 
 def test_abi_error_codes_on_device():
