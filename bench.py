@@ -265,6 +265,18 @@ def run_b200(args) -> None:
         else:
             step(i)
 
+    # rough step time (same code path on every rank) to size the load phase before the timed region
+    torch.cuda.synchronize()
+    t_est = time.perf_counter()
+    for i in range(10):
+        run_step(i)
+    torch.cuda.synchronize()
+    est_ms = (time.perf_counter() - t_est) * 100.0
+    if world > 1:
+        t = torch.tensor([est_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        est_ms = float(t.item())
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -274,10 +286,12 @@ def run_b200(args) -> None:
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        t_spin = time.perf_counter()
-        while time.perf_counter() - t_spin < 1.0:      # nvidia-smi needs ~1 s to start sampling; keep the GPU under load meanwhile
-            run_step(0)
-            torch.cuda.synchronize()
+    # nvidia-smi needs ~1 s before its first sample: keep every rank under load for a FIXED number of steps
+    # (identical on all ranks - the steps contain a collective)
+    spin_steps = int(min(5000, max(100, 1.0 / max(est_ms * 1e-3, 1e-5))))
+    for i in range(spin_steps):
+        run_step(i)
+    torch.cuda.synchronize()
     for i in range(max(3, args.warmup)):
         run_step(i)
     sync_all()
@@ -300,9 +314,13 @@ def run_b200(args) -> None:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                               "ms_per_step": ms_per_step, "quick": True, "launches_per_step": launches_per_step,
                               "clocks": clocks}), flush=True)
+        graphs = None
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         return
 
     # ---- per-call breakdown (each C-ABI call timed alone over the same rotating inputs) -----------------
@@ -377,10 +395,20 @@ def run_b200(args) -> None:
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / (float(ems.item()) * 1e-3)
 
-    if rank != 0:
+    def finish():
+        # captured graphs hold NCCL work: drop them and drain the device before tearing the communicator down
+        nonlocal graphs
+        graphs = None
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)      # skip destroy_process_group(): it can block on graph-captured collectives
+
+    if rank != 0:
+        finish()
         return
 
     peak, peak_src = hbm_peak()
@@ -416,9 +444,7 @@ def run_b200(args) -> None:
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
