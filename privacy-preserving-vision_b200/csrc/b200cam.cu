@@ -9,7 +9,7 @@
 #include <mutex>
 
 #include "../../include/b200cam.h"
-#include "fused256.cuh"
+#include "f256.cuh"
 #include "kernels.cuh"
 
 namespace b200cam {
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_accum(ColsAccumPa
     cols_accum_body<N>(ex, p, SMEM2, &st);
 }
 template <int N>
-__global__ void __launch_bounds__(Tile<N>::RCOLS * Plan<N>::LANES) k_cols_reduce_inv(ColsReduceInvParams p) {
+__global__ void __launch_bounds__(ReduceInvSmem<N>::THREADS) k_cols_reduce_inv(ColsReduceInvParams p) {
     DeviceExec ex;
     cols_reduce_inv_body<N>(ex, p, SMEM2);
 }
@@ -110,14 +110,87 @@ __global__ void __launch_bounds__(EW_THREADS) k_sum3(Sum3Params p) {
     DeviceExec ex;
     sum3_body(ex, p, gridDim.x);
 }
-__global__ void __launch_bounds__(EW_THREADS) k_f256_prep(f256::PrepParams p) {
-    DeviceExec ex;
-    f256::prep_body(ex, p, gridDim.x);
+__global__ void __launch_bounds__(f256::THREADS, 1) k_f256_fwd(f256::FwdParams p) { f256::fwd_kernel_body(p, SMEM2); }
+__global__ void __launch_bounds__(EW_THREADS) k_f256_norm(f256::NormParams p) { f256::norm_kernel_body(p); }
+__global__ void __launch_bounds__(f256::THREADS, 1) k_f256_bwd(f256::BwdParams p) { f256::bwd_kernel_body(p, SMEM2); }
+
+// sum the per-CTA accumulator planes of one spectral column (fixed order), apply (-1)^(u+v) (adjoint of the
+// roll at Optics.py:126) and the scale, inverse FFT along v -> ST layout [3][129][256] for rows_c2r.
+// grid 3*129 columns, block 256 (thread = v).
+struct AccReduceParams {
+    const float2* acc;     // [grid_bwd][129][256]
+    float2* st;            // [3][129][256]
+    const float2* tw;
+    int grid_bwd;          // CTAs of the backward kernel
+    int B;
+    float scale;
+};
+__global__ void __launch_bounds__(256) k_f256_acc_reduce(AccReduceParams p) {
+    using P = Plan<256>;
+    __shared__ float2 line[256];
+    __shared__ float2 E[P::E_SIZE];
+    const int cu = blockIdx.x, c = cu / f256::NC, u = cu % f256::NC, v = threadIdx.x;
+    int nparts = (p.grid_bwd - c + 2) / 3;
+    if (nparts > p.B) nparts = p.B;
+    const float2* src = p.acc + (static_cast<size_t>(c) * f256::NC + u) * 256 + v;
+    const size_t step = static_cast<size_t>(3) * f256::SPEC_PLANE;
+    float2 s = make_float2(0.f, 0.f);
+    int i = 0;
+    for (; i + 8 <= nparts; i += 8) {
+        float2 t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = __ldcg(src + (i + j) * step);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s.x += t[j].x; s.y += t[j].y; }
+    }
+    for (; i < nparts; ++i) { const float2 t = __ldcg(src + i * step); s.x += t.x; s.y += t.y; }
+    const float sc = ((u + v) & 1) ? -p.scale : p.scale;
+    line[v] = make_float2(s.x * sc, s.y * sc);
+    __syncthreads();
+    if (v < 16) {
+        float2 q[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) q[k] = line[v + 16 * k];
+        P::stepC(q, v, E, p.tw);
+    }
+    __syncthreads();
+    if (v < 16) {
+        float2 q[16];
+        P::stepD(q, v, E);
+        float2* dst = p.st + static_cast<size_t>(cu) * 256;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dst[16 * k + v] = q[k];
+    }
 }
-__global__ void __launch_bounds__(f256::THREADS, 1) k_f256_fwd(f256::FwdParams p) {
-    DeviceExec ex;
-    f256::FState st;
-    f256::fwd_body(ex, p, SMEM2, gridDim.x, &st);
+
+// arg-max term of the amax backward (Optics.py:128), spatial form:
+//   gpsf[c][p] -= sum_b coef_b * sum_{ties t of b in channel c} x_b[c][(p*_t - p + N/2) mod N],
+//   coef_b = sum(g_b*y_b) / (n_b m_b) = (sdot[3b]+sdot[3b+1]+sdot[3b+2]) / (2 n_b m_b^2).
+// grid (256, 3), block 256 (thread = x).  Fixed b order: deterministic.
+struct TieSpatialParams {
+    float* gpsf; const float* x; const float* sdot; const float* img_max; const int* tie_count; const int* tie_pos;
+    float* coef; int B;
+};
+__global__ void __launch_bounds__(256) k_f256_tie(TieSpatialParams p) {
+    constexpr int N = 256, NN = N * N;
+    const int py = blockIdx.x, c = blockIdx.y, px = threadIdx.x;
+    float acc = 0.f;
+    for (int b = 0; b < p.B; ++b) {
+        const int cnt = p.tie_count[b];
+        const int nt = cnt < MAX_TIES ? cnt : MAX_TIES;
+        const float m = p.img_max[b];
+        const float sd = (p.sdot[3 * b] + p.sdot[3 * b + 1]) + p.sdot[3 * b + 2];
+        const float cf = sd / (2.0f * static_cast<float>(cnt > 0 ? cnt : 1) * m * m);
+        if (py == 0 && c == 0 && px == 0) p.coef[b] = cf;
+        for (int t = 0; t < nt; ++t) {
+            const int pos = p.tie_pos[b * MAX_TIES + t];
+            if (pos / NN != c) continue;
+            const int sy = ((pos % NN) / N - py + N / 2 + N) & (N - 1);
+            const int sx = (pos % N - px + N / 2 + N) & (N - 1);
+            acc += cf * __ldg(p.x + (static_cast<size_t>(b) * 3 + c) * NN + sy * N + sx);
+        }
+    }
+    if (acc != 0.f) p.gpsf[c * NN + py * N + px] -= acc;
 }
 // ------------------------------------------------------------------------------------------
 // PSF chain as ONE cooperative launch per direction: the same bodies, run as virtual blocks, with
@@ -244,8 +317,15 @@ static int coop_grid(int N, cudaStream_t s) {
     }
     return g_state[dev].coop_grid[log2i(N)];
 }
-static bool fused_enabled() {
-    static const bool on = [] { const char* e = getenv("B200CAM_FUSED"); return e && e[0] == '1'; }();   // experimental, off by default
+// N=256 has two implementations of the sensor path: the generic row/column/row kernels (kernels.cuh) and the fused
+// one-CTA-per-plane TMEM kernels (f256.cuh).  The fused kernels execute 2.3x fewer instructions and move half the
+// bytes, but one 512-thread CTA per SM issues at ~30 % (ncu: profiles/r01_f256_*), and they work in whole rounds of
+// one plane per SM (B = 64 on 148 SMs: 1.3 rounds of work cost 2).  Measured (graph replay, fwd+bwd, us):
+//   B = 49: 243 fused;  B = 64: 361 fused / 268 generic;  B = 128: 508 fused / 428 generic.
+// So the generic pipeline is the default and the fused one is opt-in (B200CAM_FUSED=1) until its issue rate is fixed.
+static bool fused_selected(int B) {
+    (void)B;
+    static const bool on = [] { const char* e = getenv("B200CAM_FUSED"); return e && e[0] == '1'; }();
     return on;
 }
 
@@ -268,7 +348,7 @@ static cudaError_t init_kernels() {
     if ((e = optin(k_cols_conv<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_fwd<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_accum<N>, ColsSmem<N>::BYTES))) return e;
-    if ((e = optin(k_cols_reduce_inv<N>, ColsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_cols_reduce_inv<N>, ReduceInvSmem<N>::BYTES))) return e;
     if ((e = optin(k_crows_fwd<N, PupilLoad>, CRowsSmem<N>::BYTES))) return e;
     if ((e = optin(k_crows_fwd<N, GradFieldLoad>, CRowsSmem<N>::BYTES))) return e;
     if ((e = optin(k_crows_inv<N, IntensityEpilogue>, CRowsSmem<N>::BYTES))) return e;
@@ -342,21 +422,20 @@ struct PsfWs {
     }
 };
 
-constexpr int FUSED_MAX_GRID = 256;   // upper bound on resident CTAs (SMs) the parking area is sized for
+constexpr int FUSED_MAX_GRID = 160;   // upper bound on the CTAs of the fused backward kernel (one accumulator plane each)
 
 struct SensorWs {
     float2* stx; float2* stg; float2* partial; float2* stp; float* dot_partial; float* coef;
-    float2* kf; float2* kq; float* park; int* done; float2* st2; int* arrive;
+    float* plane_max; float* sdot; float2* acc; float2* st2; int* arrive;
     size_t bytes;
     SensorWs(void* p, int N, int B, bool backward) {
         Carver c(p);
         if (N == 256) {
-            kf = c.take<float2>(f256::KF_ELEMS);
-            kq = c.take<float2>(f256::KQ_ELEMS);
-            park = c.take<float>(static_cast<size_t>(FUSED_MAX_GRID) * 64 * f256::THREADS);
-            done = c.take<int>(B);
+            plane_max = c.take<float>(static_cast<size_t>(3) * B);
+            sdot = c.take<float>(static_cast<size_t>(3) * B);
+            acc = backward ? c.take<float2>(static_cast<size_t>(FUSED_MAX_GRID) * f256::SPEC_PLANE) : nullptr;
         } else {
-            kf = kq = nullptr; park = nullptr; done = nullptr;
+            plane_max = sdot = nullptr; acc = nullptr;
         }
         const size_t plane = static_cast<size_t>(N / 2 + 1) * N;
         stx = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
@@ -458,15 +537,42 @@ static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, c
 }
 
 template <int N>
-static int otf_impl(const float* psf, float2* otf, const float2* tw, cudaStream_t s) {
+static int otf_impl(const float* psf, float2* otf, const float2* tw, float scale, cudaStream_t s) {
     using T = Tile<N>;
     k_rows_r2c<N><<<dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
         RowsR2CParams{psf, otf, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
     LAUNCH_CHECK();
     const int total = 3 * T::NC;
     k_cols_fwd<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsFwdParams{otf, tw, total, 1, 1.0f / (static_cast<float>(N) * N)});
+        ColsFwdParams{otf, tw, total, 1, scale});
     LAUNCH_CHECK();
+    return 0;
+}
+
+static int fused_grid(int planes) {
+    int grid = sm_count();
+    if (grid <= 0) return 0;
+    if (grid > FUSED_MAX_GRID) grid = FUSED_MAX_GRID;
+    if (grid > planes) grid = planes;
+    return grid;
+}
+
+// N = 256: one persistent kernel (spectrum on chip) + the normalise pass
+static int fused_fwd(const float* img, float* sensor, const float2* otf, float2* spectrum, const float2* tw,
+                     const SensorWs& ws, float* img_max, int* tie_count, int* tie_pos, int B, cudaStream_t s) {
+    const int planes = 3 * B;
+    const int grid = fused_grid(planes);
+    if (grid <= 0) return B200CAM_E_NOT_INIT;
+    k_f256_fwd<<<grid, f256::THREADS, f256::SMEM_BYTES, s>>>(
+        f256::FwdParams{img, sensor, otf, spectrum, tw, ws.plane_max, tie_count, planes});
+    LAUNCH_CHECK();
+    if (sensor != nullptr) {
+        const long long n4 = static_cast<long long>(planes) * 256 * 256 / 4;
+        const int ngrid = static_cast<int>(n4 / EW_THREADS < 148 * 8 ? (n4 + EW_THREADS - 1) / EW_THREADS : 148 * 8);
+        k_f256_norm<<<ngrid, EW_THREADS, 0, s>>>(
+            f256::NormParams{sensor, ws.plane_max, img_max, tie_count, tie_pos, n4, MAX_TIES});
+        LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -476,20 +582,12 @@ static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, fl
     using T = Tile<N>;
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
-    int rc = otf_impl<N>(psf, otf, tw, s);
+    const bool fused = (N == 256) && fused_selected(B);
+    // the fused kernels take the OTF pre-halved (their real-row split yields 2*rfft, f256.cuh)
+    int rc = otf_impl<N>(psf, otf, tw, (fused ? 0.5f : 1.0f) / (static_cast<float>(N) * N), s);
     if (rc) return rc;
     SensorWs ws(ws_ptr, N, B, false);
-    if (N == 256 && fused_enabled()) {
-        k_f256_prep<<<148, EW_THREADS, 0, s>>>(f256::PrepParams{otf, ws.kf, ws.kq, ws.done, img_max, tie_count, B});
-        LAUNCH_CHECK();
-        int grid = sm_count();
-        if (grid <= 0 || grid > FUSED_MAX_GRID) return B200CAM_E_NOT_INIT;
-        if (grid > 3 * B) grid = 3 * B;
-        k_f256_fwd<<<grid, f256::THREADS, f256::SMEM_BYTES, s>>>(f256::FwdParams{
-            img, sensor, ws.kf, ws.kq, tw, spectrum, ws.park, img_max, ws.done, tie_count, tie_pos, 3 * B, MAX_TIES});
-        LAUNCH_CHECK();
-        return 0;
-    }
+    if (fused) return fused_fwd(img, sensor, otf, spectrum, tw, ws, img_max, tie_count, tie_pos, B, s);
     const int planes = 3 * B;
     const dim3 rgrid(N / T::ROWS, planes);
     float2* srow = spectrum != nullptr ? spectrum : ws.stx;      // row spectra: kept for the backward when asked
@@ -499,15 +597,63 @@ static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, fl
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int chunk = conv_chunk(N, B);
     k_cols_conv<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, chunk, 0});
+        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, chunk, 0, 1.0f});
     LAUNCH_CHECK();
     k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f});
+        RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0});
     LAUNCH_CHECK();
     const long long n4 = static_cast<long long>(planes) * N * N / 4;
     const int grid = static_cast<int>(n4 / EW_THREADS < 148 * 8 ? (n4 + EW_THREADS - 1) / EW_THREADS : 148 * 8);
     k_normalise<<<grid, EW_THREADS, 0, s>>>(NormaliseParams{sensor, img_max, tie_count, tie_pos, n4, 3 * N * N / 4});
     LAUNCH_CHECK();
+    return 0;
+}
+
+// N = 256 backward: persistent accumulate kernel, partial reduction + inverse transform, arg-max term
+static int fused_bwd(const float* g, const float* img, const float* img_max, const int* tie_count, const int* tie_pos,
+                     const float* psf, const float2* otf, const float2* spectrum, float* grad_psf, float* grad_img,
+                     const float2* tw, const SensorWs& ws, int B, cudaStream_t s) {
+    constexpr int N = 256;
+    using T = Tile<N>;
+    const int planes = 3 * B;
+    const int grid = fused_grid(planes);
+    if (grid <= 0) return B200CAM_E_NOT_INIT;
+    const float2* X = spectrum;
+    if (X == nullptr) {          // the forward did not keep the image spectra: rebuild them (no output, no max)
+        k_f256_fwd<<<grid, f256::THREADS, f256::SMEM_BYTES, s>>>(
+            f256::FwdParams{img, nullptr, otf, ws.stx, tw, nullptr, nullptr, planes});
+        LAUNCH_CHECK();
+        X = ws.stx;
+    }
+    k_f256_bwd<<<grid, f256::THREADS, f256::SMEM_BYTES, s>>>(
+        f256::BwdParams{g, X, otf, tw, img_max, ws.acc, ws.sdot, B});
+    LAUNCH_CHECK();
+    k_f256_acc_reduce<<<3 * f256::NC, 256, 0, s>>>(
+        AccReduceParams{ws.acc, ws.stp, tw, grid, B, 0.25f / (static_cast<float>(N) * N)});
+    LAUNCH_CHECK();
+    k_rows_c2r<N><<<dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
+    LAUNCH_CHECK();
+    k_f256_tie<<<dim3(N, 3), 256, 0, s>>>(TieSpatialParams{grad_psf, img, ws.sdot, img_max, tie_count, tie_pos, ws.coef, B});
+    LAUNCH_CHECK();
+    if (grad_img != nullptr) {   // optional output (no reference caller asks for it): generic kernels
+        const dim3 rgrid(N / T::ROWS, planes);
+        k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+            RowsR2CParams{g, ws.stg, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
+        LAUNCH_CHECK();
+        const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
+        const int cchunk = conv_chunk(N, B);
+        k_cols_conv<N><<<dim3(colgroups, (B + cchunk - 1) / cchunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunk, 1, 2.0f});
+        LAUNCH_CHECK();
+        k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+            RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
+        LAUNCH_CHECK();
+        const long long tot = static_cast<long long>(planes) * N * N;
+        const int tgrid = static_cast<int>(tot / EW_THREADS < 148 * 8 ? (tot + EW_THREADS - 1) / EW_THREADS : 148 * 8);
+        k_tie_term_img<<<tgrid, EW_THREADS, 0, s>>>(TieTermImgParams{grad_img, psf, tie_count, tie_pos, ws.coef, B, N});
+        LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -520,6 +666,8 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     SensorWs ws(ws_ptr, N, B, true);
+    if (N == 256 && fused_selected(B))
+        return fused_bwd(g, img, img_max, tie_count, tie_pos, psf, otf, spectrum, grad_psf, grad_img, tw, ws, B, s);
     const int planes = 3 * B, tiles = N / T::ROWS;
     const dim3 rgrid(tiles, planes);
     const float2* srow = spectrum;
@@ -539,7 +687,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     k_cols_accum<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
         ColsAccumParams{srow, ws.stg, ws.partial, tw, img_max, ws.coef, tie_count, tie_pos, B, chunk});
     LAUNCH_CHECK();
-    k_cols_reduce_inv<N><<<(3 * T::NC + T::RCOLS - 1) / T::RCOLS, T::RCOLS * Plan<N>::LANES, ColsSmem<N>::BYTES, s>>>(
+    k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
         ColsReduceInvParams{ws.partial, ws.stp, tw, (B + chunk - 1) / chunk, 1.0f / (static_cast<float>(N) * N)});
     LAUNCH_CHECK();
     k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
@@ -548,7 +696,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     if (grad_img != nullptr) {
         const int cchunk = conv_chunk(N, B);
         k_cols_conv<N><<<dim3(colgroups, (B + cchunk - 1) / cchunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunk, 1});
+            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunk, 1, 1.0f});
         LAUNCH_CHECK();
         k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
             RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
@@ -622,6 +770,11 @@ int b200cam_init(int N) {
         case 1024: e = init_kernels<1024>(); break;
     }
     if (e == cudaSuccess && N == 256) e = optin(k_f256_fwd, f256::SMEM_BYTES);
+    if (e == cudaSuccess && N == 256) e = optin(k_f256_bwd, f256::SMEM_BYTES);
+    // 132 KB of the 256 KB L1/shared array is enough for one CTA per SM: leave the rest to L1 (the OTF / spectrum
+    // columns are prefetched into it)
+    if (e == cudaSuccess && N == 256) e = cudaFuncSetAttribute(k_f256_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
+    if (e == cudaSuccess && N == 256) e = cudaFuncSetAttribute(k_f256_bwd, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_state[dev].sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) {
         const int sms = g_state[dev].sms;
@@ -684,7 +837,6 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const floa
 
 size_t b200cam_spectrum_bytes(int N, int B) {
     if (!b200cam_supported(N) || B < 1) return 0;
-    if (N == 256 && fused_enabled()) return static_cast<size_t>(3) * B * f256::XS_PLANE * sizeof(float2);
     return static_cast<size_t>(3) * B * (N / 2 + 1) * N * sizeof(float2);
 }
 
@@ -715,7 +867,7 @@ int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* 
         !aligned16(grad_psf) || (grad_img && !aligned16(grad_img)))
         return B200CAM_E_ALIGN;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const float2* spec = (N == 256 && fused_enabled()) ? nullptr : reinterpret_cast<const float2*>(spectrum);
+    const float2* spec = reinterpret_cast<const float2*>(spectrum);
     DISPATCH_N(N, (sensor_bwd_impl<NN_>(grad_sensor, img, sensor, img_max, tie_count, tie_pos, psf,
                                         reinterpret_cast<const float2*>(otf), spec, grad_psf, grad_img, workspace,
                                         B, s)));

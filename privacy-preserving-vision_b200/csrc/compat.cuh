@@ -25,11 +25,25 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 namespace b200cam {
 
 // ---- complex helpers (float2 = re, im) -------------------------------------------------
+// On the device these map to the packed fp32 instructions of sm_100a (one FADD2 / FFMA2 per complex add, two
+// per complex multiply; half swap and per-half negation are operand modifiers) - see pkfft.cuh.
+#if defined(__CUDA_ARCH__)
+B200_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+B200_HD float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+B200_HD float2 cmul(float2 a, float2 b) {
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
+// a * conj(b)
+B200_HD float2 cmulc(float2 a, float2 b) {
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(b.y, -b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
+#else
 B200_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 B200_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 B200_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 B200_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+#endif
 B200_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 B200_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 // multiply by +i / -i

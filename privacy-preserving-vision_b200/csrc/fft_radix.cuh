@@ -7,6 +7,9 @@
 #pragma once
 
 #include "compat.cuh"
+#if defined(__CUDACC__)
+#include "pkfft.cuh"
+#endif
 
 namespace b200cam {
 
@@ -67,6 +70,10 @@ struct RegFFT<2, DIR> {
 template <int DIR>
 struct RegFFT<4, DIR> {
     static B200_HD void run(float2 (&v)[4]) {
+#if defined(__CUDA_ARCH__)
+        pk::Fft<4, DIR>::run(v);         // packed fp32 (FADD2 / FFMA2) on the device
+        return;
+#endif
         const float2 t0 = cadd(v[0], v[2]);
         const float2 t1 = csub(v[0], v[2]);
         const float2 t2 = cadd(v[1], v[3]);
@@ -86,6 +93,10 @@ struct RegFFT {
     static constexpr int RA = 4;
     static constexpr int RB = R / 4;
     static B200_HD void run(float2 (&v)[R]) {
+#if defined(__CUDA_ARCH__)
+        pk::Fft<R, DIR>::run(v);         // packed fp32 (FADD2 / FFMA2) on the device
+        return;
+#endif
 #pragma unroll
         for (int nb = 0; nb < RB; ++nb) {
             float2 t[RA];

@@ -164,6 +164,7 @@ struct ColsConvParams {
     int B;
     int chunk;               // images per CTA (gridDim.y = ceil(B/chunk))
     int conj_otf;
+    float otf_scale;         // extra factor on the OTF (the fused N=256 path stores it pre-halved)
 };
 
 template <int N>
@@ -203,7 +204,7 @@ B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem, Con
             const float2* k = p.otf + static_cast<size_t>(cu) * N;
 #pragma unroll
             for (int i = 0; i < P::R2; ++i) {
-                const float2 kk = ld_ro(k + b + P::R1 * i);
+                const float2 kk = cscale(ld_ro(k + b + P::R1 * i), p.otf_scale);
                 s.k[i] = p.conj_otf ? cconj(kk) : kk;
             }
         }
@@ -305,12 +306,20 @@ B200_HD void cols_fwd_body(Exec& ex, const ColsFwdParams& p, float2* smem) {
 //      (second half of irfftn, Utils.py:11) + per-image max (Optics.py:128, amax part)
 //      grid (N/ROWS, planes), block NP*LANES
 // ---------------------------------------------------------------------------------------------
+constexpr int C2R_MAX_TIES = 8;     // = MAX_TIES (declared with the normalise kernel below)
+
 struct RowsC2RParams {
     const float2* st;    // [planes][NC][N]
-    float* out;          // [planes][N][N]
+    float* out;          // [planes][N][N]; nullptr: nothing is stored (max-only pass)
     const float2* tw;
-    float* img_max;      // nullable, [planes/3], atomically maximised
+    float* img_max;      // nullable, [planes/3]: atomically maximised (norm = 0) or read (norm = 1)
     float scale;
+    // norm = 1: second pass over the same spectrum - the rows are recomputed (bit-identical), divided by the
+    // image maximum found by the first pass (Optics.py:128) and the positions that attain it are recorded
+    // (torch's amax backward splits the gradient evenly between exact ties).  Saves writing and re-reading conv.
+    int* tie_count;      // [planes/3], zero on entry
+    int* tie_pos;        // [planes/3][MAX_TIES] flat index into (3,N,N)
+    int norm;
 };
 
 template <int N, class Exec>
@@ -353,19 +362,41 @@ B200_HD void rows_c2r_body(Exec& ex, const RowsC2RParams& p, float2* smem) {
         if (a < P::R2) {
             float2 v[P::R1];
             P::stepD(v, a, E + j * P::E_SIZE);
-            float* r0 = p.out + (static_cast<size_t>(plane) * N + y0 + 2 * j) * N;
-            float* r1 = r0 + N;
+            const size_t row = (static_cast<size_t>(plane) * N + y0 + 2 * j) * N;
+            if (p.norm) {
+                const int img = plane / 3;
+                const float m = *(p.img_max + img);
+                const int base = (plane % 3) * N * N + (y0 + 2 * j) * N;
 #pragma unroll
-            for (int i = 0; i < P::R1; ++i) {
-                const float e = v[i].x * p.scale, o = v[i].y * p.scale;
-                r0[P::R2 * i + a] = e;
-                r1[P::R2 * i + a] = o;
-                mx = fmaxf(mx, fmaxf(e, o));
+                for (int i = 0; i < P::R1; ++i) {
+                    const float e = v[i].x * p.scale, o = v[i].y * p.scale;
+                    const int x = P::R2 * i + a;
+                    if (e == m) {
+                        const int slot = atomic_add_int(p.tie_count + img, 1);
+                        if (slot < C2R_MAX_TIES) p.tie_pos[img * C2R_MAX_TIES + slot] = base + x;
+                    }
+                    if (o == m) {
+                        const int slot = atomic_add_int(p.tie_count + img, 1);
+                        if (slot < C2R_MAX_TIES) p.tie_pos[img * C2R_MAX_TIES + slot] = base + N + x;
+                    }
+                    p.out[row + x] = e / m;
+                    p.out[row + N + x] = o / m;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < P::R1; ++i) {
+                    const float e = v[i].x * p.scale, o = v[i].y * p.scale;
+                    if (p.out != nullptr) {
+                        p.out[row + P::R2 * i + a] = e;
+                        p.out[row + N + P::R2 * i + a] = o;
+                    }
+                    mx = fmaxf(mx, fmaxf(e, o));
+                }
             }
         }
         red[tid] = mx;
     });
-    if (p.img_max != nullptr) {
+    if (p.img_max != nullptr && !p.norm) {
         ex.phase([&](int tid) {
             if (tid == 0) {
                 float mx = red[0];
@@ -382,6 +413,7 @@ B200_HD void rows_c2r_body(Exec& ex, const RowsC2RParams& p, float2* smem) {
 //      1-D grid-stride over float4 elements; tie_pos[b][MAX_TIES], tie_count[b]
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_TIES = 8;
+static_assert(MAX_TIES == C2R_MAX_TIES, "tie buffers");
 
 struct NormaliseParams {
     float* y;               // [B][3][N][N] in place: conv -> sensor
@@ -392,25 +424,45 @@ struct NormaliseParams {
     int per_image4;         // 3*N*N/4
 };
 
+// Four independent float4 per thread and iteration (the kernel is a pure stream: keep loads in flight).
+// y = conv * (1/max) instead of a division per element; the arg-max element itself is written as exactly 1.
 template <class Exec>
 B200_HD void normalise_body(Exec& ex, const NormaliseParams& p, int grid_x) {
     ex.phase([&](int tid) {
-        const long long stride = static_cast<long long>(grid_x) * ex.nthreads();
-        for (long long i = static_cast<long long>(ex.bx()) * ex.nthreads() + tid; i < p.n4; i += stride) {
-            const int b = static_cast<int>(i / p.per_image4);
-            const float m = ld_ro(p.img_max + b);
-            float4 v = reinterpret_cast<float4*>(p.y)[i];
-            const float e[4] = {v.x, v.y, v.z, v.w};
+        constexpr int U = 4;
+        const long long nthr = static_cast<long long>(grid_x) * ex.nthreads();
+        float4* y4 = reinterpret_cast<float4*>(p.y);
+        for (long long i0 = static_cast<long long>(ex.bx()) * ex.nthreads() + tid; i0 < p.n4; i0 += U * nthr) {
+            float4 v[U];
+            float m[U];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (e[q] == m) {
-                    const int slot = atomic_add_int(p.tie_count + b, 1);
-                    if (slot < MAX_TIES)
-                        p.tie_pos[b * MAX_TIES + slot] = static_cast<int>(i % p.per_image4) * 4 + q;
+            for (int k = 0; k < U; ++k) {
+                const long long i = i0 + k * nthr;
+                if (i < p.n4) {
+                    v[k] = y4[i];
+                    m[k] = ld_ro(p.img_max + static_cast<int>(i / p.per_image4));
                 }
             }
-            v.x = e[0] / m; v.y = e[1] / m; v.z = e[2] / m; v.w = e[3] / m;
-            reinterpret_cast<float4*>(p.y)[i] = v;
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const long long i = i0 + k * nthr;
+                if (i >= p.n4) continue;
+                const int b = static_cast<int>(i / p.per_image4);
+                const float inv = 1.0f / m[k];
+                float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (e[q] == m[k]) {
+                        const int slot = atomic_add_int(p.tie_count + b, 1);
+                        if (slot < MAX_TIES)
+                            p.tie_pos[b * MAX_TIES + slot] = static_cast<int>(i % p.per_image4) * 4 + q;
+                        e[q] = 1.0f;
+                    } else {
+                        e[q] *= inv;
+                    }
+                }
+                y4[i] = make_float4(e[0], e[1], e[2], e[3]);
+            }
         }
     });
 }
@@ -526,7 +578,6 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
 // ---------------------------------------------------------------------------------------------
 // K7  cols_reduce_inv : sum the chunk partials in order, apply (-1)^(u+v) (the adjoint of the
 //      roll at Optics.py:126) and 1/N^2, inverse FFT along v -> ST layout for rows_c2r
-//      grid ceil(3*NC/RCOLS), block RCOLS*LANES
 // ---------------------------------------------------------------------------------------------
 struct ColsReduceInvParams {
     const float2* partial;   // [nchunks][3][NC][N]
@@ -536,44 +587,53 @@ struct ColsReduceInvParams {
     float scale;
 };
 
+// grid 3*NC (one spectral column per CTA), block N (thread = v): the chunk sum is spread over N threads with
+// coalesced 8N-byte reads; the first LANES threads then run the inverse transform of the column.
+// shared: line[N] + E[E_SIZE] float2
+template <int N>
+struct ReduceInvSmem {
+    static constexpr int THREADS = N;
+    static constexpr int FLOAT2S = N + Plan<N>::E_SIZE;
+    static constexpr int BYTES = FLOAT2S * 8;
+};
+
 template <int N, class Exec>
 B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2* smem) {
     using P = Plan<N>;
     using T = Tile<N>;
-    using S = ColsSmem<N>;
-    float2* E = smem;
-    const int cu0 = ex.bx() * T::RCOLS;
+    float2* line = smem;
+    float2* E = smem + N;
+    const int cu = ex.bx();
     constexpr int TOTAL = 3 * T::NC;
-    ex.warp_phase([&](int tid) {
-        const int jc = tid / P::LANES, b = tid % P::LANES;
-        const int cu = cu0 + jc;
-        if (cu < TOTAL && b < P::R1) {
-            const int u = cu % T::NC;
-            float2 v[P::R2];
+    const int u = cu % T::NC;
+    ex.phase([&](int v) {
+        const float2* src = p.partial + static_cast<size_t>(cu) * N + v;
+        const size_t step = static_cast<size_t>(TOTAL) * N;
+        float2 s = make_float2(0.f, 0.f);
+        int ch = 0;
+        for (; ch + 4 <= p.nchunks; ch += 4) {          // fixed order: deterministic
+            const float2 t0 = ld_ro(src + (ch + 0) * step), t1 = ld_ro(src + (ch + 1) * step);
+            const float2 t2 = ld_ro(src + (ch + 2) * step), t3 = ld_ro(src + (ch + 3) * step);
+            s = cadd(cadd(cadd(cadd(s, t0), t1), t2), t3);
+        }
+        for (; ch < p.nchunks; ++ch) s = cadd(s, ld_ro(src + ch * step));
+        line[v] = cscale(s, ((u + v) & 1) ? -p.scale : p.scale);
+    });
+    ex.phase([&](int b) {
+        if (b < P::R1) {
+            float2 q[P::R2];
 #pragma unroll
-            for (int i = 0; i < P::R2; ++i) v[i] = make_float2(0.f, 0.f);
-            for (int ch = 0; ch < p.nchunks; ++ch) {
-                const float2* src = p.partial + (static_cast<size_t>(ch) * TOTAL + cu) * N;
-#pragma unroll
-                for (int i = 0; i < P::R2; ++i) v[i] = cadd(v[i], ld_ro(src + b + P::R1 * i));
-            }
-#pragma unroll
-            for (int i = 0; i < P::R2; ++i) {
-                const int k = b + P::R1 * i;
-                v[i] = cscale(v[i], ((u + k) & 1) ? -p.scale : p.scale);
-            }
-            P::stepC(v, b, E + jc * P::E_SIZE, p.tw);
+            for (int i = 0; i < P::R2; ++i) q[i] = line[b + P::R1 * i];
+            P::stepC(q, b, E, p.tw);
         }
     });
-    ex.warp_phase([&](int tid) {
-        const int jc = tid / P::LANES, a = tid % P::LANES;
-        const int cu = cu0 + jc;
-        if (cu < TOTAL && a < P::R2) {
-            float2 v[P::R1];
-            P::stepD(v, a, E + jc * P::E_SIZE);
+    ex.phase([&](int a) {
+        if (a < P::R2) {
+            float2 q[P::R1];
+            P::stepD(q, a, E);
             float2* dst = p.st + static_cast<size_t>(cu) * N;
 #pragma unroll
-            for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = v[i];
+            for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = q[i];
         }
     });
 }

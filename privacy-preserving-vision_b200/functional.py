@@ -144,7 +144,8 @@ class SensorConv(torch.autograd.Function):
         x, p, sensor, img_max, tie_count, tie_pos, otf = ctx.saved_tensors
         B = x.shape[0]
         want_img = ctx.needs_input_grad[0]
-        grad_psf = torch.zeros(3, N, N, dtype=torch.float32, device=plan.device)
+        # the kernels overwrite every element of grad_psf; only the empty batch needs explicit zeros
+        grad_psf = (torch.empty if B > 0 else torch.zeros)(3, N, N, dtype=torch.float32, device=plan.device)
         grad_img = torch.empty_like(x) if want_img else None
         if B > 0:
             gc = _as_f32(g, plan.device)

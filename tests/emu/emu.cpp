@@ -9,7 +9,6 @@
 #include <vector>
 
 #include "../../privacy-preserving-vision_b200/csrc/kernels.cuh"
-#include "../../privacy-preserving-vision_b200/csrc/fused256.cuh"
 
 using namespace b200cam;
 
@@ -81,10 +80,10 @@ int sensor_fwd_impl(int B, const float* img, const float* psf, float* sensor, fl
     const int chunk = conv_chunk(N, B);
     std::vector<ConvState<N>> cst(ColsSmem<N>::THREADS);
     grid2(colgroups, (B + chunk - 1) / chunk, ColsSmem<N>::THREADS, [&](HostExec& ex) {
-        cols_conv_body<N>(ex, ColsConvParams{srow, st2.data(), otf, tw.data(), nullptr, B, chunk, 0}, smem.data(), cst.data());
+        cols_conv_body<N>(ex, ColsConvParams{srow, st2.data(), otf, tw.data(), nullptr, B, chunk, 0, 1.0f}, smem.data(), cst.data());
     });
     grid2(N / T::ROWS, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_c2r_body<N>(ex, RowsC2RParams{st2.data(), sensor, tw.data(), img_max, 1.0f}, smem.data());
+        rows_c2r_body<N>(ex, RowsC2RParams{st2.data(), sensor, tw.data(), img_max, 1.0f, nullptr, nullptr, 0}, smem.data());
     });
     const long long n4 = static_cast<long long>(planes) * N * N / 4;
     grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) {
@@ -127,9 +126,10 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
         cols_accum_body<N>(ex, ColsAccumParams{srow, stg.data(), partial.data(), tw.data(), img_max, coef.data(),
                                                tie_count, tie_pos, B, chunk}, smem.data(), states.data());
     });
-    grid2((3 * T::NC + T::RCOLS - 1) / T::RCOLS, 1, T::RCOLS * Plan<N>::LANES, [&](HostExec& ex) {
+    std::vector<float2> rsmem(ReduceInvSmem<N>::FLOAT2S);
+    grid2(3 * T::NC, 1, ReduceInvSmem<N>::THREADS, [&](HostExec& ex) {
         cols_reduce_inv_body<N>(ex, ColsReduceInvParams{partial.data(), stp.data(), tw.data(), used_chunks,
-                                                        1.0f / (static_cast<float>(N) * N)}, smem.data());
+                                                        1.0f / (static_cast<float>(N) * N)}, rsmem.data());
     });
     grid2(tiles, 3, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
         rows_c2r_body<N>(ex, RowsC2RParams{stp.data(), grad_psf, tw.data(), nullptr, 1.0f}, smem.data());
@@ -138,7 +138,7 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
         const int cchunk = conv_chunk(N, B);
         std::vector<ConvState<N>> cst(ColsSmem<N>::THREADS);
         grid2(colgroups, (B + cchunk - 1) / cchunk, ColsSmem<N>::THREADS, [&](HostExec& ex) {
-            cols_conv_body<N>(ex, ColsConvParams{stg.data(), stg.data(), otf, tw.data(), img_max, B, cchunk, 1}, smem.data(),
+            cols_conv_body<N>(ex, ColsConvParams{stg.data(), stg.data(), otf, tw.data(), img_max, B, cchunk, 1, 1.0f}, smem.data(),
                               cst.data());
         });
         grid2(tiles, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
@@ -223,32 +223,7 @@ int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, const fl
         default: return -1;                                    \
     }
 
-// fused N=256 forward: generic OTF -> fused tables -> persistent fused kernel with `grid` emulated CTAs
-int fused_sensor_fwd_impl(int B, int grid, const float* img, const float* psf, float* sensor, float* img_max,
-                          int* tie_count, int* tie_pos, float2* otf, float2* xs) {
-    constexpr int N = 256;
-    auto tw = make_twiddle(N);
-    otf_impl<N>(psf, otf, tw.data());
-    std::vector<float2> kf(f256::KF_ELEMS), kq(f256::KQ_ELEMS);
-    std::vector<int> done(B);
-    f256::PrepParams pp{otf, kf.data(), kq.data(), done.data(), img_max, tie_count, B};
-    grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) { f256::prep_body(ex, pp, EW_GRID); });
-    std::vector<float> park(static_cast<size_t>(grid) * 64 * f256::THREADS);
-    std::vector<float2> smem(f256::SMEM_FLOAT2);
-    std::vector<f256::FState> st(f256::THREADS);
-    f256::FwdParams fp{img, sensor, kf.data(), kq.data(), tw.data(), xs, park.data(), img_max, done.data(),
-                       tie_count, tie_pos, 3 * B, MAX_TIES};
-    grid2(grid, 1, f256::THREADS, [&](HostExec& ex) { f256::fwd_body(ex, fp, smem.data(), grid, st.data()); });
-    return 0;
-}
-
 extern "C" {
-
-int emu_fused_sensor_fwd(int B, int grid, const float* img, const float* psf, float* sensor, float* img_max,
-                         int* tie_count, int* tie_pos, float* otf, float* xs) {
-    return fused_sensor_fwd_impl(B, grid, img, psf, sensor, img_max, tie_count, tie_pos,
-                                 reinterpret_cast<float2*>(otf), reinterpret_cast<float2*>(xs));
-}
 
 int emu_fft(int N, int inverse, const float* in, float* out) {
     // one N-point FFT through stepA..D with 'LANES' emulated lanes; exercises Plan<N> in isolation

@@ -97,18 +97,3 @@ def sensor_bwd(g, img, sensor, img_max, tie_count, tie_pos, psf, otf, want_img_g
                               _p(tie_pos), _p(psf.contiguous()), _p(otf), _p(spectrum), _p(gpsf), _p(gimg))
     assert rc == 0
     return gpsf, gimg
-
-
-def fused_sensor_fwd(img, psf, grid=5, save_spectrum=False):
-    B, _, N, _ = img.shape
-    assert N == 256
-    sensor = torch.empty_like(img)
-    img_max = torch.empty(B)
-    tie_count = torch.zeros(B, dtype=torch.int32)
-    tie_pos = torch.zeros(B, 8, dtype=torch.int32)
-    otf = torch.empty(3, N // 2 + 1, N, 2)
-    xs = torch.zeros(3 * B, 2, 16, 128, 8, 2) if save_spectrum else None
-    rc = lib().emu_fused_sensor_fwd(B, grid, _p(img.contiguous()), _p(psf.contiguous()), _p(sensor), _p(img_max),
-                                    _p(tie_count), _p(tie_pos), _p(otf), _p(xs))
-    assert rc == 0
-    return sensor, img_max, tie_count, tie_pos, otf, xs

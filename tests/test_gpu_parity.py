@@ -240,3 +240,52 @@ def test_empty_batch():
     cam, _ = make_camera(N, synth.height_map(N))
     y = cam(torch.zeros(0, 3, N, N, device="cuda"))
     assert y.shape == (0, 3, N, N)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused N=256 sensor kernels (f256.cuh): opt-in with B200CAM_FUSED=1 (read once per process -> subprocess)
+# ---------------------------------------------------------------------------------------------------------
+_FORCED_FUSED_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {repo!r}); sys.path.insert(0, {repo!r} + "/tests")
+import b200cam.synthetic as synth
+from b200cam.optics import Camera
+from oracle import camera_oracle as co
+N, B = 256, int(sys.argv[1])
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+cam = Camera(device=dev, N=N, zernike_terms=6)
+h_cpu = synth.height_map(N, 41)
+h = h_cpu.to(dev).requires_grad_(True)
+cam.get_Heith_Map = lambda: h
+img = synth.images(B, N, 42)
+img[1] = img[0]                      # identical images must give identical rows
+w = synth.upstream_grad(B, N, 43)
+x = img.to(dev).requires_grad_(True)
+y = cam(x)
+((y * w.to(dev)).sum() + cam.loss_rad + cam.centering_loss).backward()
+C = co.build_constants(N)
+ho = h_cpu.clone().requires_grad_(True)
+xo = img.clone().requires_grad_(True)
+out = co.camera_forward(xo, ho, C)
+((out["sensor"] * w).sum() + out["loss_rad"] + out["centering_loss"]).backward()
+rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+print("REL", rel(y.detach(), out["sensor"].detach()), rel(h.grad, ho.grad), rel(x.grad, xo.grad))
+"""
+
+
+@pytest.mark.parametrize("B", [3, 52])
+def test_fused_kernels_forced(B):
+    """B200CAM_FUSED=1 in a fresh process: fused TMEM kernels (B = 52: more planes than SMs, i.e. two rounds and
+    per-CTA accumulators over several images), sensor, dL/dh and the optional dL/dimg against the oracle."""
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    env = dict(os.environ, B200CAM_FUSED="1")
+    res = subprocess.run([sys.executable, "-c", _FORCED_FUSED_SCRIPT.format(repo=str(REPO)), str(B)], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("REL")][-1].split()
+    e_sensor, e_grad, e_img = float(line[1]), float(line[2]), float(line[3])
+    assert e_sensor <= TOL_SENSOR and e_grad <= TOL_GRAD and e_img <= TOL_GRAD
