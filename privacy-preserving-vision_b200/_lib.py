@@ -41,6 +41,10 @@ _SIGNATURES = {
     "b200cam_spectrum_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "b200cam_sensor_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _f,
                                           _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "b200cam_sensor_split_supported": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "b200cam_sensor_rows": (ctypes.c_int, [_f, _f, _f, _f, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "b200cam_sensor_finish": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f,
+                                             _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "b200cam_sensor_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f,
                                           _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }

@@ -576,24 +576,31 @@ static int fused_fwd(const float* img, float* sensor, const float2* otf, float2*
     return 0;
 }
 
+// first half of the generic forward: row transforms of the images (independent of the PSF, so a caller may run it on a
+// second stream while b200cam_psf_fwd is still busy); also resets the per-image max / tie counters
 template <int N>
-static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
-                           int* tie_pos, float2* otf, float2* spectrum, void* ws_ptr, int B, cudaStream_t s) {
+static int sensor_rows_impl(const float* img, float2* srow, float* img_max, int* tie_count, int B, cudaStream_t s) {
     using T = Tile<N>;
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
-    const bool fused = (N == 256) && fused_selected(B);
-    // the fused kernels take the OTF pre-halved (their real-row split yields 2*rfft, f256.cuh)
-    int rc = otf_impl<N>(psf, otf, tw, (fused ? 0.5f : 1.0f) / (static_cast<float>(N) * N), s);
-    if (rc) return rc;
-    SensorWs ws(ws_ptr, N, B, false);
-    if (fused) return fused_fwd(img, sensor, otf, spectrum, tw, ws, img_max, tie_count, tie_pos, B, s);
-    const int planes = 3 * B;
-    const dim3 rgrid(N / T::ROWS, planes);
-    float2* srow = spectrum != nullptr ? spectrum : ws.stx;      // row spectra: kept for the backward when asked
+    const dim3 rgrid(N / T::ROWS, 3 * B);
     k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
         RowsR2CParams{img, srow, tw, nullptr, nullptr, img_max, tie_count, nullptr, nullptr, nullptr, nullptr});
     LAUNCH_CHECK();
+    return 0;
+}
+
+// second half: OTF of the PSF, column convolution, inverse rows + per-image max, normalise
+template <int N>
+static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos, float2* otf,
+                              const float2* srow, const SensorWs& ws, int B, cudaStream_t s) {
+    using T = Tile<N>;
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    int rc = otf_impl<N>(psf, otf, tw, 1.0f / (static_cast<float>(N) * N), s);
+    if (rc) return rc;
+    const int planes = 3 * B;
+    const dim3 rgrid(N / T::ROWS, planes);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int chunk = conv_chunk(N, B);
     k_cols_conv<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
@@ -607,6 +614,24 @@ static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, fl
     k_normalise<<<grid, EW_THREADS, 0, s>>>(NormaliseParams{sensor, img_max, tie_count, tie_pos, n4, 3 * N * N / 4});
     LAUNCH_CHECK();
     return 0;
+}
+
+template <int N>
+static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
+                           int* tie_pos, float2* otf, float2* spectrum, void* ws_ptr, int B, cudaStream_t s) {
+    SensorWs ws(ws_ptr, N, B, false);
+    if ((N == 256) && fused_selected(B)) {
+        const float2* tw = twiddle(N);
+        if (tw == nullptr) return B200CAM_E_NOT_INIT;
+        // the fused kernels take the OTF pre-halved (their real-row split yields 2*rfft, f256.cuh)
+        int rc = otf_impl<N>(psf, otf, tw, 0.5f / (static_cast<float>(N) * N), s);
+        if (rc) return rc;
+        return fused_fwd(img, sensor, otf, spectrum, tw, ws, img_max, tie_count, tie_pos, B, s);
+    }
+    float2* srow = spectrum != nullptr ? spectrum : ws.stx;      // row spectra: kept for the backward when asked
+    int rc = sensor_rows_impl<N>(img, srow, img_max, tie_count, B, s);
+    if (rc) return rc;
+    return sensor_finish_impl<N>(psf, sensor, img_max, tie_count, tie_pos, otf, srow, ws, B, s);
 }
 
 // N = 256 backward: persistent accumulate kernel, partial reduction + inverse transform, arg-max term
@@ -853,6 +878,33 @@ int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float*
     DISPATCH_N(N, (sensor_fwd_impl<NN_>(img, psf, sensor, img_max, tie_count, tie_pos,
                                         reinterpret_cast<float2*>(otf), reinterpret_cast<float2*>(spectrum), workspace,
                                         B, s)));
+}
+
+int b200cam_sensor_split_supported(int N, int B) {
+    return b200cam_supported(N) && B >= 1 && !(N == 256 && fused_selected(B));
+}
+
+int b200cam_sensor_rows(const float* img, float* spectrum, float* img_max, int* tie_count, int B, int N, void* stream) {
+    if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
+    if (!img || !spectrum || !img_max || !tie_count) return B200CAM_E_NULL;
+    if (!aligned16(img) || !aligned16(spectrum)) return B200CAM_E_ALIGN;
+    if (!b200cam_sensor_split_supported(N, B)) return B200CAM_E_BAD_SIZE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (sensor_rows_impl<NN_>(img, reinterpret_cast<float2*>(spectrum), img_max, tie_count, B, s)));
+}
+
+int b200cam_sensor_finish(const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos, float* otf,
+                          const float* spectrum, void* workspace, size_t workspace_bytes, int B, int N, void* stream) {
+    if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
+    if (!psf || !sensor || !img_max || !tie_count || !tie_pos || !otf || !spectrum || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_sensor_workspace_bytes(N, B, 0)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(sensor) || !aligned16(otf) || !aligned16(workspace) || !aligned16(psf) || !aligned16(spectrum))
+        return B200CAM_E_ALIGN;
+    if (!b200cam_sensor_split_supported(N, B)) return B200CAM_E_BAD_SIZE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (sensor_finish_impl<NN_>(psf, sensor, img_max, tie_count, tie_pos, reinterpret_cast<float2*>(otf),
+                                           reinterpret_cast<const float2*>(spectrum), SensorWs(workspace, NN_, B, false),
+                                           B, s)));
 }
 
 int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* sensor, const float* img_max,

@@ -44,6 +44,14 @@ class DevicePlan:
         self.otf_floats = self.lib.b200cam_otf_bytes(N) // 4
         self.process_group = None      # set by Camera.data_parallel(): all-reduce dL/dh over ranks
         self.average_grads = True
+        self._side_stream = None       # runs the PSF-independent half of the sensor forward beside the PSF chain
+
+    def side_stream(self) -> torch.cuda.Stream:
+        """High-priority stream for the PSF chain: its small kernels must be dispatched ahead of the thousands of
+        CTAs of the image row pass that runs beside it on the caller's stream."""
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        return self._side_stream
 
     def psf_workspace(self) -> torch.Tensor:
         return self._psf_ws
@@ -71,21 +79,32 @@ def _as_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 
 class PsfSynth(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h: torch.Tensor, plan: DevicePlan):
+    def forward(ctx, h: torch.Tensor, plan: DevicePlan, stream: torch.cuda.Stream | None = None):
+        """`stream`: enqueue the kernels there (after everything already on the current stream) and return WITHOUT
+        joining - the caller must `current_stream().wait_stream(stream)` before using the outputs."""
         N = plan.N
         hc = _as_f32(h.detach(), plan.device).reshape(N, N)
         psf = torch.empty(1, 3, N, N, dtype=torch.float32, device=plan.device)
         field = torch.empty(3, N, N, 2, dtype=torch.float32, device=plan.device)
         stats = torch.empty(4, dtype=torch.float32, device=plan.device)
         ws = plan.psf_workspace()
+        losses = torch.empty(2, dtype=torch.float32, device=plan.device)
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream(plan.device))
+        launch = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream()
         with torch.cuda.device(plan.index):
             _lib.check(plan.lib.b200cam_psf_fwd(
                 _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho), plan.kappa,
-                _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), N, _stream()))
+                _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), N, launch))
         ctx.plan = plan
         ctx.h_shape = h.shape
         ctx.save_for_backward(hc, psf, field, stats)
-        return psf, stats[1:3].clone()          # losses = (loss_rad, centering_loss)
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                losses.copy_(stats[1:3])
+        else:
+            losses.copy_(stats[1:3])
+        return psf, losses                      # losses = (loss_rad, centering_loss)
 
     @staticmethod
     def backward(ctx, g_psf, g_losses):
@@ -104,28 +123,67 @@ class PsfSynth(torch.autograd.Function):
         if plan.process_group is not None:
             from .parallel import allreduce_height_grad
             allreduce_height_grad(grad_h, plan.process_group, plan.average_grads)
-        return grad_h.reshape(ctx.h_shape), None
+        return grad_h.reshape(ctx.h_shape), None, None
+
+
+def _check_img(img: torch.Tensor, N: int) -> None:
+    if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] != N or img.shape[3] != N:
+        raise ValueError(f"expected img of shape (B,3,{N},{N}), got {tuple(img.shape)}")
+
+
+class RowSpectra:
+    """Result of :func:`sensor_rows`: the PSF-independent first half of the sensor forward (row transforms of the
+    images, first half of ``rfftn`` in ``Face-DeId/Camera/Utils.py:8``)."""
+
+    def __init__(self, x, spectrum, img_max, tie_count):
+        self.x, self.spectrum, self.img_max, self.tie_count = x, spectrum, img_max, tie_count
+
+
+def sensor_rows(img: torch.Tensor, plan: DevicePlan):
+    """Enqueue the row transforms of ``img`` on the current stream (they need no PSF, so `Camera.forward` runs them
+    while the PSF chain is busy on the plan's high-priority side stream).
+    Returns None when the split entry points do not apply (empty batch, fused N=256 kernels)."""
+    N = plan.N
+    _check_img(img, N)
+    B = img.shape[0]
+    if B == 0 or not plan.lib.b200cam_sensor_split_supported(N, B):
+        return None
+    x = _as_f32(img.detach(), plan.device)
+    spectrum = torch.empty(plan.lib.b200cam_spectrum_bytes(N, B) // 4, dtype=torch.float32, device=plan.device)
+    img_max = torch.empty(B, dtype=torch.float32, device=plan.device)
+    tie_count = torch.empty(B, dtype=torch.int32, device=plan.device)
+    with torch.cuda.device(plan.index):
+        _lib.check(plan.lib.b200cam_sensor_rows(_lib.ptr(x), _lib.ptr(spectrum), _lib.ptr(img_max), _lib.ptr(tie_count),
+                                                B, N, _stream()))
+    return RowSpectra(x, spectrum, img_max, tie_count)
 
 
 class SensorConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan):
+    def forward(ctx, img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan, rows: RowSpectra | None = None):
         N = plan.N
-        if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] != N or img.shape[3] != N:
-            raise ValueError(f"expected img of shape (B,3,{N},{N}), got {tuple(img.shape)}")
-        x = _as_f32(img.detach(), plan.device)
+        _check_img(img, N)
+        x = rows.x if rows is not None else _as_f32(img.detach(), plan.device)
         p = _as_f32(psf.detach(), plan.device).reshape(3, N, N)
         B = x.shape[0]
         sensor = torch.empty_like(x)
-        img_max = torch.empty(B, dtype=torch.float32, device=plan.device)
-        tie_count = torch.empty(B, dtype=torch.int32, device=plan.device)
+        img_max = rows.img_max if rows is not None else torch.empty(B, dtype=torch.float32, device=plan.device)
+        tie_count = rows.tie_count if rows is not None else torch.empty(B, dtype=torch.int32, device=plan.device)
         tie_pos = torch.empty(B, 8, dtype=torch.int32, device=plan.device)
         otf = torch.empty(plan.otf_floats, dtype=torch.float32, device=plan.device)
         # keep the image spectra for the backward (what autograd would save) only when a gradient is wanted
-        spectrum = None
-        if B > 0 and any(ctx.needs_input_grad[:2]):
+        spectrum = rows.spectrum if rows is not None else None
+        if rows is None and B > 0 and any(ctx.needs_input_grad[:2]):
             spectrum = torch.empty(plan.lib.b200cam_spectrum_bytes(N, B) // 4, dtype=torch.float32, device=plan.device)
-        if B > 0:
+        if rows is not None:
+            ws = plan.sensor_workspace(B)
+            with torch.cuda.device(plan.index):
+                _lib.check(plan.lib.b200cam_sensor_finish(
+                    _lib.ptr(p), _lib.ptr(sensor), _lib.ptr(img_max), _lib.ptr(tie_count), _lib.ptr(tie_pos),
+                    _lib.ptr(otf), _lib.ptr(spectrum), _lib.ptr(ws), ws.numel(), B, N, _stream()))
+            if not any(ctx.needs_input_grad[:2]):
+                spectrum = None
+        elif B > 0:
             ws = plan.sensor_workspace(B)
             with torch.cuda.device(plan.index):
                 _lib.check(plan.lib.b200cam_sensor_fwd(
@@ -156,12 +214,12 @@ class SensorConv(torch.autograd.Function):
                     _lib.ptr(tie_pos), _lib.ptr(p), _lib.ptr(otf), _lib.ptr(ctx.spectrum), _lib.ptr(grad_psf),
                     _lib.ptr(grad_img),
                     _lib.ptr(ws), ws.numel(), B, N, _stream()))
-        return grad_img, grad_psf.reshape(ctx.psf_shape), None
+        return grad_img, grad_psf.reshape(ctx.psf_shape), None, None
 
 
-def psf_synth(h: torch.Tensor, plan: DevicePlan):
-    return PsfSynth.apply(h, plan)
+def psf_synth(h: torch.Tensor, plan: DevicePlan, stream: torch.cuda.Stream | None = None):
+    return PsfSynth.apply(h, plan, stream)
 
 
-def sensor_conv(img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan) -> torch.Tensor:
-    return SensorConv.apply(img, psf, plan)
+def sensor_conv(img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan, rows: RowSpectra | None = None) -> torch.Tensor:
+    return SensorConv.apply(img, psf, plan, rows)

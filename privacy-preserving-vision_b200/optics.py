@@ -61,6 +61,7 @@ class Camera(nn.Module):
         self.centering_loss = None
         self.psf_rad = None
 
+        self.overlap_psf = True          # run the PSF-independent half of forward() beside the PSF synthesis
         self._plans: dict[torch.device, F.DevicePlan] = {}
         self._pending_centering = None
         self._process_group = None
@@ -106,16 +107,30 @@ class Camera(nn.Module):
         h = self.get_Heith_Map()
         return self.k.to(h.device) * self.flmb.to(h.device) * h
 
-    def get_psf(self):
+    def get_psf(self, _stream=None):
         h = self.get_Heith_Map()
         plan = self._plan(h.device)
-        psf, losses = F.psf_synth(h, plan)
+        psf, losses = F.psf_synth(h, plan, _stream)
         self.psfs = psf
         self.loss_rad = losses[0]
         self._pending_centering = losses[1]
         return self.psfs
 
     def forward(self, img):
-        psf = self.get_psf()
+        # The PSF synthesis is a chain of small latency-bound kernels and the row transforms of the images do not
+        # depend on it: put the chain on a high-priority side stream, run the row pass on the current stream meanwhile
+        # and join before the spectral product.
+        h_dev = self.Zer_train.device
+        overlap = (self.overlap_psf and torch.is_tensor(img) and img.is_cuda and img.dim() == 4 and img.shape[0] > 0
+                   and h_dev.type == "cuda")
+        if not overlap:
+            psf = self.get_psf()
+            self.centering_loss = self._pending_centering
+            return F.sensor_conv(img, psf, self._plan(psf.device))
+        plan = self._plan(img.device)
+        side = plan.side_stream()
+        psf = self.get_psf(_stream=side)                       # enqueued on `side`, not joined yet
+        rows = F.sensor_rows(img, plan) if psf.device == img.device else None
+        torch.cuda.current_stream(psf.device).wait_stream(side)
         self.centering_loss = self._pending_centering
-        return F.sensor_conv(img, psf, self._plan(psf.device))
+        return F.sensor_conv(img, psf, self._plan(psf.device), rows)
