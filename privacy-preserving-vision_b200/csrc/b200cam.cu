@@ -1,6 +1,5 @@
 // b200cam: __global__ wrappers, launch sequencing and the C ABI (include/b200cam.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -196,6 +195,38 @@ __global__ void __launch_bounds__(256) k_f256_tie(TieSpatialParams p) {
 // PSF chain as ONE cooperative launch per direction: the same bodies, run as virtual blocks, with
 // grid-wide barriers where the multi-kernel version had kernel boundaries.
 // ------------------------------------------------------------------------------------------
+// Grid-wide barrier for the cooperative PSF kernels (all CTAs are co-resident: cudaLaunchCooperativeKernel).
+// One monotonically increasing arrival counter; barrier number k (1-based) waits for k * gridDim.x arrivals.
+// ~1.2 us on 192 CTAs (one L2 atomic + one polled line), against ~5 us for cooperative_groups' grid.sync().
+struct GridBarrier {
+    unsigned* ctr;      // [2]: arrivals, departures; both zero between launches
+    unsigned k = 0;
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ++k;
+            __threadfence();
+            atomicAdd(ctr, 1u);
+            const unsigned target = k * gridDim.x;
+            const long long t0 = clock64();          // never hang the device: give up after ~1 s (results are then garbage)
+            while (*reinterpret_cast<volatile unsigned*>(ctr) < target && clock64() - t0 < 2000000000LL) {}
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    // after the last barrier: the last CTA to leave zeroes the counters for the next launch
+    __device__ __forceinline__ void finish() {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+                ctr[0] = 0;
+                ctr[1] = 0;
+                __threadfence();
+            }
+        }
+    }
+};
+
 constexpr int COOP_THREADS = 384;   // >= the widest body (3 wavelength groups of the N=1024 row pass)
 
 struct PsfFwdArgs {
@@ -203,12 +234,12 @@ struct PsfFwdArgs {
     CColsMixParams mix;
     CRowsInvParams rows_inv; IntensityEpilogue inten;
     PsfFinaliseParams fin;
+    unsigned* barrier;
 };
 
 template <int N>
 __global__ void __launch_bounds__(COOP_THREADS) k_psf_fwd_coop(PsfFwdArgs a) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+    GridBarrier grid{a.barrier};
     __shared__ float red[3 * EW_THREADS + 2];
     using T = Tile<N>;
     const int G = gridDim.x;
@@ -231,6 +262,7 @@ __global__ void __launch_bounds__(COOP_THREADS) k_psf_fwd_coop(PsfFwdArgs a) {
         VirtualExec ex{static_cast<int>(blockIdx.x), 0, EW_THREADS};
         psf_finalise_body(ex, a.fin, G, red);
     }
+    grid.finish();
 }
 
 struct PsfBwdArgs {
@@ -238,12 +270,12 @@ struct PsfBwdArgs {
     CRowsFwdParams rows_fwd; GradFieldLoad gload;
     CColsMixParams mix;
     CRowsInvParams rows_inv; PupilLoad pupil; float* gh;
+    unsigned* barrier;
 };
 
 template <int N>
 __global__ void __launch_bounds__(COOP_THREADS) k_psf_bwd_coop(PsfBwdArgs a) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+    GridBarrier grid{a.barrier};
     __shared__ float red[3 * EW_THREADS + 2];
     using T = Tile<N>;
     const int G = gridDim.x;
@@ -266,6 +298,7 @@ __global__ void __launch_bounds__(COOP_THREADS) k_psf_bwd_coop(PsfBwdArgs a) {
         VirtualExec ex{vb, 0, HGradSmem<N>::THREADS};
         crows_inv_hgrad_body<N>(ex, a.rows_inv, a.pupil, a.gh, SMEM2);
     }
+    grid.finish();
 }
 
 template <int N>
@@ -293,7 +326,7 @@ constexpr int MAX_DEV = 64;
 constexpr int EW_GRID = 296;   // 2 x 148 SMs for the element-wise / reduction kernels
 
 inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
-struct DeviceState { float2* tw[11] = {nullptr}; int sms = 0; int coop_grid[11] = {0}; };
+struct DeviceState { float2* tw[11] = {nullptr}; int sms = 0; int coop_grid[11] = {0}; unsigned* bar = nullptr; };
 static DeviceState g_state[MAX_DEV];
 static std::mutex g_mutex;
 
@@ -302,20 +335,27 @@ static int sm_count() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 0;
     return g_state[dev].sms;
 }
-// The PSF chain is a dozen tiny dependent kernels.  Launched eagerly, one cooperative kernel with grid-wide
-// barriers is faster (measured 346 vs 405 us per step); replayed from a CUDA graph the kernel boundaries are
-// cheaper than the grid barriers (284 vs 314 us).  So: cooperative unless the stream is being captured.
-// B200CAM_COOP=0/1 forces one or the other.
+// The PSF chain is a dozen tiny dependent steps.  Launched eagerly it runs as ONE cooperative kernel per direction
+// with grid-wide barriers (GridBarrier above) where the multi-kernel version has kernel boundaries: that saves the
+// CPU launch cost of 6 kernels.  Replayed from a CUDA graph the two cost the same device time (30 us per direction,
+// the steps themselves are latency bound) and the multi-kernel version releases its SMs between steps, which matters
+// when the image row pass runs beside it (261 vs 267 us per step) - so: cooperative unless the stream is being
+// captured.  B200CAM_COOP=0/1 forces one or the other.
 static int coop_grid(int N, cudaStream_t s) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 0;
     static const int mode = [] { const char* e = getenv("B200CAM_COOP"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
-    if (mode == 0) return 0;
+    if (mode == 0 || g_state[dev].bar == nullptr) return 0;
     if (mode < 0) {
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return 0;
     }
     return g_state[dev].coop_grid[log2i(N)];
+}
+static unsigned* coop_barrier(int which) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    return g_state[dev].bar + 2 * which;
 }
 // N=256 has two implementations of the sensor path: the generic row/column/row kernels (kernels.cuh) and the fused
 // one-CTA-per-plane TMEM kernels (f256.cuh).  The fused kernels execute 2.3x fewer instructions and move half the
@@ -484,7 +524,7 @@ static int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const
     IntensityEpilogue epi{field, ws.I, ws.part_rows, ws.arrive, N};
     PsfFinaliseParams fin{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, nrow, N};
     if (const int G = coop_grid(N, s)) {
-        PsfFwdArgs args{rf, load, mix, ri, epi, fin};
+        PsfFwdArgs args{rf, load, mix, ri, epi, fin, coop_barrier(0)};
         void* kargs[] = {&args};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_psf_fwd_coop<N>), dim3(G), dim3(COOP_THREADS), kargs,
                                        coop_smem_bytes<N>(), s));
@@ -517,7 +557,8 @@ static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, c
     CRowsInvParams ri{ws.st, tw};
     if (const int G = coop_grid(N, s)) {
         PsfBwdArgs args{PsfGradPrepParams{gpsf, gscal, psf, rho, stats, ws.gtot, ws.part_ew, N}, rf,
-                        GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, G, N}, mix, ri, pupil, grad_h};
+                        GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, G, N}, mix, ri, pupil, grad_h,
+                        coop_barrier(1)};
         void* kargs[] = {&args};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_psf_bwd_coop<N>), dim3(G), dim3(COOP_THREADS), kargs,
                                        coop_smem_bytes<N>(), s));
@@ -781,6 +822,12 @@ int b200cam_init(int N) {
     std::lock_guard<std::mutex> lock(g_mutex);
     const int l = log2i(N);
     if (g_state[dev].tw[l] != nullptr) return 0;
+    if (g_state[dev].bar == nullptr) {
+        unsigned* bar = nullptr;
+        CK(cudaMalloc(&bar, 4 * sizeof(unsigned)));
+        CK(cudaMemset(bar, 0, 4 * sizeof(unsigned)));
+        g_state[dev].bar = bar;
+    }
     float2* tw = nullptr;
     CK(cudaMalloc(&tw, sizeof(float2) * N));
     k_fill_twiddle<<<(N + 255) / 256, 256>>>(tw, N);
