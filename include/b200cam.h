@@ -111,6 +111,20 @@ int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* 
                        float* grad_psf, float* grad_img,
                        void* workspace, size_t workspace_bytes, int B, int N, void* stream);
 
+/* Plain circular convolution of a batch with one centred kernel per channel, and its adjoints.  Replaces the FFT
+ * part of img_psf_conv (Image_Caption/Camera/Utils.py:251-297): the caller zero-pads image and PSF to N (a power of
+ * two, Utils.py:266-277 and psf2otf :127-158), then
+ *     out_b = irfft2( rfft2(img_b) * rfft2(roll(kernel, -N/2)) )               (Utils.py:279-288)
+ * (the reference's abs / crop / nearest resize and the batch-global max of Lens.py:312 stay in the wrapper).
+ *   img, out    [B][3][N][N]      kernel [3][N][N] (centre at N/2, N/2)
+ *   otf         b200cam_otf_bytes(N)   out (fwd) / in (bwd)
+ *   spectrum    b200cam_spectrum_bytes(N,B) or NULL: row spectra of img kept for the backward
+ *   grad_kernel [3][N][N] out: sum over the batch;  grad_img [B][3][N][N] out or NULL */
+int b200cam_conv_fwd(const float* img, const float* kernel, float* out, float* otf, float* spectrum, void* workspace,
+                     size_t workspace_bytes, int B, int N, void* stream);
+int b200cam_conv_bwd(const float* grad_out, const float* img, const float* otf, const float* spectrum, float* grad_kernel,
+                     float* grad_img, void* workspace, size_t workspace_bytes, int B, int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,36 @@ def main() -> None:
         np.savez_compressed(out_dir / f"{name}.npz", **payload)
         print(name, "gap", r["min_top2_gap"].item(), "loss_rad", r["loss_rad"].item(),
               "centering", r["centering_loss"].item(), "bytes", (out_dir / f"{name}.npz").stat().st_size)
+    make_caption_fixture(out_dir)
+
+
+def make_caption_fixture(out_dir: Path) -> None:
+    """tests/golden/caption_*.npz: outputs of the UNMODIFIED ``OpticsZernike`` (Image_Caption/Camera/Lens.py:11) on
+    the seeded inputs of tests/test_lens_oracle.py (height tolerance off; small wave grid so the file stays small)."""
+    import os
+    import tempfile
+    sys.path.insert(0, str(REPO / "tests"))
+    import test_lens_oracle as tlo
+    Lens = ref_shim.load_image_caption_lens()
+    for case, c in tlo.CASES.items():
+        img, w, coeffs = tlo.inputs(case)
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)                      # the reference writes zernike_volumes/*.npy into cwd
+            try:
+                cam = Lens.OpticsZernike(input_shape=[1, c["patch"], c["patch"], 3], device=torch.device("cpu"),
+                                         wave_resolution=(c["wave"], c["wave"]), patch_size=c["patch"],
+                                         sample_interval=3e-6, zernike_terms=c["terms"], height_tolerance=None)
+                with torch.no_grad():
+                    cam.zernike_coeffs_train.copy_(coeffs[3])
+                    cam.zernike_coeffs_no_train2.copy_(coeffs[4:])
+                sensor, psf, _, _ = cam(img)
+                (sensor * w).sum().backward()
+            finally:
+                os.chdir(cwd)
+        np.savez_compressed(out_dir / f"{case}.npz", sensor=sensor.detach().numpy(), psf=psf.detach().numpy(),
+                            grad_defocus=cam.zernike_coeffs_train.grad.numpy())
+        print("wrote", case)
 
 
 if __name__ == "__main__":

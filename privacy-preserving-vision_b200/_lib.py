@@ -45,6 +45,10 @@ _SIGNATURES = {
     "b200cam_sensor_rows": (ctypes.c_int, [_f, _f, _f, _f, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "b200cam_sensor_finish": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f,
                                              _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "b200cam_conv_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p]),
+    "b200cam_conv_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p]),
     "b200cam_sensor_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f,
                                           _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
 }

@@ -657,6 +657,75 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     return 0;
 }
 
+// Plain circular convolution with a centred kernel (no per-image normalisation): the building block of the
+// Image_Caption camera's padded linear convolution (img_psf_conv, Image_Caption/Camera/Utils.py:251-297).
+//   out_b = irfft2( rfft2(img_b) * rfft2(roll(kernel, -N/2)) )
+template <int N>
+static int conv_fwd_impl(const float* img, const float* kern, float* out, float2* otf, float2* spectrum, void* ws_ptr,
+                         int B, cudaStream_t s) {
+    using T = Tile<N>;
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    SensorWs ws(ws_ptr, N, B, false);
+    float2* srow = spectrum != nullptr ? spectrum : ws.stx;
+    int rc = sensor_rows_impl<N>(img, srow, nullptr, nullptr, B, s);
+    if (rc) return rc;
+    rc = otf_impl<N>(kern, otf, tw, 1.0f / (static_cast<float>(N) * N), s);
+    if (rc) return rc;
+    const int planes = 3 * B;
+    const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
+    const int chunk = conv_chunk(N, B);
+    k_cols_conv<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, chunk, 0, 1.0f});
+    LAUNCH_CHECK();
+    k_rows_c2r<N><<<dim3(N / T::ROWS, planes), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsC2RParams{ws.st2, out, tw, nullptr, 1.0f, nullptr, nullptr, 0});
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// adjoints of conv_fwd: grad_kern = sum_b corr(img_b, g_b) (centred frame), grad_img_b = corr(g_b, kernel) (optional)
+template <int N>
+static int conv_bwd_impl(const float* g, const float* img, const float2* otf, const float2* spectrum, float* grad_kern,
+                         float* grad_img, void* ws_ptr, int B, cudaStream_t s) {
+    using T = Tile<N>;
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    SensorWs ws(ws_ptr, N, B, true);
+    const int planes = 3 * B, tiles = N / T::ROWS;
+    const dim3 rgrid(tiles, planes);
+    const float2* srow = spectrum;
+    if (srow == nullptr) {
+        int rc = sensor_rows_impl<N>(img, ws.stx, nullptr, nullptr, B, s);
+        if (rc) return rc;
+        srow = ws.stx;
+    }
+    int rc = sensor_rows_impl<N>(g, ws.stg, nullptr, nullptr, B, s);
+    if (rc) return rc;
+    const int nchunks = accum_chunks(N, B);
+    const int chunk = (B + nchunks - 1) / nchunks;
+    const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
+    k_cols_accum<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        ColsAccumParams{srow, ws.stg, ws.partial, tw, nullptr, nullptr, nullptr, nullptr, B, chunk});
+    LAUNCH_CHECK();
+    k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
+        ColsReduceInvParams{ws.partial, ws.stp, tw, (B + chunk - 1) / chunk, 1.0f / (static_cast<float>(N) * N)});
+    LAUNCH_CHECK();
+    k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsC2RParams{ws.stp, grad_kern, tw, nullptr, 1.0f, nullptr, nullptr, 0});
+    LAUNCH_CHECK();
+    if (grad_img != nullptr) {
+        const int cchunk = conv_chunk(N, B);
+        k_cols_conv<N><<<dim3(colgroups, (B + cchunk - 1) / cchunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+            ColsConvParams{ws.stg, ws.stg, otf, tw, nullptr, B, cchunk, 1, 1.0f});
+        LAUNCH_CHECK();
+        k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+            RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f, nullptr, nullptr, 0});
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 template <int N>
 static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
                            int* tie_pos, float2* otf, float2* spectrum, void* ws_ptr, int B, cudaStream_t s) {
@@ -952,6 +1021,32 @@ int b200cam_sensor_finish(const float* psf, float* sensor, float* img_max, int* 
     DISPATCH_N(N, (sensor_finish_impl<NN_>(psf, sensor, img_max, tie_count, tie_pos, reinterpret_cast<float2*>(otf),
                                            reinterpret_cast<const float2*>(spectrum), SensorWs(workspace, NN_, B, false),
                                            B, s)));
+}
+
+int b200cam_conv_fwd(const float* img, const float* kernel, float* out, float* otf, float* spectrum, void* workspace,
+                     size_t workspace_bytes, int B, int N, void* stream) {
+    if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
+    if (!img || !kernel || !out || !otf || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_sensor_workspace_bytes(N, B, 0)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(img) || !aligned16(kernel) || !aligned16(out) || !aligned16(otf) || !aligned16(workspace) ||
+        (spectrum && !aligned16(spectrum)))
+        return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (conv_fwd_impl<NN_>(img, kernel, out, reinterpret_cast<float2*>(otf), reinterpret_cast<float2*>(spectrum),
+                                      workspace, B, s)));
+}
+
+int b200cam_conv_bwd(const float* grad_out, const float* img, const float* otf, const float* spectrum, float* grad_kernel,
+                     float* grad_img, void* workspace, size_t workspace_bytes, int B, int N, void* stream) {
+    if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
+    if (!grad_out || !img || !otf || !grad_kernel || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_sensor_workspace_bytes(N, B, grad_img != nullptr)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(grad_out) || !aligned16(img) || !aligned16(otf) || !aligned16(grad_kernel) || !aligned16(workspace) ||
+        (spectrum && !aligned16(spectrum)) || (grad_img && !aligned16(grad_img)))
+        return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (conv_bwd_impl<NN_>(grad_out, img, reinterpret_cast<const float2*>(otf),
+                                      reinterpret_cast<const float2*>(spectrum), grad_kernel, grad_img, workspace, B, s)));
 }
 
 int b200cam_sensor_bwd(const float* grad_sensor, const float* img, const float* sensor, const float* img_max,

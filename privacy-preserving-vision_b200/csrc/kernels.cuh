@@ -479,7 +479,7 @@ struct ColsAccumParams {
     const float2* stg;      // [B*3][NC][N] row-transformed upstream gradient
     float2* partial;        // [nchunks][3][NC][N]
     const float2* tw;
-    const float* img_max;   // [B]
+    const float* img_max;   // [B]; nullptr: no per-image scale (plain convolution adjoint)
     // arg-max term of the amax backward, applied as  G' = G/m - coef * sum_t exp(-2 pi i (v ty + u tx)/N)
     // on the channel that holds the tie (nullable: term left to the spatial tie_term kernel)
     const float* coef;      // [B]
@@ -532,7 +532,7 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
             const int cu = cu0 + jc;
             if (cu < TOTAL && bb < P::R1) {
                 AccumState<N>& s = st[ex.slot(tid)];
-                const float inv_m = 1.0f / ld_ro(p.img_max + b);
+                const float inv_m = p.img_max != nullptr ? 1.0f / ld_ro(p.img_max + b) : 1.0f;
                 float2 vx[P::R2], vg[P::R2];
                 P::stepB(vx, bb, Ex + jc * P::E_SIZE);
                 P::stepB(vg, bb, Eg + jc * P::E_SIZE);

@@ -33,13 +33,14 @@ class DevicePlan:
         if not self.lib.b200cam_supported(N):
             raise ValueError(f"b200cam supports N in (64,128,256,512,1024), got {N}")
         _lib.ensure_init(N, self.index)
-        t = tables if tables is not None else K.build(N)
-        self.A = torch.view_as_real(t.table_A).contiguous().to(device)
-        self.Ht = torch.view_as_real(t.table_Ht).contiguous().to(device)
-        self.rho = t.rho.to(torch.float32).contiguous().to(device)
-        self.kappa = (ctypes.c_float * 3)(*t.kappa)
-        self.kappa_list = list(t.kappa)
-        self._psf_ws = torch.empty(self.lib.b200cam_psf_workspace_bytes(N), dtype=torch.uint8, device=device)
+        if tables is not False:           # tables=False: convolution-only plan (Image_Caption camera), no PSF chain
+            t = tables if tables is not None else K.build(N)
+            self.A = torch.view_as_real(t.table_A).contiguous().to(device)
+            self.Ht = torch.view_as_real(t.table_Ht).contiguous().to(device)
+            self.rho = t.rho.to(torch.float32).contiguous().to(device)
+            self.kappa = (ctypes.c_float * 3)(*t.kappa)
+            self.kappa_list = list(t.kappa)
+            self._psf_ws = torch.empty(self.lib.b200cam_psf_workspace_bytes(N), dtype=torch.uint8, device=device)
         self._sensor_ws: dict[int, torch.Tensor] = {}
         self.otf_floats = self.lib.b200cam_otf_bytes(N) // 4
         self.process_group = None      # set by Camera.data_parallel(): all-reduce dL/dh over ranks

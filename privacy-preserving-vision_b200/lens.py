@@ -1,0 +1,338 @@
+"""``OpticsZernike`` - drop-in for the Image_Caption optical encoder (``Image_Caption/Camera/Lens.py:11``).
+
+Same constructor signature, parameters / ``state_dict`` keys (``zernike_coeffs_no_train`` (3,1,1),
+``zernike_coeffs_no_train2`` (T-4,1,1), ``zernike_coeffs_train`` (1,1)), ``forward`` signature and
+4-tuple result ``(sensor_img, psf, zernike_coeffs_concat, loss)``.
+
+What runs where
+* the per-image work - the padded *linear* convolution of every image channel with its PSF
+  (``img_psf_conv``, ``Image_Caption/Camera/Utils.py:251-297``) and its backward into the PSF - runs in the
+  b200cam CUDA kernels (``b200cam_conv_fwd`` / ``b200cam_conv_bwd``: power-of-two 2*patch FFT size);
+* the batch-independent PSF synthesis (``Lens.py:158-239``: phase plate, spherical wavefront, aperture,
+  Fresnel propagation on a (5/4 * wave_res)^2 grid - 1344^2 = 2^6*3*7 for the shipped config, not a power of
+  two - area down-sampling, normalisation) is expressed in torch tensor ops on the module's device with the
+  reference's dtypes (fp64 phases, complex128 propagation) and uses the library FFT for the odd size.
+  A hand-written mixed-radix kernel for that step is listed as "next" in DESIGN.md;
+* ``abs`` / crop / nearest resize (``Utils.py:289-295``) and the batch-global max (``Lens.py:312``) are
+  element-wise torch ops around the kernel; with ``data_parallel(group)`` the max is all-reduced and its backward
+  term is routed to the owning rank, so N ranks reproduce the 1-GPU result.
+
+Not reproduced: comet.ml summaries (``attach_summaries``), the ``psf_lab`` image file path, ``upsample=True``
+(1792^2 convolution, not a power of two) - they raise ``NotImplementedError`` - and the side effect of caching the
+Zernike volume as ``zernike_volumes/*.npy`` in the working directory (``Lens.py:66-75``).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as TF
+
+from . import _lib
+from . import functional as F
+from .zernike import zernike_volume as _zernike_volume
+
+
+def get_zernike_volume(resolution, n_terms, scale_factor=1e-6):
+    """Noll Zernike stack in metres (reference: ``Image_Caption/Camera/Utils.py:75-77``, via poppy)."""
+    return _zernike_volume(resolution, n_terms, scale_factor)
+
+
+def _disc_masks(size: int = 256, radius: int = 32):
+    """mask_1 (1 outside the disc) and mask_2 (1 inside), (size,size,3) fp64, as drawn by ``cv2.circle`` with
+    ``thickness=-1`` at ``Lens.py:113-129``."""
+    try:
+        import cv2
+        m1 = np.ones((size, size, 3))
+        cv2.circle(img=m1, center=[size // 2, size // 2], radius=radius, color=0, thickness=-1, lineType=cv2.FILLED)
+        m2 = np.zeros((size, size, 3))
+        cv2.circle(img=m2, center=[size // 2, size // 2], radius=radius, color=(255, 255, 255), thickness=-1,
+                   lineType=cv2.FILLED)
+        m2 = m2 / m2.max()
+    except ImportError:       # same disc from its definition when OpenCV is not installed
+        yy, xx = np.mgrid[0:size, 0:size]
+        inside = ((xx - size // 2) ** 2 + (yy - size // 2) ** 2 <= radius ** 2).astype(np.float64)
+        m2 = np.repeat(inside[:, :, None], 3, axis=2)
+        m1 = 1.0 - m2
+    return torch.from_numpy(m1), torch.from_numpy(m2)
+
+
+class CircConv(torch.autograd.Function):
+    """out = irfft2(rfft2(img) * rfft2(roll(kernel, -N/2))) per channel, N a power of two (b200cam_conv_fwd/bwd)."""
+
+    @staticmethod
+    def forward(ctx, img: torch.Tensor, kernel: torch.Tensor, plan: F.DevicePlan):
+        N = plan.N
+        x = F._as_f32(img.detach(), plan.device)
+        k = F._as_f32(kernel.detach(), plan.device).reshape(3, N, N)
+        B = x.shape[0]
+        out = torch.empty_like(x)
+        otf = torch.empty(plan.otf_floats, dtype=torch.float32, device=plan.device)
+        spectrum = None
+        if any(ctx.needs_input_grad[:2]):
+            spectrum = torch.empty(plan.lib.b200cam_spectrum_bytes(N, B) // 4, dtype=torch.float32, device=plan.device)
+        ws = plan.sensor_workspace(B)
+        with torch.cuda.device(plan.index):
+            _lib.check(plan.lib.b200cam_conv_fwd(_lib.ptr(x), _lib.ptr(k), _lib.ptr(out), _lib.ptr(otf), _lib.ptr(spectrum),
+                                                 _lib.ptr(ws), ws.numel(), B, N, F._stream()))
+        ctx.plan, ctx.spectrum, ctx.kshape = plan, spectrum, kernel.shape
+        ctx.save_for_backward(x, otf)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan: F.DevicePlan = ctx.plan
+        N = plan.N
+        x, otf = ctx.saved_tensors
+        B = x.shape[0]
+        gc = F._as_f32(g, plan.device)
+        grad_k = torch.empty(3, N, N, dtype=torch.float32, device=plan.device)
+        grad_img = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        ws = plan.sensor_workspace(B)
+        with torch.cuda.device(plan.index):
+            _lib.check(plan.lib.b200cam_conv_bwd(_lib.ptr(gc), _lib.ptr(x), _lib.ptr(otf), _lib.ptr(ctx.spectrum),
+                                                 _lib.ptr(grad_k), _lib.ptr(grad_img), _lib.ptr(ws), ws.numel(), B, N,
+                                                 F._stream()))
+        return grad_img, grad_k.reshape(ctx.kshape), None
+
+
+class GlobalMaxNormalise(torch.autograd.Function):
+    """y = x / max(x) over the whole batch (``Lens.py:312``); with a process group the max is taken over all ranks
+    and the backward's arg-max term (-sum(g*y)/m at the arg-max) is routed to the rank that owns it."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, group):
+        import torch.distributed as dist
+        m_local = x.max()
+        m = m_local.clone()
+        if group is not None and dist.is_initialized():
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+        y = x / m
+        ctx.group = group
+        ctx.save_for_backward(y, m, m_local)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        y, m, m_local = ctx.saved_tensors
+        s = (g * y).sum()
+        if ctx.group is not None and dist.is_initialized():
+            dist.all_reduce(s, op=dist.ReduceOp.SUM, group=ctx.group)
+        # only the rank that holds the maximum carries the arg-max term (no host sync: a 0/1 factor);
+        # exact ties are split evenly like torch's max() backward (cross-rank exact ties: measure zero, not split)
+        owner = (m_local == m).to(g.dtype)
+        ties = (y == 1).to(g.dtype)
+        n = ties.sum().clamp(min=1)
+        return g / m - ties * (owner * s / (m * n)), None
+
+
+class OpticsZernike(nn.Module):
+    def __init__(self,
+                 input_shape,
+                 device,
+                 experiment=None,
+                 sensor_distance=25e-3,
+                 refractive_idcs=np.array([1.499, 1.493, 1.488]),
+                 wave_lengths=np.array([460, 550, 640]) * 1e-9,
+                 height_tolerance=20e-9,
+                 wave_resolution=(736, 736),
+                 patch_size=368,
+                 sample_interval=2e-6,
+                 upsample=False,
+                 frames=8,
+                 optics_cfg=1,
+                 zernike_terms=350,
+                 mask_1=None,
+                 mask_2=None):
+        super().__init__()
+        self.device = device
+        self.sensor_distance = sensor_distance
+        self.height_tolerance = height_tolerance
+        self.upsample = upsample
+        self.patch_size = patch_size
+        self.wave_lengths = np.asarray(wave_lengths, dtype=np.float64)
+        self.sample_interval = sample_interval
+        self.refractive_idcs = np.asarray(refractive_idcs, dtype=np.float64)
+        self.frames = frames
+        self.optics_cfg = optics_cfg
+        self.zernike_terms = zernike_terms
+        self.wave_res = [patch_size * 4, patch_size * 4] if wave_resolution is None else list(wave_resolution)
+        self.physical_size = float(self.wave_res[0] * self.sample_interval)
+        self.channels = input_shape[-1]
+        if self.channels != 3 or len(self.wave_lengths) != 3:
+            raise ValueError("the camera models three wavelengths / colour channels")
+
+        vol = get_zernike_volume(resolution=self.wave_res[0], n_terms=self.zernike_terms).astype(np.float32)
+        self.zernike_volume = torch.tensor(vol, dtype=torch.float32, device=self.device)
+        num = self.zernike_volume.shape[0]
+        inits = np.zeros((num, 1, 1))
+        inits[3] = -22                                           # defocus (Lens.py:88)
+        self.zernike_coeffs_no_train = nn.Parameter(torch.tensor(inits[:3, ...], dtype=torch.float32),
+                                                    requires_grad=False)
+        self.zernike_coeffs_no_train2 = nn.Parameter(torch.tensor(inits[4:, ...], dtype=torch.float32),
+                                                     requires_grad=False)
+        self.zernike_coeffs_train = nn.Parameter(torch.tensor(inits[3, ...], dtype=torch.float32))
+
+        self.training_info = None
+        self.gpu_rank = None
+        self.experiment = experiment
+        m1, m2 = _disc_masks()
+        self.mask_1 = m1.to(self.device)
+        self.mask_2 = m2.to(self.device)
+
+        self._const: dict = {}            # per-device constant tables (wavefront, aperture, transfer function)
+        self._plans: dict = {}
+        self._process_group = None
+
+    # ------------------------------------------------------------------ helpers
+    def data_parallel(self, process_group=None, enabled: bool = True):
+        """Batch sharded over ranks: the batch-global max of ``Lens.py:312`` is all-reduced (one float) in forward
+        and its arg-max term routed to the owning rank in backward."""
+        import torch.distributed as dist
+        self._process_group = (process_group or dist.group.WORLD) if enabled else None
+        return self
+
+    def get_Heith_Map(self):
+        coeffs = torch.cat((self.zernike_coeffs_no_train, self.zernike_coeffs_train.unsqueeze(0),
+                            self.zernike_coeffs_no_train2), 0)
+        return torch.sum(coeffs * self.zernike_volume, dim=0).unsqueeze(0)
+
+    def _constants(self, dev: torch.device):
+        """Spherical wavefront (Lens.py:191-210), aperture (Utils.py:88-97) and Fresnel transfer function
+        (Utils.py:329-373): built in fp64 with numpy exactly like the reference, once per device."""
+        key = (dev, self.optics_cfg)
+        c = self._const.get(key)
+        if c is not None:
+            return c
+        N, M = self.wave_res
+        x, y = np.mgrid[-N // 2:N // 2, -M // 2:M // 2].astype(np.float64)
+        x = x / N * self.physical_size
+        y = y / M * self.physical_size
+        squared_sum = x ** 2 + y ** 2
+        wave_nos = torch.tensor((2. * np.pi / self.wave_lengths).reshape([1, 1, 1, -1]))
+        depth = 1 / 2 if self.optics_cfg == 1 else 1
+        curvature = torch.sqrt(torch.tensor(squared_sum) + torch.tensor(depth, dtype=torch.float64) ** 2)
+        phase = (wave_nos * curvature.unsqueeze(0).unsqueeze(-1)).to(torch.float64)
+        wavefront = torch.cos(phase).to(torch.complex64) + 1.j * torch.sin(phase).to(torch.complex64)
+
+        ax, ay = np.mgrid[-N // 2: N // 2, -M // 2: M // 2].astype(np.float64)
+        r = np.sqrt(ax ** 2 + ay ** 2)[None, :, :, None]
+        aperture = torch.tensor((r < np.amax(ax)).astype(np.float64))
+
+        Mpad, Npad = N // 4, M // 4
+        Mp, Np = N + 2 * Mpad, M + 2 * Npad
+        fx, fy = np.mgrid[-Np // 2:Np // 2, -Mp // 2:Mp // 2]
+        fx = np.fft.ifftshift(fx / (self.sample_interval * Np))
+        fy = np.fft.ifftshift(fy / (self.sample_interval * Mp))
+        sq = (np.square(fx) + np.square(fy))[None, :, :, None]
+        expo = torch.tensor(np.float64(self.wave_lengths * np.pi * -1. * sq * self.sensor_distance), dtype=torch.float64)
+        H = torch.cos(expo).to(torch.complex64) + 1.j * torch.sin(expo).to(torch.complex64)
+        delta = torch.tensor((2. * np.pi / self.wave_lengths).reshape([1, 1, 1, -1])
+                             * (self.refractive_idcs.reshape([1, 1, 1, -1]) - 1.))
+        c = {"wavefront": wavefront.to(dev), "aperture": aperture.to(dev), "H": H.to(dev), "delta": delta.to(dev),
+             "pad": (Mpad, Npad)}
+        self._const[key] = c
+        return c
+
+    def _plan(self, device: torch.device, n: int) -> F.DevicePlan:
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        plan = self._plans.get((device, n))
+        if plan is None:
+            plan = F.DevicePlan(n, device, tables=False)
+            self._plans[(device, n)] = plan
+        return plan
+
+    def _psf(self, height_map: torch.Tensor) -> torch.Tensor:
+        """height map (1,R,R,1) -> normalised PSF (1,P,P,3)  (Lens.py:180-239)."""
+        c = self._constants(height_map.device)
+        if self.height_tolerance is not None:                      # PhasePlate._build, Utils.py:396-406
+            height_map = height_map + ((-self.height_tolerance - self.height_tolerance)
+                                       * torch.rand(list(height_map.shape), dtype=height_map.dtype,
+                                                    device=height_map.device) + self.height_tolerance)
+        phi = (c["delta"] * height_map).to(torch.float64)          # Utils.py:192-205
+        shifts = torch.cos(phi).to(torch.complex64) + 1.j * torch.sin(phi).to(torch.complex64)
+        field = c["aperture"] * (shifts * c["wavefront"])          # Lens.py:212-213 (fp64 mask: complex128 from here)
+        Mpad, Npad = c["pad"]
+        padded = TF.pad(field, [0, 0, Npad, Npad, Mpad, Mpad])
+        obj = torch.fft.fftn(padded.permute(0, 3, 1, 2), dim=[-1, -2]).permute(0, 2, 3, 1)
+        out = torch.fft.ifftn((obj * c["H"]).permute(0, 3, 1, 2), dim=[-1, -2]).permute(0, 2, 3, 1)
+        out = out[:, Mpad:-Mpad, Npad:-Npad, :]
+        psf = torch.square(torch.abs(out))                         # get_intensities, Utils.py:208
+        psf = self._area_downsample(psf, self.patch_size)
+        return psf / torch.sum(psf, dim=[1, 2], keepdim=True)      # per channel (Lens.py:239)
+
+    @staticmethod
+    def _area_downsample(img: torch.Tensor, target: int) -> torch.Tensor:
+        """area_downsampling_tf, Utils.py:216-248."""
+        img = img.to(torch.float32)
+        side = img.shape[1]
+        x = img.permute(0, 3, 1, 2)
+        if side % target == 0:
+            f = side // target
+            return TF.avg_pool2d(x, f, stride=f).permute(0, 2, 3, 1)
+        lcm = abs(target * side) // np.gcd(target, side) / target
+        up = 10 if lcm > 10 else int(lcm)
+        x = TF.interpolate(x, size=2 * [up * target], mode="nearest")     # torchvision Resize(interpolation=0)
+        return TF.avg_pool2d(x, up, stride=up).permute(0, 2, 3, 1)
+
+    def _sensor(self, img: torch.Tensor, psf: torch.Tensor) -> torch.Tensor:
+        """img_psf_conv (Utils.py:251-297): zero-pad to 2P, circular FFT convolution, abs, crop, nearest resize."""
+        P = img.shape[2]
+        if img.dim() != 4 or img.shape[1] != 3 or img.shape[3] != P or psf.shape[1] != P:
+            raise ValueError(f"expected images (B,3,{psf.shape[1]},{psf.shape[1]}), got {tuple(img.shape)}")
+        if img.device.type != "cuda":
+            raise RuntimeError("b200cam runs on CUDA (sm_100a) only; there is no CPU path")
+        n = 2 * P
+        pad = (n - P) / 2
+        pt, pb = int(np.ceil(pad)), int(np.floor(pad))
+        x = TF.pad(img.to(torch.float32), [pt, pb, pt, pb])
+        # psf2otf (Utils.py:127-158): pad so that the PSF centre lands on n/2, the kernel's "centred frame"
+        if (n - P) % 2 != 0:
+            kt, kb = int(np.ceil(pad)), int(np.floor(pad))
+        else:
+            kt, kb = int(pad) + 1, int(pad) - 1
+        k = TF.pad(psf[0].permute(2, 0, 1).to(torch.float32), [kt, kb, kt, kb])          # (3, n, n)
+        res = torch.abs(CircConv.apply(x, k, self._plan(img.device, n)))
+        res = res[:, :, pt + 1:n - pb, pt + 1:n - pb]                                     # (P-1)^2
+        idx = torch.clamp(torch.arange(P, device=img.device) - 1, min=0)                  # nearest resize to P
+        return res.index_select(2, idx).index_select(3, idx)
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, input_img, new_zernike=None, prueba=None, psf_lab=None, enfoco=None):
+        if psf_lab is True:
+            raise NotImplementedError("psf_lab loads '../dataset_paula_real/psf_lab.jpg' in the reference (Lens.py:222-236)")
+        if self.upsample:
+            raise NotImplementedError("upsample=True convolves at the wave resolution (not a power of two)")
+        coeffs = torch.cat((self.zernike_coeffs_no_train, self.zernike_coeffs_train.unsqueeze(0),
+                            self.zernike_coeffs_no_train2), 0)
+        if enfoco is True:                                          # Lens.py:160-162
+            coeffs = coeffs.clone()
+            coeffs[:] = 0
+            coeffs[3] = -22
+        height_map = torch.sum(coeffs * self.zernike_volume, dim=0).unsqueeze(0).unsqueeze(-1)
+        psf = self._psf(height_map)
+
+        loss = None
+        if prueba == "1" or prueba == "3":
+            loss = torch.norm((psf * self.mask_1) - psf)
+        if prueba == "2" or prueba == "3":
+            psf = psf * self.mask_2
+
+        sensor = self._sensor(input_img, psf)
+        np.random.uniform(low=0.001, high=0.02)                     # noise_sigma is drawn and discarded (Lens.py:295)
+        sensor = GlobalMaxNormalise.apply(sensor, self._process_group)
+        return sensor, psf, coeffs, loss
+
+    def load_pretrained_from_numpy(self, path):
+        weights = np.load(path)['optics_trained_weights']
+        self.state_dict()['zernike_coeffs_train'].copy_(torch.tensor(weights))
+
+    def load_pretrained_from_warmup(self, path):
+        import os
+        ckpt = torch.load(os.path.expanduser(path), map_location=self.device)
+        self.state_dict()['zernike_coeffs_train'].copy_(ckpt['model_state_dict']['optics.zernike_coeffs_train'])

@@ -74,3 +74,35 @@ def test_two_rank_gradient_equals_single_process(tmp_path):
     img, w, h0 = synth.images(B, N, 3), synth.upstream_grad(B, N, 4), synth.height_map(N, 5)
     ref = _grad(img, w, h0, 1.0 / WORLD)                           # mean over ranks of the data term
     assert rel_l2(g0, ref) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Image_Caption camera: batch-global max (Lens.py:312) over two ranks == one process
+# ---------------------------------------------------------------------------------------------------------------
+def _max_worker(rank: int, port: int, result_dir: str):
+    from b200cam.lens import GlobalMaxNormalise
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    parallel.init_from_env("gloo")
+    g = torch.Generator().manual_seed(11)
+    x_all, w_all = torch.rand(6, 3, 8, 8, generator=g), torch.rand(6, 3, 8, 8, generator=g)
+    x = parallel.shard(x_all, rank, WORLD).clone().requires_grad_(True)
+    y = GlobalMaxNormalise.apply(x, dist.group.WORLD)
+    (y * parallel.shard(w_all, rank, WORLD)).sum().backward()
+    torch.save((y.detach(), x.grad), os.path.join(result_dir, f"max_{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_global_max_equals_single_process(tmp_path):
+    port = _free_port()
+    mp.spawn(_max_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    g = torch.Generator().manual_seed(11)
+    x_all, w_all = torch.rand(6, 3, 8, 8, generator=g), torch.rand(6, 3, 8, 8, generator=g)
+    x = x_all.clone().requires_grad_(True)
+    (x / x.max() * w_all).sum().backward()                        # the reference expression (Lens.py:312)
+    ys, gs = zip(*[torch.load(os.path.join(str(tmp_path), f"max_{r}.pt")) for r in range(WORLD)])
+    assert torch.allclose(torch.cat(ys), (x / x.max()).detach(), rtol=1e-6, atol=0)
+    assert torch.allclose(torch.cat(gs), x.grad, rtol=1e-5, atol=1e-6)

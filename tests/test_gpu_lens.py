@@ -1,0 +1,83 @@
+"""GPU (-m gpu): the Image_Caption camera (``b200cam.lens.OpticsZernike``: CUDA convolution kernels behind the
+reference's nn.Module interface) against the CPU oracle ``oracle/lens_oracle.py`` and the reference golden vectors.
+Tolerances: rel-L2 <= 1e-4 on sensor images and the PSF, <= 1e-3 on gradients (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+
+import b200cam.zernike as zern
+from b200cam.lens import OpticsZernike
+from conftest import GOLDEN_DIR, rel_l2
+from oracle import lens_oracle as lo
+from test_lens_oracle import CASES, inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def make(wave, patch, terms, coeffs):
+    dev = torch.device("cuda", 0)
+    cam = OpticsZernike(input_shape=[1, patch, patch, 3], device=dev, wave_resolution=(wave, wave), patch_size=patch,
+                        sample_interval=3e-6, zernike_terms=terms, height_tolerance=None).to(dev)
+    with torch.no_grad():
+        cam.zernike_coeffs_train.copy_(coeffs[3])
+        cam.zernike_coeffs_no_train2.copy_(coeffs[4:])
+    return cam
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_matches_reference_golden_vectors(case):
+    c = CASES[case]
+    gold = np.load(GOLDEN_DIR / f"{case}.npz")
+    img, w, coeffs = inputs(case)
+    cam = make(c["wave"], c["patch"], c["terms"], coeffs)
+    sensor, psf, zc, loss = cam(img.cuda())
+    (sensor * w.cuda()).sum().backward()
+    assert loss is None and zc.shape == (c["terms"], 1, 1)
+    assert sensor.shape == img.shape and psf.shape == (1, c["patch"], c["patch"], 3)
+    assert rel_l2(sensor, torch.from_numpy(gold["sensor"])) <= 1e-4
+    assert rel_l2(psf, torch.from_numpy(gold["psf"])) <= 1e-4
+    gd = float(gold["grad_defocus"].reshape(-1)[0])
+    assert abs(float(cam.zernike_coeffs_train.grad) - gd) <= 1e-3 * abs(gd)
+    assert float(sensor.max()) == 1.0                                          # Lens.py:312
+
+
+def test_shipped_geometry_patch256():
+    """wave_resolution 896, patch 256 (train.py:64-66) -> 1344^2 propagation, 512^2 convolution; 12 Zernike terms
+    instead of 350 to keep the test small; `prueba="3"` exercises both masks and the energy loss."""
+    wave, patch, terms, B = 896, 256, 12, 3
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(B, 3, patch, patch, generator=g)
+    img[1, 2, 100, 140] += 3.0
+    w = torch.rand(B, 3, patch, patch, generator=g)
+    coeffs = torch.zeros(terms, 1, 1)
+    coeffs[3], coeffs[4], coeffs[7] = -22.0, 0.5, -0.3
+    cam = make(wave, patch, terms, coeffs)
+    x = img.cuda().requires_grad_(True)
+    sensor, psf, _, loss = cam(x, prueba="3")
+    ((sensor * w.cuda()).sum() + loss).backward()
+
+    cfg = lo.LensConfig(wave_res=wave, patch=patch, sample_interval=3e-6)
+    vol = torch.tensor(zern.zernike_volume(wave, terms, 1e-6).astype(np.float32))
+    cz = coeffs.clone().requires_grad_(True)
+    xo = img.clone().requires_grad_(True)
+    out = lo.lens_forward(xo, cz, vol, cfg, prueba="3", mask_1=cam.mask_1.cpu(), mask_2=cam.mask_2.cpu())
+    ((out["sensor"] * w).sum() + out["loss"]).backward()
+    assert rel_l2(sensor, out["sensor"]) <= 1e-4
+    assert rel_l2(psf, out["psf"]) <= 1e-4
+    assert abs(float(loss) - float(out["loss"])) <= 1e-4 * abs(float(out["loss"]))
+    assert abs(float(cam.zernike_coeffs_train.grad) - float(cz.grad[3])) <= 1e-3 * abs(float(cz.grad[3]))
+    assert rel_l2(x.grad, xo.grad) <= 1e-3
+
+
+def test_state_dict_and_signature_match_reference():
+    cam = make(128, 64, 10, torch.zeros(10, 1, 1))
+    sd = cam.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {
+        "zernike_coeffs_no_train": (3, 1, 1), "zernike_coeffs_no_train2": (6, 1, 1), "zernike_coeffs_train": (1, 1)}
+    assert float(sd["zernike_coeffs_train"]) == 0.0
+    fresh = OpticsZernike(input_shape=[1, 64, 64, 3], device=torch.device("cuda", 0), wave_resolution=(128, 128),
+                          patch_size=64, zernike_terms=10)
+    assert float(fresh.zernike_coeffs_train) == -22.0 and fresh.height_tolerance == 20e-9
+    assert [p for p, v in fresh.named_parameters() if v.requires_grad] == ["zernike_coeffs_train"]
+    with pytest.raises(NotImplementedError):
+        fresh(torch.rand(1, 3, 64, 64).cuda(), psf_lab=True)
