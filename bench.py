@@ -349,7 +349,7 @@ def run_b200(args) -> None:
     ys = [F.sensor_conv(imgs[r], p_req, plan) for r in range(R)]
     time_call("sensor_bwd", lambda i: torch.autograd.grad(ys[i % R], p_req, ws[i % R], retain_graph=True))
     hr = h.detach().clone().requires_grad_(True)
-    pp, ll = F.psf_synth(hr, plan)
+    pp, _l1, _l2 = F.psf_synth(hr, plan)
     gp = torch.rand_like(pp)
     time_call("psf_bwd", lambda i: torch.autograd.grad(pp, hr, gp, retain_graph=True))
 

@@ -93,12 +93,17 @@ int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float*
  * sensor path (same reference lines as b200cam_sensor_fwd; sensor_fwd == sensor_rows + sensor_finish on one stream):
  *   b200cam_sensor_rows    row transforms of the images (first half of rfftn, Utils.py:8) into `spectrum`; resets
  *                          img_max / tie_count.  Needs no PSF: may run on another stream beside b200cam_psf_fwd.
- *   b200cam_sensor_finish  OTF of the PSF, spectral product, inverse transform, per-image max, normalise.
+ *   b200cam_psf_otf        OTF of the PSF in the library's layout: rfft2(roll(psf, -N/2)) / N^2 (Optics.py:126 +
+ *                          second operand of Utils.py:9-10).  Batch independent: may follow b200cam_psf_fwd on its stream.
+ *   b200cam_sensor_finish  [OTF of the PSF unless otf_ready != 0], spectral product, inverse transform, per-image
+ *                          max, normalise.
  * b200cam_sensor_split_supported(N, B) tells whether the split entry points apply (not with B200CAM_FUSED=1 at N=256). */
 int b200cam_sensor_split_supported(int N, int B);
 int b200cam_sensor_rows(const float* img, float* spectrum, float* img_max, int* tie_count, int B, int N, void* stream);
+int b200cam_psf_otf(const float* psf, float* otf, int N, void* stream);
 int b200cam_sensor_finish(const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos, float* otf,
-                          const float* spectrum, void* workspace, size_t workspace_bytes, int B, int N, void* stream);
+                          const float* spectrum, int otf_ready, void* workspace, size_t workspace_bytes, int B, int N,
+                          void* stream);
 
 /* Sensor image, backward (autograd through Optics.py:126-128 in closed form, incl. the amax term).
  *   grad_sensor [B][3][N][N]   dL/dsensor

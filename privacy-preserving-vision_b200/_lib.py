@@ -43,7 +43,8 @@ _SIGNATURES = {
                                           _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "b200cam_sensor_split_supported": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "b200cam_sensor_rows": (ctypes.c_int, [_f, _f, _f, _f, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
-    "b200cam_sensor_finish": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f,
+    "b200cam_psf_otf": (ctypes.c_int, [_f, _f, ctypes.c_int, ctypes.c_void_p]),
+    "b200cam_sensor_finish": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, ctypes.c_int,
                                              _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "b200cam_conv_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p]),

@@ -634,12 +634,14 @@ static int sensor_rows_impl(const float* img, float2* srow, float* img_max, int*
 // second half: OTF of the PSF, column convolution, inverse rows + per-image max, normalise
 template <int N>
 static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos, float2* otf,
-                              const float2* srow, const SensorWs& ws, int B, cudaStream_t s) {
+                              const float2* srow, const SensorWs& ws, int B, int otf_ready, cudaStream_t s) {
     using T = Tile<N>;
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
-    int rc = otf_impl<N>(psf, otf, tw, 1.0f / (static_cast<float>(N) * N), s);
-    if (rc) return rc;
+    if (!otf_ready) {
+        int rc = otf_impl<N>(psf, otf, tw, 1.0f / (static_cast<float>(N) * N), s);
+        if (rc) return rc;
+    }
     const int planes = 3 * B;
     const dim3 rgrid(N / T::ROWS, planes);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
@@ -741,7 +743,7 @@ static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, fl
     float2* srow = spectrum != nullptr ? spectrum : ws.stx;      // row spectra: kept for the backward when asked
     int rc = sensor_rows_impl<N>(img, srow, img_max, tie_count, B, s);
     if (rc) return rc;
-    return sensor_finish_impl<N>(psf, sensor, img_max, tie_count, tie_pos, otf, srow, ws, B, s);
+    return sensor_finish_impl<N>(psf, sensor, img_max, tie_count, tie_pos, otf, srow, ws, B, 0, s);
 }
 
 // N = 256 backward: persistent accumulate kernel, partial reduction + inverse transform, arg-max term
@@ -1009,8 +1011,19 @@ int b200cam_sensor_rows(const float* img, float* spectrum, float* img_max, int* 
     DISPATCH_N(N, (sensor_rows_impl<NN_>(img, reinterpret_cast<float2*>(spectrum), img_max, tie_count, B, s)));
 }
 
+int b200cam_psf_otf(const float* psf, float* otf, int N, void* stream) {
+    if (!b200cam_supported(N)) return B200CAM_E_BAD_SIZE;
+    if (!psf || !otf) return B200CAM_E_NULL;
+    if (!aligned16(psf) || !aligned16(otf)) return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    DISPATCH_N(N, (otf_impl<NN_>(psf, reinterpret_cast<float2*>(otf), tw, 1.0f / (static_cast<float>(NN_) * NN_), s)));
+}
+
 int b200cam_sensor_finish(const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos, float* otf,
-                          const float* spectrum, void* workspace, size_t workspace_bytes, int B, int N, void* stream) {
+                          const float* spectrum, int otf_ready, void* workspace, size_t workspace_bytes, int B, int N,
+                          void* stream) {
     if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
     if (!psf || !sensor || !img_max || !tie_count || !tie_pos || !otf || !spectrum || !workspace) return B200CAM_E_NULL;
     if (workspace_bytes < b200cam_sensor_workspace_bytes(N, B, 0)) return B200CAM_E_WORKSPACE;
@@ -1020,7 +1033,7 @@ int b200cam_sensor_finish(const float* psf, float* sensor, float* img_max, int* 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DISPATCH_N(N, (sensor_finish_impl<NN_>(psf, sensor, img_max, tie_count, tie_pos, reinterpret_cast<float2*>(otf),
                                            reinterpret_cast<const float2*>(spectrum), SensorWs(workspace, NN_, B, false),
-                                           B, s)));
+                                           B, otf_ready, s)));
 }
 
 int b200cam_conv_fwd(const float* img, const float* kernel, float* out, float* otf, float* spectrum, void* workspace,

@@ -2,7 +2,7 @@
 
 Two differentiable ops, both thin ctypes calls into ``libb200cam.so`` on the current CUDA stream:
 
-* ``psf_synth(h, plan)        -> psf (1,3,N,N), losses (2,) = (loss_rad, centering_loss)``
+* ``psf_synth(h, plan)        -> psf (1,3,N,N), loss_rad (), centering_loss ()``
   (``Face-DeId/Camera/Optics.py:89-120,124-125``)
 * ``sensor_conv(img, psf, plan) -> sensor (B,3,N,N)``
   (``Optics.py:126-128`` + ``Face-DeId/Camera/Utils.py:7-12``)
@@ -45,6 +45,7 @@ class DevicePlan:
         self.otf_floats = self.lib.b200cam_otf_bytes(N) // 4
         self.process_group = None      # set by Camera.data_parallel(): all-reduce dL/dh over ranks
         self.average_grads = True
+        self.otf_cache = None          # (psf tensor, its OTF) left by the last asynchronous psf_synth
         self._side_stream = None       # runs the PSF-independent half of the sensor forward beside the PSF chain
 
     def side_stream(self) -> torch.cuda.Stream:
@@ -89,7 +90,6 @@ class PsfSynth(torch.autograd.Function):
         field = torch.empty(3, N, N, 2, dtype=torch.float32, device=plan.device)
         stats = torch.empty(4, dtype=torch.float32, device=plan.device)
         ws = plan.psf_workspace()
-        losses = torch.empty(2, dtype=torch.float32, device=plan.device)
         if stream is not None:
             stream.wait_stream(torch.cuda.current_stream(plan.device))
         launch = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream()
@@ -97,23 +97,28 @@ class PsfSynth(torch.autograd.Function):
             _lib.check(plan.lib.b200cam_psf_fwd(
                 _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho), plan.kappa,
                 _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), N, launch))
+            if stream is not None:
+                # the OTF only depends on the PSF: compute it here, beside the image row pass, and hand it to sensor_conv
+                otf = torch.empty(plan.otf_floats, dtype=torch.float32, device=plan.device)
+                _lib.check(plan.lib.b200cam_psf_otf(_lib.ptr(psf), _lib.ptr(otf), N, launch))
+                plan.otf_cache = (psf.data_ptr(), otf)
         ctx.plan = plan
         ctx.h_shape = h.shape
         ctx.save_for_backward(hc, psf, field, stats)
-        if stream is not None:
-            with torch.cuda.stream(stream):
-                losses.copy_(stats[1:3])
-        else:
-            losses.copy_(stats[1:3])
-        return psf, losses                      # losses = (loss_rad, centering_loss)
+        # the two regularisers are returned as separate 0-dim outputs (views of `stats`): their upstream gradients then
+        # arrive as two scalars instead of going through select-backward (zeros + index_put + add per loss)
+        return psf, stats[1], stats[2]
 
     @staticmethod
-    def backward(ctx, g_psf, g_losses):
+    def backward(ctx, g_psf, g_rad, g_cen):
         plan: DevicePlan = ctx.plan
         N = plan.N
         hc, psf, field, stats = ctx.saved_tensors
         gp = _as_f32(g_psf, plan.device).reshape(3, N, N) if g_psf is not None else None
-        gs = _as_f32(g_losses, plan.device) if g_losses is not None else None
+        gs = None
+        if g_rad is not None or g_cen is not None:
+            zero = torch.zeros((), dtype=torch.float32, device=plan.device)
+            gs = torch.stack((g_rad if g_rad is not None else zero, g_cen if g_cen is not None else zero)).float()
         grad_h = torch.empty(N, N, dtype=torch.float32, device=plan.device)
         ws = plan.psf_workspace()
         with torch.cuda.device(plan.index):
@@ -178,10 +183,15 @@ class SensorConv(torch.autograd.Function):
             spectrum = torch.empty(plan.lib.b200cam_spectrum_bytes(N, B) // 4, dtype=torch.float32, device=plan.device)
         if rows is not None:
             ws = plan.sensor_workspace(B)
+            cached = plan.otf_cache
+            otf_ready = int(cached is not None and cached[0] == p.data_ptr())
+            if otf_ready:
+                otf = cached[1]
+            plan.otf_cache = None
             with torch.cuda.device(plan.index):
                 _lib.check(plan.lib.b200cam_sensor_finish(
                     _lib.ptr(p), _lib.ptr(sensor), _lib.ptr(img_max), _lib.ptr(tie_count), _lib.ptr(tie_pos),
-                    _lib.ptr(otf), _lib.ptr(spectrum), _lib.ptr(ws), ws.numel(), B, N, _stream()))
+                    _lib.ptr(otf), _lib.ptr(spectrum), otf_ready, _lib.ptr(ws), ws.numel(), B, N, _stream()))
             if not any(ctx.needs_input_grad[:2]):
                 spectrum = None
         elif B > 0:

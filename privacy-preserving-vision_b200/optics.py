@@ -110,10 +110,10 @@ class Camera(nn.Module):
     def get_psf(self, _stream=None):
         h = self.get_Heith_Map()
         plan = self._plan(h.device)
-        psf, losses = F.psf_synth(h, plan, _stream)
+        psf, loss_rad, centering = F.psf_synth(h, plan, _stream)
         self.psfs = psf
-        self.loss_rad = losses[0]
-        self._pending_centering = losses[1]
+        self.loss_rad = loss_rad
+        self._pending_centering = centering
         return self.psfs
 
     def forward(self, img):
