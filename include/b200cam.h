@@ -73,6 +73,20 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const floa
                     const float* psf, const float* field, float* stats, float* grad_h,
                     void* workspace, size_t workspace_bytes, int N, void* stream);
 
+/* Data parallel (one process per GPU, batch sharded): b200cam_psf_bwd whose last kernel also all-reduces
+ * dL/dh over NVLink peer memory - every rank pushes its rows into all peers' buffers, per-tile flags, rank-ordered sum,
+ * result * scale (1/world for the mean) in grad_h on every rank, bit-identical.  Replaces the framework-level gradient
+ * all-reduce a DDP wrapper would issue for the reference's Camera parameters.
+ *   peer_bufs  HOST array [world] of device pointers: rank r's symmetric buffer of b200cam_comm_bytes(N, world) bytes as
+ *              mapped in THIS process (e.g. torch.distributed._symmetric_memory buffer_ptrs); zero-filled once before
+ *              the first call, then owned by the library (flags / epochs / double-buffered slots live in it).
+ * All ranks must call it the same number of times (it is a collective). */
+size_t b200cam_comm_bytes(int N, int world);
+int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_scalars, const float* h, const float* A,
+                              const float* Ht, const float* rho, const float* kappa, const float* psf, const float* field,
+                              float* stats, float* grad_h, void* workspace, size_t workspace_bytes, int N, void* stream,
+                              void* const* peer_bufs, int rank, int world, float scale);
+
 /* Sensor image, forward.  Replaces Optics.py:126-128 + conv2D (Face-DeId/Camera/Utils.py:7-12):
  *   sensor_b = circconv(img_b, roll(psf, -N/2)) / max over (c,y,x).
  *   img      [B][3][N][N]

@@ -95,6 +95,71 @@ __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad(CRows
     DeviceExec ex;
     crows_inv_hgrad_body<N>(ex, p, pupil, gh, SMEM2);
 }
+// ------------------------------------------------------------------------------------------
+// dL/dh tile + all-reduce over NVLink peer memory in ONE kernel (data parallel: SURVEY 8e).
+// Every rank owns a symmetric buffer  [flags 4 KB][epochs 4 KB][2 parities][world][N*N floats].
+// CTA t computes its CROWS rows of the local dL/dh (same body as k_crows_inv_hgrad), PUSHES them into slot[rank] of
+// every peer's buffer (plain P2P stores), bumps flag t on every peer (system-scope atomic), waits until its own
+// flag t shows `world` arrivals for this epoch, and sums the `world` slots in rank order - so all ranks hold the
+// bit-identical sum.  No grid-wide barrier: tile t only ever waits for tile t of the peers.  Flags and epochs are
+// monotone counters kept in the buffer itself (CUDA-graph replays reuse the frozen kernel arguments); data slots
+// are double buffered by epoch parity (a peer can be at most one step ahead).
+// ------------------------------------------------------------------------------------------
+constexpr int COMM_MAX_WORLD = 16;
+constexpr size_t COMM_FLAG_BYTES = 4096, COMM_HEADER_BYTES = 8192;
+struct CommDev {
+    unsigned char* buf[COMM_MAX_WORLD];     // every rank's buffer, as mapped in this process
+    int rank, world;
+    float scale;
+};
+
+template <int N>
+__global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad_allreduce(CRowsInvParams p, PupilLoad pupil,
+                                                                                     float* gh, CommDev c) {
+    DeviceExec ex;
+    crows_inv_hgrad_body<N>(ex, p, pupil, gh, SMEM2);            // local dL/dh rows of this tile -> gh
+    __shared__ unsigned s_epoch;
+    constexpr int COUNT4 = Tile<N>::CROWS * N / 4;
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const size_t NN = static_cast<size_t>(N) * N, base = static_cast<size_t>(tile) * Tile<N>::CROWS * N;
+    if (tid == 0) {
+        unsigned* ep = reinterpret_cast<unsigned*>(c.buf[c.rank] + COMM_FLAG_BYTES) + tile;
+        s_epoch = *ep + 1;
+        *ep = s_epoch;
+    }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const size_t parity_off = static_cast<size_t>(epoch & 1) * c.world * NN;
+    const float4* mine = reinterpret_cast<const float4*>(gh + base);
+    for (int i = tid; i < COUNT4; i += blockDim.x) {
+        const float4 v = mine[i];
+        for (int r = 0; r < c.world; ++r) {
+            float* slot = reinterpret_cast<float*>(c.buf[r] + COMM_HEADER_BYTES) + parity_off + c.rank * NN + base;
+            reinterpret_cast<float4*>(slot)[i] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        for (int r = 0; r < c.world; ++r) atomicAdd_system(reinterpret_cast<unsigned*>(c.buf[r]) + tile, 1u);
+        const volatile unsigned* flag = reinterpret_cast<const volatile unsigned*>(c.buf[c.rank]) + tile;
+        const unsigned target = epoch * static_cast<unsigned>(c.world);
+        const long long t0 = clock64();                       // never hang the device if a peer died (~2 s)
+        while (*flag < target && clock64() - t0 < 4000000000LL) {}
+        __threadfence_system();
+    }
+    __syncthreads();
+    const float* slots = reinterpret_cast<const float*>(c.buf[c.rank] + COMM_HEADER_BYTES) + parity_off + base;
+    for (int i = tid; i < COUNT4; i += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < c.world; ++r) {                    // rank order: identical on every rank
+            const float4 v = __ldcv(reinterpret_cast<const float4*>(slots + r * NN) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(gh + base)[i] = make_float4(acc.x * c.scale, acc.y * c.scale, acc.z * c.scale, acc.w * c.scale);
+    }
+}
+
 __global__ void __launch_bounds__(EW_THREADS) k_psf_finalise(PsfFinaliseParams p) {
     __shared__ float red[3 * EW_THREADS + 2];
     DeviceExec ex;
@@ -393,6 +458,7 @@ static cudaError_t init_kernels() {
     if ((e = optin(k_crows_fwd<N, GradFieldLoad>, CRowsSmem<N>::BYTES))) return e;
     if ((e = optin(k_crows_inv<N, IntensityEpilogue>, CRowsSmem<N>::BYTES))) return e;
     if ((e = optin(k_crows_inv_hgrad<N>, HGradSmem<N>::BYTES))) return e;
+    if ((e = optin(k_crows_inv_hgrad_allreduce<N>, HGradSmem<N>::BYTES))) return e;
     if ((e = optin(k_ccols_mix<N>, CColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_psf_fwd_coop<N>, coop_smem_bytes<N>()))) return e;
     if ((e = optin(k_psf_bwd_coop<N>, coop_smem_bytes<N>()))) return e;
@@ -546,7 +612,7 @@ static int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const
 template <int N>
 static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, const float2* A, const float2* Ht,
                         const float* rho, const float* kappa, const float* psf, const float2* field, float* stats,
-                        float* grad_h, void* ws_ptr, cudaStream_t s) {
+                        float* grad_h, void* ws_ptr, cudaStream_t s, const CommDev* comm = nullptr) {
     using T = Tile<N>;
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
@@ -555,7 +621,7 @@ static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, c
     CRowsFwdParams rf{ws.st, tw};
     CColsMixParams mix{ws.st, Ht, tw, 1, 1.0f / (3.0f * N * N)};
     CRowsInvParams ri{ws.st, tw};
-    if (const int G = coop_grid(N, s)) {
+    if (const int G = (comm != nullptr ? 0 : coop_grid(N, s))) {
         PsfBwdArgs args{PsfGradPrepParams{gpsf, gscal, psf, rho, stats, ws.gtot, ws.part_ew, N}, rf,
                         GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, G, N}, mix, ri, pupil, grad_h,
                         coop_barrier(1)};
@@ -572,7 +638,10 @@ static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, c
     LAUNCH_CHECK();
     k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(mix);
     LAUNCH_CHECK();
-    k_crows_inv_hgrad<N><<<N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s>>>(ri, pupil, grad_h);
+    if (comm != nullptr)
+        k_crows_inv_hgrad_allreduce<N><<<N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s>>>(ri, pupil, grad_h, *comm);
+    else
+        k_crows_inv_hgrad<N><<<N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s>>>(ri, pupil, grad_h);
     LAUNCH_CHECK();
     return 0;
 }
@@ -976,6 +1045,33 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const floa
     DISPATCH_N(N, (psf_bwd_impl<NN_>(grad_psf, grad_scalars, h, reinterpret_cast<const float2*>(A),
                                      reinterpret_cast<const float2*>(Ht), rho, kappa, psf,
                                      reinterpret_cast<const float2*>(field), stats, grad_h, workspace, s)));
+}
+
+size_t b200cam_comm_bytes(int N, int world) {
+    if (!b200cam_supported(N) || world < 1 || world > COMM_MAX_WORLD) return 0;
+    return COMM_HEADER_BYTES + static_cast<size_t>(2) * world * N * N * sizeof(float);
+}
+
+int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_scalars, const float* h, const float* A,
+                              const float* Ht, const float* rho, const float* kappa, const float* psf, const float* field,
+                              float* stats, float* grad_h, void* workspace, size_t workspace_bytes, int N, void* stream,
+                              void* const* peer_bufs, int rank, int world, float scale) {
+    if (!b200cam_supported(N) || world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world) return B200CAM_E_BAD_SIZE;
+    if (N / Tile<64>::CROWS > static_cast<int>(COMM_FLAG_BYTES / sizeof(unsigned))) return B200CAM_E_BAD_SIZE;
+    if (!h || !A || !Ht || !rho || !kappa || !psf || !field || !stats || !grad_h || !workspace || !peer_bufs) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_psf_workspace_bytes(N)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(A) || !aligned16(Ht) || !aligned16(field) || !aligned16(workspace) || !aligned16(grad_h)) return B200CAM_E_ALIGN;
+    CommDev comm;
+    for (int r = 0; r < world; ++r) {
+        if (!peer_bufs[r] || !aligned16(peer_bufs[r])) return B200CAM_E_NULL;
+        comm.buf[r] = static_cast<unsigned char*>(peer_bufs[r]);
+    }
+    for (int r = world; r < COMM_MAX_WORLD; ++r) comm.buf[r] = nullptr;
+    comm.rank = rank; comm.world = world; comm.scale = scale;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (psf_bwd_impl<NN_>(grad_psf, grad_scalars, h, reinterpret_cast<const float2*>(A),
+                                     reinterpret_cast<const float2*>(Ht), rho, kappa, psf,
+                                     reinterpret_cast<const float2*>(field), stats, grad_h, workspace, s, &comm)));
 }
 
 size_t b200cam_spectrum_bytes(int N, int B) {

@@ -45,6 +45,7 @@ class DevicePlan:
         self.otf_floats = self.lib.b200cam_otf_bytes(N) // 4
         self.process_group = None      # set by Camera.data_parallel(): all-reduce dL/dh over ranks
         self.average_grads = True
+        self.peer_comm = None          # parallel.PeerComm: fused NVLink all-reduce instead of the NCCL call
         self.otf_cache = None          # (psf tensor, its OTF) left by the last asynchronous psf_synth
         self._side_stream = None       # runs the PSF-independent half of the sensor forward beside the PSF chain
 
@@ -121,6 +122,16 @@ class PsfSynth(torch.autograd.Function):
             gs = torch.stack((g_rad if g_rad is not None else zero, g_cen if g_cen is not None else zero)).float()
         grad_h = torch.empty(N, N, dtype=torch.float32, device=plan.device)
         ws = plan.psf_workspace()
+        comm = plan.peer_comm
+        if comm is not None:
+            # all-reduce fused into the last kernel: peer-memory pushes over NVLink, no NCCL call
+            with torch.cuda.device(plan.index):
+                _lib.check(plan.lib.b200cam_psf_bwd_allreduce(
+                    _lib.ptr(gp), _lib.ptr(gs), _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho),
+                    plan.kappa, _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(grad_h),
+                    _lib.ptr(ws), ws.numel(), N, _stream(), comm.ptr_array, comm.rank, comm.world,
+                    1.0 / comm.world if plan.average_grads else 1.0))
+            return grad_h.reshape(ctx.h_shape), None, None
         with torch.cuda.device(plan.index):
             _lib.check(plan.lib.b200cam_psf_bwd(
                 _lib.ptr(gp), _lib.ptr(gs), _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho),

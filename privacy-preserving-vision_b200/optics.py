@@ -77,17 +77,37 @@ class Camera(nn.Module):
             plan = F.DevicePlan(self.N, device, self._tables)
             plan.process_group = self._process_group
             plan.average_grads = self._average_grads
+            comm = getattr(self, "_peer_comm", None)
+            plan.peer_comm = comm if comm is not None and comm.buf.device == device else None
             self._plans[device] = plan
         return plan
 
-    def data_parallel(self, process_group=None, average: bool = True, enabled: bool = True):
-        """All-reduce dL/dh (N*N floats) over ``process_group`` inside backward (one rank per GPU)."""
+    def data_parallel(self, process_group=None, average: bool = True, enabled: bool = True, peer_memory: bool = True,
+                      device=None):
+        """All-reduce dL/dh (N*N floats) over ``process_group`` inside backward (one rank per GPU).
+
+        With ``peer_memory`` (default, NCCL groups on CUDA) the all-reduce is fused into the last PSF-backward kernel
+        over NVLink peer memory (``parallel.PeerComm``; a collective set-up happens here, so call it on every rank);
+        otherwise, or if symmetric memory is unavailable, ``dist.all_reduce`` is used."""
         import torch.distributed as dist
+        from .parallel import PeerComm
         self._process_group = (process_group or dist.group.WORLD) if enabled else None
         self._average_grads = average
+        self._peer_comm = None
+        if (enabled and peer_memory and torch.cuda.is_available() and dist.get_backend(self._process_group) == "nccl"
+                and dist.get_world_size(self._process_group) > 1):
+            dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+            try:
+                F._lib.ensure_init(self.N, dev.index if dev.index is not None else torch.cuda.current_device())
+                self._peer_comm = PeerComm(self.N, dev, self._process_group)
+            except Exception as exc:      # no symmetric memory on this system: NCCL path
+                import warnings
+                warnings.warn(f"b200cam: peer-memory all-reduce unavailable ({exc}); using dist.all_reduce")
+                self._peer_comm = None
         for plan in self._plans.values():
             plan.process_group = self._process_group
             plan.average_grads = average
+            plan.peer_comm = self._peer_comm if plan.device == getattr(self._peer_comm, "buf", torch.empty(0)).device else None
         return self
 
     # ------------------------------------------------------------------ reference API

@@ -14,7 +14,7 @@ import os
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard", "allreduce_height_grad", "init_from_env"]
+__all__ = ["shard_range", "shard", "allreduce_height_grad", "init_from_env", "PeerComm"]
 
 
 def shard_range(batch: int, rank: int, world: int) -> tuple[int, int]:
@@ -58,3 +58,32 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
         else:
             dist.init_process_group(backend)
     return rank, world, local
+
+
+class PeerComm:
+    """NVLink peer-memory buffers for the fused dL/dh all-reduce (``b200cam_psf_bwd_allreduce``).
+
+    One symmetric allocation per rank (``torch.distributed._symmetric_memory``: CUDA VMM handles exchanged over the
+    process group's store, every rank's buffer mapped into every process); the library's last PSF-backward kernel pushes
+    its rows of dL/dh straight into the peers' buffers and sums them - no NCCL call on the data path.
+    Construction is a collective.  Raises if symmetric memory is not available (callers fall back to NCCL)."""
+
+    def __init__(self, N: int, device: torch.device, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        group = group or dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        lib = _lib.load_library()
+        nbytes = lib.b200cam_comm_bytes(N, self.world)
+        if nbytes == 0:
+            raise RuntimeError(f"b200cam: no peer all-reduce for N={N}, world={self.world}")
+        self.buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                    # every rank's flags are zero before anyone pushes
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.ptr_array = (ctypes.c_void_p * self.world)(*ptrs)
+        self.N = N
