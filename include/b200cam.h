@@ -66,9 +66,10 @@ int b200cam_psf_fwd(const float* h, const float* A, const float* Ht, const float
 
 /* PSF synthesis, backward (autograd through Optics.py:89-125 in closed form).
  *   grad_psf     [3][N][N] or NULL   dL/dpsf
- *   grad_scalars [2] or NULL         dL/dloss_rad, dL/dcentering_loss
+ *   grad_rad     [1] or NULL         dL/dloss_rad        (device scalars: the two regularisers are separate autograd
+ *   grad_cen     [1] or NULL         dL/dcentering_loss   outputs, so their gradients arrive as two 0-dim tensors)
  *   grad_h       [N][N]              out: dL/dh */
-int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const float* h,
+int b200cam_psf_bwd(const float* grad_psf, const float* grad_rad, const float* grad_cen, const float* h,
                     const float* A, const float* Ht, const float* rho, const float* kappa,
                     const float* psf, const float* field, float* stats, float* grad_h,
                     void* workspace, size_t workspace_bytes, int N, void* stream);
@@ -82,7 +83,7 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const floa
  *              the first call, then owned by the library (flags / epochs / double-buffered slots live in it).
  * All ranks must call it the same number of times (it is a collective). */
 size_t b200cam_comm_bytes(int N, int world);
-int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_scalars, const float* h, const float* A,
+int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_rad, const float* grad_cen, const float* h, const float* A,
                               const float* Ht, const float* rho, const float* kappa, const float* psf, const float* field,
                               float* stats, float* grad_h, void* workspace, size_t workspace_bytes, int N, void* stream,
                               void* const* peer_bufs, int rank, int world, float scale);

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_r2c(RowsR2CPar
     rows_r2c_body<N>(ex, p, SMEM2);
 }
 template <int N>
-__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_conv(ColsConvParams p) {
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 4 : 1) k_cols_conv(ColsConvParams p) {
     DeviceExec ex;
     ConvState<N> st;
     cols_conv_body<N>(ex, p, SMEM2, &st);
@@ -54,10 +54,6 @@ template <int N>
 __global__ void __launch_bounds__(ReduceInvSmem<N>::THREADS) k_cols_reduce_inv(ColsReduceInvParams p) {
     DeviceExec ex;
     cols_reduce_inv_body<N>(ex, p, SMEM2);
-}
-__global__ void __launch_bounds__(EW_THREADS) k_tie_coef(TieTermParams p) {
-    DeviceExec ex;
-    tie_coef_body(ex, p, gridDim.x);
 }
 __global__ void __launch_bounds__(EW_THREADS) k_tie_term(TieTermParams p) {
     __shared__ float s_coef[TIE_PASS * MAX_TIES];
@@ -391,7 +387,10 @@ constexpr int MAX_DEV = 64;
 constexpr int EW_GRID = 296;   // 2 x 148 SMs for the element-wise / reduction kernels
 
 inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
-struct DeviceState { float2* tw[11] = {nullptr}; int sms = 0; int coop_grid[11] = {0}; unsigned* bar = nullptr; };
+struct DeviceState {
+    float2* tw[11] = {nullptr}; int sms = 0; int coop_grid[11] = {0}; unsigned* bar = nullptr;
+    int conv_slots[11] = {0}, accum_slots[11] = {0};     // resident CTAs of the persistent column kernels
+};
 static DeviceState g_state[MAX_DEV];
 static std::mutex g_mutex;
 
@@ -450,7 +449,7 @@ static cudaError_t init_kernels() {
     cudaError_t e;
     if ((e = optin(k_rows_r2c<N>, RowsR2CSmem<N>::BYTES))) return e;
     if ((e = optin(k_rows_c2r<N>, RowsR2CSmem<N>::BYTES))) return e;
-    if ((e = optin(k_cols_conv<N>, ColsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_cols_conv<N>, ColsSmem<N>::BYTES_CONV))) return e;
     if ((e = optin(k_cols_fwd<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_accum<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_reduce_inv<N>, ReduceInvSmem<N>::BYTES))) return e;
@@ -481,6 +480,18 @@ static cudaError_t coop_grid_size(int dev, int sms, int* out) {
     return cudaSuccess;
 }
 
+// resident CTAs (one wave) of the persistent column kernels on this device
+template <int N>
+static cudaError_t column_slots(int sms, int* conv, int* accum) {
+    int nc = 0, na = 0;
+    cudaError_t e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nc, k_cols_conv<N>, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV))) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, k_cols_accum<N>, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES))) return e;
+    *conv = sms * nc;
+    *accum = sms * na;
+    return cudaSuccess;
+}
+
 // ------------------------------------------------------------------------------------------
 // workspace carving (256-byte aligned slices of the caller's buffer)
 // ------------------------------------------------------------------------------------------
@@ -496,19 +507,27 @@ struct Carver {
     }
 };
 
-static int accum_chunks(int N, int B) {
-    const int colgroups = (3 * (N / 2 + 1) + 7) / 8;
-    int n = 592 / colgroups;
-    if (n < 1) n = 1;
+// The column kernels are persistent over images: CTA (colgroup, chunk) walks its chunk of the batch.  The number of
+// chunks is chosen so that the whole grid is ONE wave of resident CTAs (slots = SMs x occupancy, measured at init):
+// a second, partly filled wave costs as much as a full one.
+constexpr int MAX_CHUNKS = 16;          // sizes the partial-sum workspace of the backward
+static int col_chunks(int N, int B, int slots) {
+    const int colgroups = (3 * (N / 2 + 1) + Tile<64>::COLS - 1) / Tile<64>::COLS;
+    int n = slots / colgroups;
+    if (n > MAX_CHUNKS) n = MAX_CHUNKS;
     if (n > B) n = B;
+    if (n < 1) n = 1;
     return n;
 }
-
-static int conv_chunk(int N, int B) {      // images per CTA of the persistent column-convolution kernel
-    const int colgroups = (3 * (N / 2 + 1) + 7) / 8;
-    int nchunks = (148 * 5 + colgroups - 1) / colgroups;      // ~5 CTAs per SM
-    if (nchunks > B) nchunks = B;
-    return (B + nchunks - 1) / nchunks;
+static int conv_chunks(int N, int B) {
+    int dev = 0;
+    const int slots = (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MAX_DEV) ? g_state[dev].conv_slots[log2i(N)] : 0;
+    return col_chunks(N, B, slots > 0 ? slots : 592);
+}
+static int accum_chunks(int N, int B) {
+    int dev = 0;
+    const int slots = (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MAX_DEV) ? g_state[dev].accum_slots[log2i(N)] : 0;
+    return col_chunks(N, B, slots > 0 ? slots : 592);
 }
 
 struct PsfWs {
@@ -531,7 +550,7 @@ struct PsfWs {
 constexpr int FUSED_MAX_GRID = 160;   // upper bound on the CTAs of the fused backward kernel (one accumulator plane each)
 
 struct SensorWs {
-    float2* stx; float2* stg; float2* partial; float2* stp; float* dot_partial; float* coef;
+    float2* stx; float2* stg; float2* partial; float2* stp; float* dot_lanes; float* coef;
     float* plane_max; float* sdot; float2* acc; float2* st2; int* arrive;
     size_t bytes;
     SensorWs(void* p, int N, int B, bool backward) {
@@ -549,12 +568,12 @@ struct SensorWs {
         arrive = c.take<int>(B);
         if (backward) {
             stg = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
-            partial = c.take<float2>(static_cast<size_t>(accum_chunks(N, B)) * 3 * plane);
+            partial = c.take<float2>(static_cast<size_t>(B < MAX_CHUNKS ? B : MAX_CHUNKS) * 3 * plane);
             stp = c.take<float2>(3 * plane);
-            dot_partial = c.take<float>(static_cast<size_t>(B) * 3 * N);
+            dot_lanes = c.take<float>(static_cast<size_t>(B) * 3 * (N / 2 + 1) * 32);   // [B][3*NC][R1 <= 32]
             coef = c.take<float>(B);
         } else {
-            stg = nullptr; partial = nullptr; stp = nullptr; dot_partial = nullptr; coef = nullptr;
+            stg = nullptr; partial = nullptr; stp = nullptr; dot_lanes = nullptr; coef = nullptr;
         }
         bytes = c.off;
     }
@@ -610,7 +629,7 @@ static int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const
 }
 
 template <int N>
-static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, const float2* A, const float2* Ht,
+static int psf_bwd_impl(const float* gpsf, const float* g_rad, const float* g_cen, const float* h, const float2* A, const float2* Ht,
                         const float* rho, const float* kappa, const float* psf, const float2* field, float* stats,
                         float* grad_h, void* ws_ptr, cudaStream_t s, const CommDev* comm = nullptr) {
     using T = Tile<N>;
@@ -622,7 +641,7 @@ static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, c
     CColsMixParams mix{ws.st, Ht, tw, 1, 1.0f / (3.0f * N * N)};
     CRowsInvParams ri{ws.st, tw};
     if (const int G = (comm != nullptr ? 0 : coop_grid(N, s))) {
-        PsfBwdArgs args{PsfGradPrepParams{gpsf, gscal, psf, rho, stats, ws.gtot, ws.part_ew, N}, rf,
+        PsfBwdArgs args{PsfGradPrepParams{gpsf, g_rad, g_cen, psf, rho, stats, ws.gtot, ws.part_ew, N}, rf,
                         GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, G, N}, mix, ri, pupil, grad_h,
                         coop_barrier(1)};
         void* kargs[] = {&args};
@@ -631,7 +650,7 @@ static int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, c
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
-    k_psf_grad_prepare<<<EW_GRID, EW_THREADS, 0, s>>>(PsfGradPrepParams{gpsf, gscal, psf, rho, stats, ws.gtot, ws.part_ew, N});
+    k_psf_grad_prepare<<<EW_GRID, EW_THREADS, 0, s>>>(PsfGradPrepParams{gpsf, g_rad, g_cen, psf, rho, stats, ws.gtot, ws.part_ew, N});
     LAUNCH_CHECK();
     k_crows_fwd<N, GradFieldLoad><<<dim3(N / T::CROWS, 3), CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(
         rf, GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, EW_GRID, N});
@@ -650,7 +669,7 @@ template <int N>
 static int otf_impl(const float* psf, float2* otf, const float2* tw, float scale, cudaStream_t s) {
     using T = Tile<N>;
     k_rows_r2c<N><<<dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsR2CParams{psf, otf, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
+        RowsR2CParams{psf, otf, tw, nullptr, nullptr});
     LAUNCH_CHECK();
     const int total = 3 * T::NC;
     k_cols_fwd<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
@@ -695,7 +714,7 @@ static int sensor_rows_impl(const float* img, float2* srow, float* img_max, int*
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     const dim3 rgrid(N / T::ROWS, 3 * B);
     k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsR2CParams{img, srow, tw, nullptr, nullptr, img_max, tie_count, nullptr, nullptr, nullptr, nullptr});
+        RowsR2CParams{img, srow, tw, img_max, tie_count});
     LAUNCH_CHECK();
     return 0;
 }
@@ -714,9 +733,9 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     const int planes = 3 * B;
     const dim3 rgrid(N / T::ROWS, planes);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
-    const int chunk = conv_chunk(N, B);
-    k_cols_conv<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, chunk, 0, 1.0f});
+    const int nchunks = conv_chunks(N, B);
+    k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f});
     LAUNCH_CHECK();
     k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
         RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0});
@@ -745,9 +764,9 @@ static int conv_fwd_impl(const float* img, const float* kern, float* out, float2
     if (rc) return rc;
     const int planes = 3 * B;
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
-    const int chunk = conv_chunk(N, B);
-    k_cols_conv<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, chunk, 0, 1.0f});
+    const int nchunks = conv_chunks(N, B);
+    k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f});
     LAUNCH_CHECK();
     k_rows_c2r<N><<<dim3(N / T::ROWS, planes), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
         RowsC2RParams{ws.st2, out, tw, nullptr, 1.0f, nullptr, nullptr, 0});
@@ -774,21 +793,21 @@ static int conv_bwd_impl(const float* g, const float* img, const float2* otf, co
     int rc = sensor_rows_impl<N>(g, ws.stg, nullptr, nullptr, B, s);
     if (rc) return rc;
     const int nchunks = accum_chunks(N, B);
-    const int chunk = (B + nchunks - 1) / nchunks;
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
-    k_cols_accum<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsAccumParams{srow, ws.stg, ws.partial, tw, nullptr, nullptr, nullptr, nullptr, B, chunk});
+    k_cols_accum<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        ColsAccumParams{srow, ws.stg, ws.partial, tw, nullptr, nullptr, nullptr, B, nchunks});
     LAUNCH_CHECK();
     k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
-        ColsReduceInvParams{ws.partial, ws.stp, tw, (B + chunk - 1) / chunk, 1.0f / (static_cast<float>(N) * N)});
+        ColsReduceInvParams{ws.partial, ws.stp, tw, nchunks, 1.0f / (static_cast<float>(N) * N),
+                            nullptr, nullptr, nullptr, nullptr, 0});
     LAUNCH_CHECK();
     k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
         RowsC2RParams{ws.stp, grad_kern, tw, nullptr, 1.0f, nullptr, nullptr, 0});
     LAUNCH_CHECK();
     if (grad_img != nullptr) {
-        const int cchunk = conv_chunk(N, B);
-        k_cols_conv<N><<<dim3(colgroups, (B + cchunk - 1) / cchunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-            ColsConvParams{ws.stg, ws.stg, otf, tw, nullptr, B, cchunk, 1, 1.0f});
+        const int cchunks = conv_chunks(N, B);
+        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+            ColsConvParams{ws.stg, ws.stg, otf, tw, nullptr, B, cchunks, 1, 1.0f});
         LAUNCH_CHECK();
         k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
             RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f, nullptr, nullptr, 0});
@@ -845,12 +864,12 @@ static int fused_bwd(const float* g, const float* img, const float* img_max, con
     if (grad_img != nullptr) {   // optional output (no reference caller asks for it): generic kernels
         const dim3 rgrid(N / T::ROWS, planes);
         k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-            RowsR2CParams{g, ws.stg, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
+            RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
         LAUNCH_CHECK();
         const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
-        const int cchunk = conv_chunk(N, B);
-        k_cols_conv<N><<<dim3(colgroups, (B + cchunk - 1) / cchunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunk, 1, 2.0f});
+        const int cchunks = conv_chunks(N, B);
+        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunks, 1, 2.0f});
         LAUNCH_CHECK();
         k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
             RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
@@ -879,30 +898,36 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     const float2* srow = spectrum;
     if (srow == nullptr) {                       // forward did not keep the row spectra: recompute them
         k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-            RowsR2CParams{img, ws.stx, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
+            RowsR2CParams{img, ws.stx, tw, nullptr, nullptr});
         LAUNCH_CHECK();
         srow = ws.stx;
     }
-    CK(cudaMemsetAsync(ws.arrive, 0, sizeof(int) * B, s));
-    k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsR2CParams{g, ws.stg, tw, sensor, ws.dot_partial, nullptr, nullptr, ws.arrive, ws.coef, img_max, tie_count});
+    // upstream gradient rows; sum(g*conv) of the amax term comes out of the accumulate kernel (Parseval), so the
+    // sensor image is not read again
+    (void)sensor;
+    k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
     LAUNCH_CHECK();
     const int nchunks = accum_chunks(N, B);
-    const int chunk = (B + nchunks - 1) / nchunks;
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
-    k_cols_accum<N><<<dim3(colgroups, (B + chunk - 1) / chunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsAccumParams{srow, ws.stg, ws.partial, tw, img_max, ws.coef, tie_count, tie_pos, B, chunk});
+    k_cols_accum<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        ColsAccumParams{srow, ws.stg, ws.partial, tw, img_max, otf, ws.dot_lanes, B, nchunks});
     LAUNCH_CHECK();
     k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
-        ColsReduceInvParams{ws.partial, ws.stp, tw, (B + chunk - 1) / chunk, 1.0f / (static_cast<float>(N) * N)});
+        ColsReduceInvParams{ws.partial, ws.stp, tw, nchunks, 1.0f / (static_cast<float>(N) * N),
+                            ws.dot_lanes, img_max, tie_count, ws.coef, B});
     LAUNCH_CHECK();
     k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
         RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
     LAUNCH_CHECK();
+    {   // arg-max term of the amax backward (spatial form), ties of channel c handled by the CTAs of row c
+        const int per_ch = N * N / EW_THREADS < 592 ? N * N / EW_THREADS : 592;   // N <= 256: one output element per thread
+        k_tie_term<<<dim3(per_ch, 3), EW_THREADS, 0, s>>>(TieTermParams{grad_psf, img, tie_count, tie_pos, ws.coef, B, N});
+        LAUNCH_CHECK();
+    }
     if (grad_img != nullptr) {
-        const int cchunk = conv_chunk(N, B);
-        k_cols_conv<N><<<dim3(colgroups, (B + cchunk - 1) / cchunk), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunk, 1, 1.0f});
+        const int cchunks = conv_chunks(N, B);
+        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunks, 1, 1.0f});
         LAUNCH_CHECK();
         k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
             RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
@@ -998,6 +1023,18 @@ int b200cam_init(int N) {
             case 1024: e = coop_grid_size<1024>(dev, sms, &g_state[dev].coop_grid[l]); break;
         }
     }
+    if (e == cudaSuccess) {
+        const int sms = g_state[dev].sms;
+        int* cs = &g_state[dev].conv_slots[l];
+        int* as = &g_state[dev].accum_slots[l];
+        switch (N) {
+            case 64: e = column_slots<64>(sms, cs, as); break;
+            case 128: e = column_slots<128>(sms, cs, as); break;
+            case 256: e = column_slots<256>(sms, cs, as); break;
+            case 512: e = column_slots<512>(sms, cs, as); break;
+            case 1024: e = column_slots<1024>(sms, cs, as); break;
+        }
+    }
     if (e != cudaSuccess) {
         cudaFree(tw);
         (void)cudaGetLastError();          // do not leave a sticky error behind for later launches
@@ -1034,7 +1071,7 @@ int b200cam_psf_fwd(const float* h, const float* A, const float* Ht, const float
                                      kappa, psf, reinterpret_cast<float2*>(field), stats, workspace, s)));
 }
 
-int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const float* h, const float* A,
+int b200cam_psf_bwd(const float* grad_psf, const float* grad_rad, const float* grad_cen, const float* h, const float* A,
                     const float* Ht, const float* rho, const float* kappa, const float* psf, const float* field,
                     float* stats, float* grad_h, void* workspace, size_t workspace_bytes, int N, void* stream) {
     if (!b200cam_supported(N)) return B200CAM_E_BAD_SIZE;
@@ -1042,7 +1079,7 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_scalars, const floa
     if (workspace_bytes < b200cam_psf_workspace_bytes(N)) return B200CAM_E_WORKSPACE;
     if (!aligned16(A) || !aligned16(Ht) || !aligned16(field) || !aligned16(workspace)) return B200CAM_E_ALIGN;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    DISPATCH_N(N, (psf_bwd_impl<NN_>(grad_psf, grad_scalars, h, reinterpret_cast<const float2*>(A),
+    DISPATCH_N(N, (psf_bwd_impl<NN_>(grad_psf, grad_rad, grad_cen, h, reinterpret_cast<const float2*>(A),
                                      reinterpret_cast<const float2*>(Ht), rho, kappa, psf,
                                      reinterpret_cast<const float2*>(field), stats, grad_h, workspace, s)));
 }
@@ -1052,7 +1089,7 @@ size_t b200cam_comm_bytes(int N, int world) {
     return COMM_HEADER_BYTES + static_cast<size_t>(2) * world * N * N * sizeof(float);
 }
 
-int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_scalars, const float* h, const float* A,
+int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_rad, const float* grad_cen, const float* h, const float* A,
                               const float* Ht, const float* rho, const float* kappa, const float* psf, const float* field,
                               float* stats, float* grad_h, void* workspace, size_t workspace_bytes, int N, void* stream,
                               void* const* peer_bufs, int rank, int world, float scale) {
@@ -1069,7 +1106,7 @@ int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_scalars, 
     for (int r = world; r < COMM_MAX_WORLD; ++r) comm.buf[r] = nullptr;
     comm.rank = rank; comm.world = world; comm.scale = scale;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    DISPATCH_N(N, (psf_bwd_impl<NN_>(grad_psf, grad_scalars, h, reinterpret_cast<const float2*>(A),
+    DISPATCH_N(N, (psf_bwd_impl<NN_>(grad_psf, grad_rad, grad_cen, h, reinterpret_cast<const float2*>(A),
                                      reinterpret_cast<const float2*>(Ht), rho, kappa, psf,
                                      reinterpret_cast<const float2*>(field), stats, grad_h, workspace, s, &comm)));
 }

@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
@@ -57,6 +58,24 @@ B200_HD T ld_ro(const T* p) {
     return __ldg(p);
 #else
     return *p;
+#endif
+}
+
+// ---- asynchronous global -> shared copies (LDGSTS: no register staging, the warp keeps computing) -----------
+// 16 bytes, both addresses 16-byte aligned; L2 only (.cg): the data is consumed once from shared memory.
+B200_HD void async_copy16(void* smem_dst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+                 "l"(gsrc)
+                 : "memory");
+#else
+    std::memcpy(smem_dst, gsrc, 16);
+#endif
+}
+// all copies issued by THIS thread have landed (other lanes' copies: follow with a warp / block barrier)
+B200_HD void async_wait_all() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
 #endif
 }
 

@@ -14,6 +14,7 @@ namespace b200cam {
 
 #if defined(__CUDACC__)
 struct DeviceExec {
+    static constexpr bool IS_HOST = false;
     __device__ __forceinline__ int bx() const { return blockIdx.x; }
     __device__ __forceinline__ int by() const { return blockIdx.y; }
     __device__ __forceinline__ int nthreads() const { return blockDim.x; }
@@ -37,6 +38,7 @@ struct DeviceExec {
 // A "virtual block" of a cooperative kernel: the CTA plays block (vbx, vby) of a body written for
 // `nthr` threads; surplus threads only take part in the barriers.
 struct VirtualExec {
+    static constexpr bool IS_HOST = false;
     int vbx, vby, nthr;
     __device__ __forceinline__ int bx() const { return vbx; }
     __device__ __forceinline__ int by() const { return vby; }
@@ -60,6 +62,7 @@ struct VirtualExec {
 #endif
 
 struct HostExec {
+    static constexpr bool IS_HOST = true;     // per-thread state that crosses a phase needs one slot per thread
     int bx_, by_, nthreads_;
     int bx() const { return bx_; }
     int by() const { return by_; }

@@ -25,7 +25,8 @@ struct Tile {
     static constexpr int FP_PAIR = N + 16 / NP;        // natural-order smem row pitch (float2)
     static constexpr int FP_ROW = N + 16 / ROWS;
     static constexpr int COLS = 8;                     // spectral columns per CTA in column passes
-    static constexpr int CROWS = (N >= 1024) ? 2 : 4;  // rows per CTA in the complex (PSF chain) row passes
+    static constexpr int CROWS = (N >= 256) ? 2 : 4;   // rows per CTA in the complex (PSF chain) row passes: these kernels are
+                                                       // latency chains - more, smaller CTAs shorten the chain per thread
     static constexpr int FP_CROW = N + 16 / CROWS;
     static constexpr int RCOLS = 2;                    // columns per CTA in the small batch-independent column passes
 };
@@ -33,36 +34,37 @@ struct Tile {
 // ---------------------------------------------------------------------------------------------
 // K1  rows_r2c : real rows -> transposed half spectrum (first half of rfftn, Utils.py:8-9)
 //      grid (N/ROWS, planes), block NP*LANES.
-//      optional: dot_with != nullptr accumulates sum(x*dot_with) per CTA into dot_partial
-//      (the s_b = sum(g*y) term of the amax backward), and init_max/init_count (tile 0 of channel
-//      0) reset the per-image max / tie counters for the kernels that follow in the stream.
+//      init_max/init_count (tile 0 of channel 0) reset the per-image max / tie counters for the
+//      kernels that follow in the stream.
 // ---------------------------------------------------------------------------------------------
 struct RowsR2CParams {
     const float* x;          // [planes][N][N]
     float2* st;              // [planes][NC][N]
     const float2* tw;
-    const float* dot_with;   // nullable, same shape as x
-    float* dot_partial;      // [planes][N/ROWS]
     float* init_max;         // nullable, [planes/3]
     int* init_count;         // nullable, [planes/3]
-    // with dot_with: the last CTA of an image to finish turns the partials into
-    //   coef[b] = sum(g*y) / (n_ties * max)      (the weight of the arg-max term of the amax backward)
-    int* arrive;             // [planes/3], zeroed by the caller before the launch
-    float* coef;             // [planes/3]
-    const float* img_max;    // [planes/3]
-    const int* tie_count;    // [planes/3]
 };
 
+// Shared memory of the row passes: one block of PA float2 per row pair, used first as the exchange array E of the
+// two-pass FFT and then, IN PLACE, as the natural-order line F of the same pair (only the 16/32 lanes of the pair touch
+// the block in between, so a warp-level sync separates the two uses).  Half the footprint of separate E and F arrays
+// = twice the resident CTAs: these kernels are latency bound and live on occupancy.
+// PA == FP_PAIR (mod 16 float2) keeps the transposing accesses of the unpack phase on distinct banks.
 template <int N>
 struct RowsR2CSmem {
     using P = Plan<N>;
     using T = Tile<N>;
-    static constexpr int E_OFF = 0;
-    static constexpr int F_OFF = T::NP * P::E_SIZE;
-    static constexpr int RED_OFF = F_OFF + T::NP * T::FP_PAIR;            // float2 units
-    static constexpr int FLOAT2S = RED_OFF + (T::NP * P::LANES + 2) / 2 + 1;  // reduction scratch (floats) + flag
+    static constexpr int PA = P::E_SIZE + (((T::FP_PAIR - P::E_SIZE) % 16) + 16) % 16;
+    static_assert(PA >= P::E_SIZE && PA >= T::FP_PAIR, "pair block too small");
+    static constexpr int RED_OFF = T::NP * PA;                                 // float2 units
+    static constexpr int FLOAT2S = RED_OFF + (T::NP * P::LANES + 2) / 2 + 1;   // reduction scratch (floats) of rows_c2r
     static constexpr int BYTES = FLOAT2S * 8;
     static constexpr int THREADS = T::NP * P::LANES;
+};
+
+template <int N>
+struct RowState {
+    float2 v[Plan<N>::R2];
 };
 
 template <int N, class Exec>
@@ -72,80 +74,46 @@ B200_HD void rows_r2c_body(Exec& ex, const RowsR2CParams& p, float2* smem) {
     using S = RowsR2CSmem<N>;
     const int tile = ex.bx(), plane = ex.by();
     const int y0 = tile * T::ROWS;
-    float2* E = smem + S::E_OFF;
-    float2* F = smem + S::F_OFF;
-    float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
+    RowState<N> st[Exec::IS_HOST ? S::THREADS : 1];
 
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
         const int j = tid / P::LANES, a = tid % P::LANES;
-        float dot = 0.f;
         if (a < P::R2) {
             const float* r0 = p.x + (static_cast<size_t>(plane) * N + y0 + 2 * j) * N;
             const float* r1 = r0 + N;
             float2 v[P::R1];
 #pragma unroll
             for (int i = 0; i < P::R1; ++i) v[i] = make_float2(ld_ro(r0 + P::R2 * i + a), ld_ro(r1 + P::R2 * i + a));
-            if (p.dot_with != nullptr) {
-                const float* d0 = p.dot_with + (static_cast<size_t>(plane) * N + y0 + 2 * j) * N;
-                const float* d1 = d0 + N;
-#pragma unroll
-                for (int i = 0; i < P::R1; ++i)
-                    dot += v[i].x * ld_ro(d0 + P::R2 * i + a) + v[i].y * ld_ro(d1 + P::R2 * i + a);
-            }
-            P::stepA(v, a, E + j * P::E_SIZE, p.tw);
+            P::stepA(v, a, smem + j * S::PA, p.tw);
         }
-        red[tid] = dot;
         if (tid == 0 && tile == 0 && plane % 3 == 0) {
             if (p.init_max != nullptr) p.init_max[plane / 3] = neg_inf();
             if (p.init_count != nullptr) p.init_count[plane / 3] = 0;
         }
     });
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
+        const int j = tid / P::LANES, b = tid % P::LANES;
+        if (b < P::R1) P::stepB(st[ex.slot(tid)].v, b, smem + j * S::PA);
+    });
+    ex.phase([&](int tid) {                       // every lane of the pair has read E: overwrite it with the line
         const int j = tid / P::LANES, b = tid % P::LANES;
         if (b < P::R1) {
-            float2 v[P::R2];
-            P::stepB(v, b, E + j * P::E_SIZE);
+            const RowState<N>& s = st[ex.slot(tid)];
 #pragma unroll
-            for (int i = 0; i < P::R2; ++i) F[j * T::FP_PAIR + b + P::R1 * i] = v[i];
-        }
-        if (tid == 0 && p.dot_with != nullptr) {
-            float s = 0.f;
-            for (int t = 0; t < S::THREADS; ++t) s += red[t];
-            p.dot_partial[plane * (N / T::ROWS) + tile] = s;
-            ex.threadfence();
-            const int old = atomic_add_int(p.arrive + plane / 3, 1);
-            red[S::THREADS] = (old == 3 * (N / T::ROWS) - 1) ? 1.f : 0.f;     // this CTA completes the image
+            for (int i = 0; i < P::R2; ++i) smem[j * S::PA + b + P::R1 * i] = s.v[i];
         }
     });
     ex.phase([&](int tid) {
-        if (p.dot_with != nullptr && red[S::THREADS] != 0.f && tid < 32) {
-            ex.threadfence();
-            float s = 0.f;                                                          // fixed order: deterministic
-            for (int t = tid; t < 3 * (N / T::ROWS); t += 32)
-                s += ex.load_cg(p.dot_partial + (plane / 3) * 3 * (N / T::ROWS) + t);
-            red[tid] = s;
-        }
         // unpack the pair spectrum Z = FFT(row_even + i*row_odd) into the two Hermitian halves
         for (int w = tid; w < T::NP * T::NC; w += S::THREADS) {
             const int u = w / T::NP, j = w % T::NP;
-            const float2 z1 = F[j * T::FP_PAIR + u];
-            const float2 z2 = F[j * T::FP_PAIR + ((N - u) & (N - 1))];
+            const float2 z1 = smem[j * S::PA + u];
+            const float2 z2 = smem[j * S::PA + ((N - u) & (N - 1))];
             const float4 o = make_float4(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y),    // X_even[u]
                                          0.5f * (z1.y + z2.y), -0.5f * (z1.x - z2.x));  // X_odd[u]
             *reinterpret_cast<float4*>(p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0 + 2 * j) = o;
         }
     });
-    if (p.dot_with != nullptr) {
-        ex.phase([&](int tid) {
-            if (tid == 0 && red[S::THREADS] != 0.f) {
-                float s = 0.f;
-                for (int t = 0; t < 32; ++t) s += red[t];
-                const int b = plane / 3;
-                const int n = p.tie_count[b] > 0 ? p.tie_count[b] : 1;
-                p.coef[b] = s / (static_cast<float>(n) * p.img_max[b]);
-            }
-        });
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -162,7 +130,7 @@ struct ColsConvParams {
     const float2* tw;
     const float* img_scale;  // nullable: per image multiplier is 1/img_scale[b]
     int B;
-    int chunk;               // images per CTA (gridDim.y = ceil(B/chunk))
+    int nchunks;             // = gridDim.y: CTA (., y) owns images [B*y/nchunks, B*(y+1)/nchunks) (balanced split)
     int conj_otf;
     float otf_scale;         // extra factor on the OTF (the fused N=256 path stores it pre-halved)
 };
@@ -172,9 +140,29 @@ struct ColsSmem {
     using P = Plan<N>;
     static constexpr int COLS = Tile<N>::COLS;
     static constexpr int THREADS = COLS * P::LANES;
-    static constexpr int FLOAT2S = 2 * COLS * P::E_SIZE;
+    // N <= 256: the next image's columns are copied global -> shared ASYNCHRONOUSLY (cp.async) while the current image
+    // is transformed, one staging line of N float2 per column and operand.  The lanes of one column FFT are the only
+    // readers and writers of their line, so warp-level syncs are enough.  Larger N: direct loads (the staging
+    // lines would cost the occupancy they are meant to replace).
+    static constexpr bool STAGED = N <= 256;
+    static constexpr int STAGE_OFF = 2 * COLS * P::E_SIZE;                          // float2 units
+    static constexpr int FLOAT2S_CONV = STAGE_OFF + (STAGED ? COLS * N : 0);        // one operand
+    static constexpr int FLOAT2S_ACCUM = STAGE_OFF + (STAGED ? 2 * COLS * N : 0);   // two operands
+    static constexpr int FLOAT2S = FLOAT2S_ACCUM;
+    static constexpr int BYTES_CONV = FLOAT2S_CONV * 8;
     static constexpr int BYTES = FLOAT2S * 8;
 };
+
+// lane `a` of a column's LANES lanes issues its share of the async copy of one spectral column (N float2)
+template <int N>
+B200_HD void stage_column(float2* line, const float2* src, int a) {
+    constexpr int CHUNKS = N / 2;                        // 16-byte chunks
+#pragma unroll
+    for (int k = 0; k < CHUNKS / Plan<N>::LANES; ++k) {
+        const int ch = a + Plan<N>::LANES * k;
+        async_copy16(line + 2 * ch, src + 2 * ch);
+    }
+}
 
 template <int N>
 struct ConvState {
@@ -191,35 +179,56 @@ B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem, Con
     using S = ColsSmem<N>;
     float2* E1 = smem;
     float2* E2 = smem + S::COLS * P::E_SIZE;
+    float2* stage = smem + S::STAGE_OFF;
     constexpr int TOTAL = 3 * T::NC;
     const int cu0 = ex.bx() * S::COLS;
-    const int b0 = ex.by() * p.chunk;
-    const int b1 = (b0 + p.chunk < p.B) ? b0 + p.chunk : p.B;
+    const int b0 = static_cast<int>(static_cast<long long>(p.B) * ex.by() / p.nchunks);
+    const int b1 = static_cast<int>(static_cast<long long>(p.B) * (ex.by() + 1) / p.nchunks);
+    auto column = [&](int img, int cu) {
+        return p.in + (static_cast<size_t>(img * 3 + cu / T::NC) * T::NC + cu % T::NC) * N;   // may alias out: plain loads
+    };
 
     ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, b = tid % P::LANES;
         const int cu = cu0 + jc;
-        if (cu < TOTAL && b < P::R1) {
-            ConvState<N>& s = st[ex.slot(tid)];
-            const float2* k = p.otf + static_cast<size_t>(cu) * N;
+        if (cu < TOTAL) {
+            if (b < P::R1) {
+                ConvState<N>& s = st[ex.slot(tid)];
+                const float2* k = p.otf + static_cast<size_t>(cu) * N;
 #pragma unroll
-            for (int i = 0; i < P::R2; ++i) {
-                const float2 kk = cscale(ld_ro(k + b + P::R1 * i), p.otf_scale);
-                s.k[i] = p.conj_otf ? cconj(kk) : kk;
+                for (int i = 0; i < P::R2; ++i) {
+                    const float2 kk = cscale(ld_ro(k + b + P::R1 * i), p.otf_scale);
+                    s.k[i] = p.conj_otf ? cconj(kk) : kk;
+                }
             }
+            if (S::STAGED && b0 < b1) stage_column<N>(stage + jc * N, column(b0, cu), b);
         }
+        if (S::STAGED) async_wait_all();
     });
     for (int img = b0; img < b1; ++img) {
         ex.warp_phase([&](int tid) {
             const int jc = tid / P::LANES, a = tid % P::LANES;
             const int cu = cu0 + jc;
             if (cu < TOTAL && a < P::R2) {
-                const int c = cu / T::NC, u = cu % T::NC;
-                const float2* src = p.in + (static_cast<size_t>(img * 3 + c) * T::NC + u) * N;   // may alias out: plain loads
-                float2 v[P::R1];
+                ConvState<N>& s = st[ex.slot(tid)];
+                const float2* src = S::STAGED ? stage + jc * N : column(img, cu);
 #pragma unroll
-                for (int i = 0; i < P::R1; ++i) v[i] = src[P::R2 * i + a];
-                P::stepA(v, a, E1 + jc * P::E_SIZE, p.tw);
+                for (int i = 0; i < P::R1; ++i) s.v[i] = src[P::R2 * i + a];
+            }
+        });
+        ex.warp_phase([&](int tid) {
+            const int jc = tid / P::LANES, a = tid % P::LANES;
+            const int cu = cu0 + jc;
+            if (cu < TOTAL) {
+                // every lane holds its part of the staged column: refill the line with the next image's column
+                if (S::STAGED && img + 1 < b1) stage_column<N>(stage + jc * N, column(img + 1, cu), a);
+                if (a < P::R2) {
+                    float2 v[P::R1];
+                    const ConvState<N>& s = st[ex.slot(tid)];
+#pragma unroll
+                    for (int i = 0; i < P::R1; ++i) v[i] = s.v[i];
+                    P::stepA(v, a, E1 + jc * P::E_SIZE, p.tw);
+                }
             }
         });
         ex.warp_phase([&](int tid) {
@@ -249,6 +258,7 @@ B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem, Con
 #pragma unroll
                 for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = v[i];
             }
+            if (S::STAGED) async_wait_all();
         });
     }
 }
@@ -329,9 +339,8 @@ B200_HD void rows_c2r_body(Exec& ex, const RowsC2RParams& p, float2* smem) {
     using S = RowsR2CSmem<N>;
     const int tile = ex.bx(), plane = ex.by();
     const int y0 = tile * T::ROWS;
-    float2* E = smem + S::E_OFF;
-    float2* F = smem + S::F_OFF;
     float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
+    RowState<N> st[Exec::IS_HOST ? S::THREADS : 1];
 
     ex.phase([&](int tid) {
         for (int w = tid; w < T::NP * T::NC; w += S::THREADS) {
@@ -339,29 +348,33 @@ B200_HD void rows_c2r_body(Exec& ex, const RowsC2RParams& p, float2* smem) {
             const float4 q = ld_ro(reinterpret_cast<const float4*>(
                 p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0 + 2 * j));
             // Z = X_even + i X_odd ; Z[N-u] = conj(X_even[u]) + i conj(X_odd[u])
+            float2* F = smem + j * S::PA;
             if (u == 0 || u == N / 2) {
-                F[j * T::FP_PAIR + u] = make_float2(q.x, q.z);   // irfft ignores Im at DC/Nyquist
+                F[u] = make_float2(q.x, q.z);   // irfft ignores Im at DC/Nyquist
             } else {
-                F[j * T::FP_PAIR + u] = make_float2(q.x - q.w, q.y + q.z);
-                F[j * T::FP_PAIR + N - u] = make_float2(q.x + q.w, q.z - q.y);
+                F[u] = make_float2(q.x - q.w, q.y + q.z);
+                F[N - u] = make_float2(q.x + q.w, q.z - q.y);
             }
         }
     });
-    ex.phase([&](int tid) {
+    ex.warp_phase([&](int tid) {
         const int j = tid / P::LANES, b = tid % P::LANES;
         if (b < P::R1) {
-            float2 v[P::R2];
+            RowState<N>& s = st[ex.slot(tid)];
 #pragma unroll
-            for (int i = 0; i < P::R2; ++i) v[i] = F[j * T::FP_PAIR + b + P::R1 * i];
-            P::stepC(v, b, E + j * P::E_SIZE, p.tw);
+            for (int i = 0; i < P::R2; ++i) s.v[i] = smem[j * S::PA + b + P::R1 * i];
         }
+    });
+    ex.warp_phase([&](int tid) {                  // every lane of the pair holds its part of the line: reuse it as E
+        const int j = tid / P::LANES, b = tid % P::LANES;
+        if (b < P::R1) P::stepC(st[ex.slot(tid)].v, b, smem + j * S::PA, p.tw);
     });
     ex.phase([&](int tid) {
         const int j = tid / P::LANES, a = tid % P::LANES;
         float mx = neg_inf();
         if (a < P::R2) {
             float2 v[P::R1];
-            P::stepD(v, a, E + j * P::E_SIZE);
+            P::stepD(v, a, smem + j * S::PA);
             const size_t row = (static_cast<size_t>(plane) * N + y0 + 2 * j) * N;
             if (p.norm) {
                 const int img = plane / 3;
@@ -473,6 +486,11 @@ B200_HD void normalise_body(Exec& ex, const NormaliseParams& p, int grid_x) {
 //      (closed form of autograd through Utils.py:7-12 w.r.t. the kernel)
 //      grid (ceil(3*NC/COLS), nchunks), block COLS*LANES.  Output partial[chunk][3][NC][N].
 //      Deterministic: fixed b order inside a chunk, chunks summed in order by K7.
+//
+//      With `otf` the same registers also give the amax backward's  sum(g_b * conv_b)  (Optics.py:128) by
+//      Parseval:  sum_{y,x} g conv = sum_{u<=N/2,v} wt_u Re( G conj(X K) ),  K = OTF (already / N^2), wt = 1 at
+//      u = 0, N/2 and 2 elsewhere.  Every thread stores its own partial (dot_lanes[b][column][lane], summed in a
+//      fixed order by K7) - the upstream gradient's row pass then needs no second operand (sensor image) at all.
 // ---------------------------------------------------------------------------------------------
 struct ColsAccumParams {
     const float2* stx;      // [B*3][NC][N] row-transformed image
@@ -480,13 +498,10 @@ struct ColsAccumParams {
     float2* partial;        // [nchunks][3][NC][N]
     const float2* tw;
     const float* img_max;   // [B]; nullptr: no per-image scale (plain convolution adjoint)
-    // arg-max term of the amax backward, applied as  G' = G/m - coef * sum_t exp(-2 pi i (v ty + u tx)/N)
-    // on the channel that holds the tie (nullable: term left to the spatial tie_term kernel)
-    const float* coef;      // [B]
-    const int* tie_count;   // [B]
-    const int* tie_pos;     // [B][MAX_TIES]
+    const float2* otf;      // nullable [3][NC][N]: also emit the per-thread partials of sum(g * conv)
+    float* dot_lanes;       // [B][3*NC][R1]
     int B;
-    int chunk;              // images per chunk
+    int nchunks;            // = gridDim.y: chunk y owns images [B*y/nchunks, B*(y+1)/nchunks) (balanced split)
 };
 
 template <int N>
@@ -502,31 +517,52 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
     float2* Ex = smem;
     float2* Eg = smem + S::COLS * P::E_SIZE;
     const int cu0 = ex.bx() * S::COLS;
-    const int b0 = ex.by() * p.chunk;
-    const int b1 = (b0 + p.chunk < p.B) ? b0 + p.chunk : p.B;
+    const int b0 = static_cast<int>(static_cast<long long>(p.B) * ex.by() / p.nchunks);
+    const int b1 = static_cast<int>(static_cast<long long>(p.B) * (ex.by() + 1) / p.nchunks);
     constexpr int TOTAL = 3 * T::NC;
 
+    float2* stage = smem + S::STAGE_OFF;                 // [2 operands][COLS][N]
+    auto column = [&](const float2* base, int b, int cu) {
+        return base + (static_cast<size_t>(b * 3 + cu / T::NC) * T::NC + cu % T::NC) * N;
+    };
     ex.warp_phase([&](int tid) {
         AccumState<N>& s = st[ex.slot(tid)];
 #pragma unroll
         for (int i = 0; i < P::R2; ++i) s.acc[i] = make_float2(0.f, 0.f);
+        const int jc = tid / P::LANES, a = tid % P::LANES;
+        const int cu = cu0 + jc;
+        if (S::STAGED && cu < TOTAL && b0 < b1) {
+            stage_column<N>(stage + jc * N, column(p.stx, b0, cu), a);
+            stage_column<N>(stage + (S::COLS + jc) * N, column(p.stg, b0, cu), a);
+        }
+        if (S::STAGED) async_wait_all();
     });
     for (int b = b0; b < b1; ++b) {
         ex.warp_phase([&](int tid) {
             const int jc = tid / P::LANES, a = tid % P::LANES;
             const int cu = cu0 + jc;
             if (cu < TOTAL && a < P::R2) {
-                const int c = cu / T::NC, u = cu % T::NC;
-                const size_t off = (static_cast<size_t>(b * 3 + c) * T::NC + u) * N;
+                const float2* sx = S::STAGED ? stage + jc * N : column(p.stx, b, cu);
+                const float2* sg = S::STAGED ? stage + (S::COLS + jc) * N : column(p.stg, b, cu);
                 float2 v[P::R1];
 #pragma unroll
-                for (int i = 0; i < P::R1; ++i) v[i] = ld_ro(p.stx + off + P::R2 * i + a);
+                for (int i = 0; i < P::R1; ++i) v[i] = S::STAGED ? sx[P::R2 * i + a] : ld_ro(sx + P::R2 * i + a);
                 P::stepA(v, a, Ex + jc * P::E_SIZE, p.tw);
 #pragma unroll
-                for (int i = 0; i < P::R1; ++i) v[i] = ld_ro(p.stg + off + P::R2 * i + a);
+                for (int i = 0; i < P::R1; ++i) v[i] = S::STAGED ? sg[P::R2 * i + a] : ld_ro(sg + P::R2 * i + a);
                 P::stepA(v, a, Eg + jc * P::E_SIZE, p.tw);
             }
         });
+        if (S::STAGED && b + 1 < b1) {
+            ex.warp_phase([&](int tid) {               // both staged columns are in registers / E: refill the lines
+                const int jc = tid / P::LANES, a = tid % P::LANES;
+                const int cu = cu0 + jc;
+                if (cu < TOTAL) {
+                    stage_column<N>(stage + jc * N, column(p.stx, b + 1, cu), a);
+                    stage_column<N>(stage + (S::COLS + jc) * N, column(p.stg, b + 1, cu), a);
+                }
+            });
+        }
         ex.warp_phase([&](int tid) {
             const int jc = tid / P::LANES, bb = tid % P::LANES;
             const int cu = cu0 + jc;
@@ -536,31 +572,26 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
                 float2 vx[P::R2], vg[P::R2];
                 P::stepB(vx, bb, Ex + jc * P::E_SIZE);
                 P::stepB(vg, bb, Eg + jc * P::E_SIZE);
-#pragma unroll
-                for (int i = 0; i < P::R2; ++i) vg[i] = cscale(vg[i], inv_m);
-                if (p.coef != nullptr) {
-                    const int c = cu / T::NC, u = cu % T::NC;
-                    const int nt = p.tie_count[b] < MAX_TIES ? p.tie_count[b] : MAX_TIES;
-                    const float cf = ld_ro(p.coef + b);
-                    for (int t = 0; t < nt; ++t) {
-                        const int pos = p.tie_pos[b * MAX_TIES + t];
-                        if (pos / (N * N) != c) continue;
-                        const int ty = (pos % (N * N)) / N, tx = pos % N;
-                        const float2 pu = cscale(ld_ro(p.tw + ((u * tx) & (N - 1))), cf);
-#pragma unroll
-                        for (int i = 0; i < P::R2; ++i) {
-                            const int v = bb + P::R1 * i;
-                            vg[i] = csub(vg[i], cmul(pu, ld_ro(p.tw + ((v * ty) & (N - 1)))));
-                        }
-                    }
-                }
+                float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < P::R2; ++i) {
-                    const float2 t = cmulc(vg[i], vx[i]);   // G' * conj(X)
-                    s.acc[i].x += t.x;
-                    s.acc[i].y += t.y;
+                    const float2 t = cmulc(vg[i], vx[i]);   // G * conj(X)
+                    if (p.otf != nullptr) {
+                        // Re(G conj(X K)) = Re(t conj(K)) = t.x K.x + t.y K.y  (kept as two lanes: one packed FMA)
+                        const float2 k = ld_ro(p.otf + static_cast<size_t>(cu) * N + bb + P::R1 * i);
+                        d2.x += t.x * k.x;
+                        d2.y += t.y * k.y;
+                    }
+                    s.acc[i].x += t.x * inv_m;
+                    s.acc[i].y += t.y * inv_m;
+                }
+                if (p.otf != nullptr) {
+                    const int u = cu % T::NC;
+                    const float wt = (u == 0 || u == N / 2) ? 1.0f : 2.0f;
+                    p.dot_lanes[(static_cast<size_t>(b) * TOTAL + cu) * P::R1 + bb] = wt * (d2.x + d2.y);
                 }
             }
+            if (S::STAGED) async_wait_all();
         });
     }
     ex.warp_phase([&](int tid) {
@@ -585,6 +616,13 @@ struct ColsReduceInvParams {
     const float2* tw;
     int nchunks;
     float scale;
+    // side job (dot_lanes != nullptr): CTA i also reduces image i's partials of sum(g*conv) written by K6 into
+    //   coef[b] = sum(g_b*y_b) / (n_b m_b) = sum(g_b*conv_b) / (n_b m_b^2)     (weight of the arg-max term, Optics.py:128)
+    const float* dot_lanes;  // nullable [B][3*NC*R1]
+    const float* img_max;    // [B]
+    const int* tie_count;    // [B]
+    float* coef;             // [B]
+    int B;
 };
 
 // grid 3*NC (one spectral column per CTA), block N (thread = v): the chunk sum is spread over N threads with
@@ -606,6 +644,34 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
     const int cu = ex.bx();
     constexpr int TOTAL = 3 * T::NC;
     const int u = cu % T::NC;
+    if (p.dot_lanes != nullptr) {
+        constexpr int PER_IMAGE = TOTAL * P::R1;
+        float* red = reinterpret_cast<float*>(E);            // N floats of scratch (E is free until the second phase below)
+        for (int b = cu; b < p.B; b += TOTAL) {
+            ex.phase([&](int t) {
+                const float* src = p.dot_lanes + static_cast<size_t>(b) * PER_IMAGE;
+                float s = 0.f;
+                for (int i = t; i < PER_IMAGE; i += N) s += src[i];      // fixed order: deterministic
+                red[t] = s;
+            });
+            ex.phase([&](int t) {
+                if (t < 16) {
+                    float s = 0.f;
+                    for (int i = t; i < N; i += 16) s += red[i];
+                    red[N + t] = s;
+                }
+            });
+            ex.phase([&](int t) {
+                if (t == 0) {
+                    float s = 0.f;
+                    for (int i = 0; i < 16; ++i) s += red[N + i];
+                    const int n = p.tie_count[b] > 0 ? p.tie_count[b] : 1;
+                    const float m = p.img_max[b];
+                    p.coef[b] = s / (static_cast<float>(n) * m * m);
+                }
+            });
+        }
+    }
     ex.phase([&](int v) {
         const float2* src = p.partial + static_cast<size_t>(cu) * N + v;
         const size_t step = static_cast<size_t>(TOTAL) * N;
@@ -641,33 +707,17 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
 // ---------------------------------------------------------------------------------------------
 // K8  tie_term : the arg-max part of the amax backward, in the spatial domain
 //      gpsf[c][p] -= sum_b sum_{ties t of image b in channel c} (s_b/(n_b m_b)) * x_b[c][(p*_t - p + N/2) mod N]
-//      with s_b = sum(g_b * y_b) assembled from the K1 partials in fixed order.
+//      with s_b = sum(g_b * y_b) from the Parseval partials of K6, reduced by K7 (coef).
 //      grid-stride over 3*N*N outputs.
 // ---------------------------------------------------------------------------------------------
 struct TieTermParams {
     float* gpsf;              // [3][N][N] in place
     const float* x;           // [B][3][N][N]
-    const float* img_max;     // [B]
     const int* tie_count;     // [B]
     const int* tie_pos;       // [B][MAX_TIES]
-    const float* dot_partial; // [B*3][tiles]
-    float* coef;              // [B] scratch: s_b / (n_b m_b), filled by tie_coef_body
-    int B, N, tiles;
+    const float* coef;        // [B]: s_b / (n_b m_b), written by K7
+    int B, N;
 };
-
-template <class Exec>
-B200_HD void tie_coef_body(Exec& ex, const TieTermParams& p, int grid_x) {
-    ex.phase([&](int tid) {
-        const int b = ex.bx() * ex.nthreads() + tid;
-        (void)grid_x;
-        if (b < p.B) {
-            float s = 0.f;
-            for (int t = 0; t < 3 * p.tiles; ++t) s += p.dot_partial[b * 3 * p.tiles + t];
-            const int n = p.tie_count[b] > 0 ? p.tie_count[b] : 1;
-            p.coef[b] = s / (static_cast<float>(n) * p.img_max[b]);
-        }
-    });
-}
 
 constexpr int TIE_PASS = 256;   // images staged per pass (= block size of the kernel)
 
@@ -690,17 +740,13 @@ B200_HD void tie_term_body(Exec& ex, const TieTermParams& p, int grid_x, float* 
             if (tid < TIE_PASS) s_cnt[tid] = cnt;
         });
         ex.phase([&](int tid) {
-            if (tid == 0) {
-                int run = 0;
-                for (int t = 0; t < nb; ++t) { const int v = s_cnt[t]; s_cnt[t] = run; run += v; }
-                s_cnt[TIE_PASS] = run;
-            }
-        });
-        ex.phase([&](int tid) {
             if (tid < nb) {
+                // exclusive prefix of the counts: every thread sums the (broadcast) counts below it - no serial scan
+                int k = 0;
+                for (int t = 0; t < tid; ++t) k += s_cnt[t];
+                if (tid == nb - 1) s_cnt[TIE_PASS] = k + s_cnt[tid];
                 const int b = b0 + tid;
                 const int n = p.tie_count[b] < MAX_TIES ? p.tie_count[b] : MAX_TIES;
-                int k = s_cnt[tid];
                 for (int t = 0; t < n; ++t) {
                     const int pos = p.tie_pos[b * MAX_TIES + t];
                     if (pos / NN != c) continue;
@@ -719,10 +765,20 @@ B200_HD void tie_term_body(Exec& ex, const TieTermParams& p, int grid_x, float* 
                 for (int idx = ex.bx() * ex.nthreads() + tid; idx < NN; idx += stride) {
                     const int py = idx / N, px = idx % N;
                     float acc = 0.f;
-                    for (int e = 0; e < k; ++e) {
-                        const int sy = (s_meta[3 * e + 1] - py + N / 2 + N) & (N - 1);
-                        const int sx = (s_meta[3 * e + 2] - px + N / 2 + N) & (N - 1);
-                        acc += s_coef[e] * ld_ro(p.x + (static_cast<size_t>(s_meta[3 * e]) * 3 + c) * NN + sy * N + sx);
+                    // the gathers are DRAM-latency bound: always 16 in flight per thread (tail entries are clamped to
+                    // the last valid one and weighted 0, which adds exact zeros: same sum, fixed order)
+                    for (int e = 0; e < k; e += 16) {
+                        float v[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int ee = e + q < k ? e + q : k - 1;
+                            const int sy = (s_meta[3 * ee + 1] - py + N / 2 + N) & (N - 1);
+                            const int sx = (s_meta[3 * ee + 2] - px + N / 2 + N) & (N - 1);
+                            v[q] = ld_ro(p.x + (static_cast<size_t>(s_meta[3 * ee]) * 3 + c) * NN + sy * N + sx);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 16; ++q)
+                            if (e + q < k) acc += s_coef[e + q] * v[q];
                     }
                     p.gpsf[c * NN + idx] -= acc;
                 }
@@ -1287,7 +1343,8 @@ B200_HD void psf_finalise_body(Exec& ex, const PsfFinaliseParams& p, int grid_x,
 // Q1  psf_grad_prepare: gtot = gpsf + g_rad * d loss_rad/dpsf + g_cen * d centering/dpsf ; partial sum(gtot*psf)
 struct PsfGradPrepParams {
     const float* gpsf;     // nullable [3][N][N]
-    const float* gscal;    // nullable device [2]: upstream grads of (loss_rad, centering_loss)
+    const float* g_rad;    // nullable device scalar: upstream gradient of loss_rad
+    const float* g_cen;    // nullable device scalar: upstream gradient of centering_loss
     const float* psf;      // [3][N][N]
     const float* rho;
     const float* scal;
@@ -1300,8 +1357,8 @@ template <class Exec>
 B200_HD void psf_grad_prepare_body(Exec& ex, const PsfGradPrepParams& p, int grid_x, float* red) {
     const int N = p.N, NN = N * N, total = 3 * NN;
     ex.phase([&](int tid) {
-        const float g_rad = p.gscal != nullptr ? p.gscal[0] : 0.f;
-        const float g_cen = p.gscal != nullptr ? p.gscal[1] : 0.f;
+        const float g_rad = p.g_rad != nullptr ? *p.g_rad : 0.f;
+        const float g_cen = p.g_cen != nullptr ? *p.g_cen : 0.f;
         const float loss_rad = p.scal[1];
         const float kc = g_cen * 4.0f / static_cast<float>(total);
         float dot = 0.f;

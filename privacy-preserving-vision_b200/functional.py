@@ -116,10 +116,9 @@ class PsfSynth(torch.autograd.Function):
         N = plan.N
         hc, psf, field, stats = ctx.saved_tensors
         gp = _as_f32(g_psf, plan.device).reshape(3, N, N) if g_psf is not None else None
-        gs = None
-        if g_rad is not None or g_cen is not None:
-            zero = torch.zeros((), dtype=torch.float32, device=plan.device)
-            gs = torch.stack((g_rad if g_rad is not None else zero, g_cen if g_cen is not None else zero)).float()
+        # the two regulariser gradients are passed as two device scalars (no stack / zeros kernels in between)
+        gr = _as_f32(g_rad, plan.device).reshape(1) if g_rad is not None else None
+        gc = _as_f32(g_cen, plan.device).reshape(1) if g_cen is not None else None
         grad_h = torch.empty(N, N, dtype=torch.float32, device=plan.device)
         ws = plan.psf_workspace()
         comm = plan.peer_comm
@@ -127,15 +126,15 @@ class PsfSynth(torch.autograd.Function):
             # all-reduce fused into the last kernel: peer-memory pushes over NVLink, no NCCL call
             with torch.cuda.device(plan.index):
                 _lib.check(plan.lib.b200cam_psf_bwd_allreduce(
-                    _lib.ptr(gp), _lib.ptr(gs), _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho),
-                    plan.kappa, _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(grad_h),
+                    _lib.ptr(gp), _lib.ptr(gr), _lib.ptr(gc), _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht),
+                    _lib.ptr(plan.rho), plan.kappa, _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(grad_h),
                     _lib.ptr(ws), ws.numel(), N, _stream(), comm.ptr_array, comm.rank, comm.world,
                     1.0 / comm.world if plan.average_grads else 1.0))
             return grad_h.reshape(ctx.h_shape), None, None
         with torch.cuda.device(plan.index):
             _lib.check(plan.lib.b200cam_psf_bwd(
-                _lib.ptr(gp), _lib.ptr(gs), _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho),
-                plan.kappa, _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(grad_h),
+                _lib.ptr(gp), _lib.ptr(gr), _lib.ptr(gc), _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht),
+                _lib.ptr(plan.rho), plan.kappa, _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(grad_h),
                 _lib.ptr(ws), ws.numel(), N, _stream()))
         if plan.process_group is not None:
             from .parallel import allreduce_height_grad

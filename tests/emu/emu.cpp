@@ -34,11 +34,12 @@ void grid2(int gx, int gy, int threads, F&& f) {
 
 constexpr int EW_GRID = 7;   // any grid works for the grid-stride bodies; a small odd one on purpose
 
-int accum_chunks(int N, int B) {
+int accum_chunks(int N, int B) {          // the library sizes this from the device's occupancy; any value works
     const int colgroups = (3 * (N / 2 + 1) + 7) / 8;
-    int n = 592 / colgroups;
-    if (n < 1) n = 1;
+    int n = 444 / colgroups;
+    if (n > 16) n = 16;
     if (n > B) n = B;
+    if (n < 1) n = 1;
     return n;
 }
 
@@ -47,7 +48,7 @@ void otf_impl(const float* psf, float2* otf, const float2* tw) {
     using T = Tile<N>;
     std::vector<float2> smem(RowsR2CSmem<N>::FLOAT2S > ColsSmem<N>::FLOAT2S ? RowsR2CSmem<N>::FLOAT2S : ColsSmem<N>::FLOAT2S);
     grid2(N / T::ROWS, 3, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_r2c_body<N>(ex, RowsR2CParams{psf, otf, tw, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, smem.data());
+        rows_r2c_body<N>(ex, RowsR2CParams{psf, otf, tw, nullptr, nullptr}, smem.data());
     });
     const int total = 3 * T::NC;
     grid2((total + T::COLS - 1) / T::COLS, 1, ColsSmem<N>::THREADS, [&](HostExec& ex) {
@@ -55,11 +56,13 @@ void otf_impl(const float* psf, float2* otf, const float2* tw) {
     });
 }
 
-int conv_chunk(int N, int B) {
+int conv_chunks(int N, int B) {
     const int colgroups = (3 * (N / 2 + 1) + 7) / 8;
-    int nchunks = (148 * 5 + colgroups - 1) / colgroups;
-    if (nchunks > B) nchunks = B;
-    return (B + nchunks - 1) / nchunks;
+    int n = 592 / colgroups;
+    if (n > 16) n = 16;
+    if (n > B) n = B;
+    if (n < 1) n = 1;
+    return n;
 }
 
 template <int N>
@@ -73,14 +76,13 @@ int sensor_fwd_impl(int B, const float* img, const float* psf, float* sensor, fl
     float2* srow = spectrum != nullptr ? spectrum : stx.data();
     std::vector<float2> smem(RowsR2CSmem<N>::FLOAT2S > ColsSmem<N>::FLOAT2S ? RowsR2CSmem<N>::FLOAT2S : ColsSmem<N>::FLOAT2S);
     grid2(N / T::ROWS, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_r2c_body<N>(ex, RowsR2CParams{img, srow, tw.data(), nullptr, nullptr, img_max, tie_count, nullptr, nullptr,
-                                           nullptr, nullptr}, smem.data());
+        rows_r2c_body<N>(ex, RowsR2CParams{img, srow, tw.data(), img_max, tie_count}, smem.data());
     });
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
-    const int chunk = conv_chunk(N, B);
+    const int nchunks = conv_chunks(N, B);
     std::vector<ConvState<N>> cst(ColsSmem<N>::THREADS);
-    grid2(colgroups, (B + chunk - 1) / chunk, ColsSmem<N>::THREADS, [&](HostExec& ex) {
-        cols_conv_body<N>(ex, ColsConvParams{srow, st2.data(), otf, tw.data(), nullptr, B, chunk, 0, 1.0f}, smem.data(), cst.data());
+    grid2(colgroups, nchunks, ColsSmem<N>::THREADS, [&](HostExec& ex) {
+        cols_conv_body<N>(ex, ColsConvParams{srow, st2.data(), otf, tw.data(), nullptr, B, nchunks, 0, 1.0f}, smem.data(), cst.data());
     });
     grid2(N / T::ROWS, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
         rows_c2r_body<N>(ex, RowsC2RParams{st2.data(), sensor, tw.data(), img_max, 1.0f, nullptr, nullptr, 0}, smem.data());
@@ -102,43 +104,50 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
     const size_t plane_sz = static_cast<size_t>(T::NC) * N;
     std::vector<float2> stx(planes * plane_sz), stg(planes * plane_sz), stp(3 * plane_sz);
     const int nchunks = accum_chunks(N, B);
-    const int chunk = (B + nchunks - 1) / nchunks;
-    const int used_chunks = (B + chunk - 1) / chunk;
+    const int used_chunks = nchunks;
     std::vector<float2> partial(static_cast<size_t>(nchunks) * 3 * plane_sz);
-    std::vector<float> dot_partial(static_cast<size_t>(planes) * N), coef(B);
-    std::vector<int> arrive(B, 0);
+    std::vector<float> dot_lanes(static_cast<size_t>(B) * 3 * T::NC * 32), coef(B);
+    (void)sensor;
     std::vector<float2> smem(RowsR2CSmem<N>::FLOAT2S > ColsSmem<N>::FLOAT2S ? RowsR2CSmem<N>::FLOAT2S : ColsSmem<N>::FLOAT2S);
     const float2* srow = spectrum;
     if (srow == nullptr) {
         grid2(tiles, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-            rows_r2c_body<N>(ex, RowsR2CParams{img, stx.data(), tw.data(), nullptr, nullptr, nullptr, nullptr, nullptr,
-                                               nullptr, nullptr, nullptr}, smem.data());
+            rows_r2c_body<N>(ex, RowsR2CParams{img, stx.data(), tw.data(), nullptr, nullptr}, smem.data());
         });
         srow = stx.data();
     }
     grid2(tiles, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_r2c_body<N>(ex, RowsR2CParams{g, stg.data(), tw.data(), sensor, dot_partial.data(), nullptr, nullptr,
-                                           arrive.data(), coef.data(), img_max, tie_count}, smem.data());
+        rows_r2c_body<N>(ex, RowsR2CParams{g, stg.data(), tw.data(), nullptr, nullptr}, smem.data());
     });
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     std::vector<AccumState<N>> states(ColsSmem<N>::THREADS);
     grid2(colgroups, used_chunks, ColsSmem<N>::THREADS, [&](HostExec& ex) {
-        cols_accum_body<N>(ex, ColsAccumParams{srow, stg.data(), partial.data(), tw.data(), img_max, coef.data(),
-                                               tie_count, tie_pos, B, chunk}, smem.data(), states.data());
+        cols_accum_body<N>(ex, ColsAccumParams{srow, stg.data(), partial.data(), tw.data(), img_max, otf,
+                                               dot_lanes.data(), B, nchunks}, smem.data(), states.data());
     });
     std::vector<float2> rsmem(ReduceInvSmem<N>::FLOAT2S);
     grid2(3 * T::NC, 1, ReduceInvSmem<N>::THREADS, [&](HostExec& ex) {
         cols_reduce_inv_body<N>(ex, ColsReduceInvParams{partial.data(), stp.data(), tw.data(), used_chunks,
-                                                        1.0f / (static_cast<float>(N) * N)}, rsmem.data());
+                                                        1.0f / (static_cast<float>(N) * N), dot_lanes.data(), img_max,
+                                                        tie_count, coef.data(), B}, rsmem.data());
     });
     grid2(tiles, 3, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
         rows_c2r_body<N>(ex, RowsC2RParams{stp.data(), grad_psf, tw.data(), nullptr, 1.0f}, smem.data());
     });
+    {
+        const int per_ch = N * N / EW_THREADS < 592 ? N * N / EW_THREADS : 592;   // N <= 256: one output element per thread
+        std::vector<float> s_coef(TIE_PASS * MAX_TIES);
+        std::vector<int> s_meta(3 * TIE_PASS * MAX_TIES), s_cnt(TIE_PASS + 1);
+        grid2(per_ch, 3, EW_THREADS, [&](HostExec& ex) {
+            tie_term_body(ex, TieTermParams{grad_psf, img, tie_count, tie_pos, coef.data(), B, N}, per_ch, s_coef.data(),
+                          s_meta.data(), s_cnt.data());
+        });
+    }
     if (grad_img != nullptr) {
-        const int cchunk = conv_chunk(N, B);
+        const int cchunks = conv_chunks(N, B);
         std::vector<ConvState<N>> cst(ColsSmem<N>::THREADS);
-        grid2(colgroups, (B + cchunk - 1) / cchunk, ColsSmem<N>::THREADS, [&](HostExec& ex) {
-            cols_conv_body<N>(ex, ColsConvParams{stg.data(), stg.data(), otf, tw.data(), img_max, B, cchunk, 1, 1.0f}, smem.data(),
+        grid2(colgroups, cchunks, ColsSmem<N>::THREADS, [&](HostExec& ex) {
+            cols_conv_body<N>(ex, ColsConvParams{stg.data(), stg.data(), otf, tw.data(), img_max, B, cchunks, 1, 1.0f}, smem.data(),
                               cst.data());
         });
         grid2(tiles, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
@@ -184,7 +193,7 @@ int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const float*
 }
 
 template <int N>
-int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, const float2* A, const float2* Ht,
+int psf_bwd_impl(const float* gpsf, const float* g_rad, const float* g_cen, const float* h, const float2* A, const float2* Ht,
                  const float* rho, const float* kappa, const float* psf, const float2* field, float* stats,
                  float* grad_h) {
     using T = Tile<N>;
@@ -193,7 +202,7 @@ int psf_bwd_impl(const float* gpsf, const float* gscal, const float* h, const fl
     std::vector<float2> smem(CRowsSmem<N>::FLOAT2S > CColsSmem<N>::FLOAT2S ? CRowsSmem<N>::FLOAT2S : CColsSmem<N>::FLOAT2S);
     std::vector<float> red(3 * EW_THREADS + 2);
     grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) {
-        psf_grad_prepare_body(ex, PsfGradPrepParams{gpsf, gscal, psf, rho, stats, ws.gtot.data(), ws.part_ew.data(), N},
+        psf_grad_prepare_body(ex, PsfGradPrepParams{gpsf, g_rad, g_cen, psf, rho, stats, ws.gtot.data(), ws.part_ew.data(), N},
                               EW_GRID, red.data());
     });
     GradFieldLoad load{field, ws.gtot.data(), stats, ws.part_ew.data(), nullptr, EW_GRID, N};
@@ -275,10 +284,10 @@ int emu_psf_fwd(int N, const float* h, const float* A, const float* Ht, const fl
                                      kappa, psf, reinterpret_cast<float2*>(field), stats)));
 }
 
-int emu_psf_bwd(int N, const float* gpsf, const float* gscal, const float* h, const float* A, const float* Ht,
+int emu_psf_bwd(int N, const float* gpsf, const float* g_rad, const float* g_cen, const float* h, const float* A, const float* Ht,
                 const float* rho, const float* kappa, const float* psf, const float* field, float* stats,
                 float* grad_h) {
-    DISPATCH_N(N, (psf_bwd_impl<NN_>(gpsf, gscal, h, reinterpret_cast<const float2*>(A),
+    DISPATCH_N(N, (psf_bwd_impl<NN_>(gpsf, g_rad, g_cen, h, reinterpret_cast<const float2*>(A),
                                      reinterpret_cast<const float2*>(Ht), rho, kappa, psf,
                                      reinterpret_cast<const float2*>(field), stats, grad_h)));
 }

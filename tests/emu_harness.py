@@ -67,7 +67,9 @@ def psf_bwd(gpsf, gscal, h, tables, psf, field, stats):
     rho = tables.rho.float().contiguous()
     kappa = (ctypes.c_float * 3)(*tables.kappa)
     gh = torch.empty(N, N)
-    rc = lib().emu_psf_bwd(N, _p(gpsf), _p(gscal), _p(h.contiguous()), _p(A), _p(Ht), _p(rho), kappa, _p(psf),
+    g_rad = gscal[0:1] if gscal is not None else None
+    g_cen = gscal[1:2] if gscal is not None else None
+    rc = lib().emu_psf_bwd(N, _p(gpsf), _p(g_rad), _p(g_cen), _p(h.contiguous()), _p(A), _p(Ht), _p(rho), kappa, _p(psf),
                            _p(field), _p(stats), _p(gh))
     assert rc == 0
     return gh

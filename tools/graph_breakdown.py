@@ -56,7 +56,7 @@ def main():
                                           p(psf), p(otf), p(spectrum), p(gpsf), None, p(ws), ws.numel(), B, N, st()))
 
     def psf_bwd(i):
-        _lib.check(lib.b200cam_psf_bwd(p(gpsf), p(gscal), p(h), p(plan.A), p(plan.Ht), p(plan.rho), plan.kappa, p(psf),
+        _lib.check(lib.b200cam_psf_bwd(p(gpsf), p(gscal[0:1]), p(gscal[1:2]), p(h), p(plan.A), p(plan.Ht), p(plan.rho), plan.kappa, p(psf),
                                        p(field), p(stats), p(gh), p(pws), pws.numel(), N, st()))
 
     def step(i):
