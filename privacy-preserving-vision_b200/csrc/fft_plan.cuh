@@ -46,6 +46,24 @@ struct Plan {
             E[k1 * PITCH_AB + a] = t;
         }
     }
+    // The same two steps with the lane's twiddles w[k] = tw[lane*k] held in REGISTERS (persistent kernels load them once:
+    // the 15 table look-ups per step are a quarter of the shared/L1 pipe traffic of a column pass).  Needs R1 == R2.
+    static constexpr bool REG_TW = (R1 == R2) && (R1 <= 16);
+    static B200_HD void load_tw(float2 (&w)[R1], const float2* tw, int lane) {
+#pragma unroll
+        for (int k = 0; k < R1; ++k) w[k] = ld_ro(tw + lane * k);
+    }
+    static B200_HD void stepA(float2 (&v)[R1], int a, float2* E, const float2 (&w)[R1]) {
+        RegFFT<R1, -1>::run(v);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) E[k1 * PITCH_AB + a] = k1 > 0 ? cmul(v[k1], w[k1]) : v[k1];
+    }
+    static B200_HD void stepC(float2 (&v)[R2], int b, float2* E, const float2 (&w)[R1]) {
+        static_assert(R1 == R2, "register twiddles need R1 == R2");
+        RegFFT<R2, +1>::run(v);
+#pragma unroll
+        for (int m2 = 0; m2 < R2; ++m2) E[m2 * PITCH_CD + b] = m2 > 0 ? cmulc(v[m2], w[m2]) : v[m2];
+    }
     // E -> Q.  lane b < R1, result v[i] = X[b + R1*i]
     static B200_HD void stepB(float2 (&v)[R2], int b, const float2* E) {
 #pragma unroll

@@ -140,38 +140,19 @@ struct ColsSmem {
     using P = Plan<N>;
     static constexpr int COLS = Tile<N>::COLS;
     static constexpr int THREADS = COLS * P::LANES;
-    // N <= 256: the next image's columns are copied global -> shared ASYNCHRONOUSLY (cp.async) while the current image
-    // is transformed, one staging line of N float2 per column and operand.  The lanes of one column FFT are the only
-    // readers and writers of their line, so warp-level syncs are enough.  Larger N: direct loads (the staging
-    // lines would cost the occupancy they are meant to replace).
-    static constexpr bool STAGED = N <= 256;
-    static constexpr int STAGE_OFF = 2 * COLS * P::E_SIZE;                          // float2 units
-    static constexpr int FLOAT2S_CONV = STAGE_OFF + (STAGED ? COLS * N : 0);        // one operand
-    static constexpr int FLOAT2S_ACCUM = STAGE_OFF + (STAGED ? 2 * COLS * N : 0);   // two operands
-    static constexpr int FLOAT2S = FLOAT2S_ACCUM;
-    static constexpr int BYTES_CONV = FLOAT2S_CONV * 8;
+    static constexpr int FLOAT2S = 2 * COLS * P::E_SIZE;
     static constexpr int BYTES = FLOAT2S * 8;
 };
-
-// lane `a` of a column's LANES lanes issues its share of the async copy of one spectral column (N float2)
-template <int N>
-B200_HD void stage_column(float2* line, const float2* src, int a) {
-    constexpr int CHUNKS = N / 2;                        // 16-byte chunks
-#pragma unroll
-    for (int k = 0; k < CHUNKS / Plan<N>::LANES; ++k) {
-        const int ch = a + Plan<N>::LANES * k;
-        async_copy16(line + 2 * ch, src + 2 * ch);
-    }
-}
 
 template <int N>
 struct ConvState {
     float2 k[Plan<N>::R2];   // this lane's OTF values, loaded once per CTA
-    float2 v[Plan<N>::R2 > Plan<N>::R1 ? Plan<N>::R2 : Plan<N>::R1];
 };
 
-// grid (ceil(3*NC/COLS), ceil(B/chunk)), block COLS*LANES.  A CTA owns COLS columns of one channel
-// (flat index cu over [3][NC]) and walks its chunk of images, so the OTF is read once per CTA.
+// grid (ceil(3*NC/COLS), nchunks), block COLS*LANES.  A CTA owns COLS columns of one channel
+// (flat index cu over [3][NC]) and walks its chunk of images, so the OTF - and, for R1 == R2, the lane's FFT
+// twiddles - are read once per CTA and stay in registers.  (These passes are bound by the shared/L1 data pipe:
+// every look-up that does not go through it counts.)
 template <int N, class Exec>
 B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem, ConvState<N>* st) {
     using P = Plan<N>;
@@ -179,54 +160,41 @@ B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem, Con
     using S = ColsSmem<N>;
     float2* E1 = smem;
     float2* E2 = smem + S::COLS * P::E_SIZE;
-    float2* stage = smem + S::STAGE_OFF;
     constexpr int TOTAL = 3 * T::NC;
+    constexpr bool RT = P::REG_TW;
     const int cu0 = ex.bx() * S::COLS;
     const int b0 = static_cast<int>(static_cast<long long>(p.B) * ex.by() / p.nchunks);
     const int b1 = static_cast<int>(static_cast<long long>(p.B) * (ex.by() + 1) / p.nchunks);
-    auto column = [&](int img, int cu) {
-        return p.in + (static_cast<size_t>(img * 3 + cu / T::NC) * T::NC + cu % T::NC) * N;   // may alias out: plain loads
-    };
+    float2 wreg[RT ? P::R1 : 1];                 // device: loaded once; host emulator: reloaded inside every phase
 
     ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, b = tid % P::LANES;
         const int cu = cu0 + jc;
-        if (cu < TOTAL) {
-            if (b < P::R1) {
-                ConvState<N>& s = st[ex.slot(tid)];
-                const float2* k = p.otf + static_cast<size_t>(cu) * N;
+        if (cu < TOTAL && b < P::R1) {
+            ConvState<N>& s = st[ex.slot(tid)];
+            const float2* k = p.otf + static_cast<size_t>(cu) * N;
 #pragma unroll
-                for (int i = 0; i < P::R2; ++i) {
-                    const float2 kk = cscale(ld_ro(k + b + P::R1 * i), p.otf_scale);
-                    s.k[i] = p.conj_otf ? cconj(kk) : kk;
-                }
+            for (int i = 0; i < P::R2; ++i) {
+                const float2 kk = cscale(ld_ro(k + b + P::R1 * i), p.otf_scale);
+                s.k[i] = p.conj_otf ? cconj(kk) : kk;
             }
-            if (S::STAGED && b0 < b1) stage_column<N>(stage + jc * N, column(b0, cu), b);
         }
-        if (S::STAGED) async_wait_all();
+        if constexpr (RT && !Exec::IS_HOST) P::load_tw(wreg, p.tw, b);
     });
     for (int img = b0; img < b1; ++img) {
         ex.warp_phase([&](int tid) {
             const int jc = tid / P::LANES, a = tid % P::LANES;
             const int cu = cu0 + jc;
             if (cu < TOTAL && a < P::R2) {
-                ConvState<N>& s = st[ex.slot(tid)];
-                const float2* src = S::STAGED ? stage + jc * N : column(img, cu);
+                const int c = cu / T::NC, u = cu % T::NC;
+                const float2* src = p.in + (static_cast<size_t>(img * 3 + c) * T::NC + u) * N;   // may alias out: plain loads
+                float2 v[P::R1];
 #pragma unroll
-                for (int i = 0; i < P::R1; ++i) s.v[i] = src[P::R2 * i + a];
-            }
-        });
-        ex.warp_phase([&](int tid) {
-            const int jc = tid / P::LANES, a = tid % P::LANES;
-            const int cu = cu0 + jc;
-            if (cu < TOTAL) {
-                // every lane holds its part of the staged column: refill the line with the next image's column
-                if (S::STAGED && img + 1 < b1) stage_column<N>(stage + jc * N, column(img + 1, cu), a);
-                if (a < P::R2) {
-                    float2 v[P::R1];
-                    const ConvState<N>& s = st[ex.slot(tid)];
-#pragma unroll
-                    for (int i = 0; i < P::R1; ++i) v[i] = s.v[i];
+                for (int i = 0; i < P::R1; ++i) v[i] = src[P::R2 * i + a];
+                if constexpr (RT) {
+                    if constexpr (Exec::IS_HOST) P::load_tw(wreg, p.tw, a);
+                    P::stepA(v, a, E1 + jc * P::E_SIZE, wreg);
+                } else {
                     P::stepA(v, a, E1 + jc * P::E_SIZE, p.tw);
                 }
             }
@@ -244,7 +212,12 @@ B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem, Con
                     v[i] = cmul(v[i], s.k[i]);
                     if (p.img_scale != nullptr) v[i] = cscale(v[i], sc);
                 }
-                P::stepC(v, b, E2 + jc * P::E_SIZE, p.tw);
+                if constexpr (RT) {
+                    if constexpr (Exec::IS_HOST) P::load_tw(wreg, p.tw, b);
+                    P::stepC(v, b, E2 + jc * P::E_SIZE, wreg);
+                } else {
+                    P::stepC(v, b, E2 + jc * P::E_SIZE, p.tw);
+                }
             }
         });
         ex.warp_phase([&](int tid) {
@@ -258,7 +231,6 @@ B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem, Con
 #pragma unroll
                 for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = v[i];
             }
-            if (S::STAGED) async_wait_all();
         });
     }
 }
@@ -520,49 +492,37 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
     const int b0 = static_cast<int>(static_cast<long long>(p.B) * ex.by() / p.nchunks);
     const int b1 = static_cast<int>(static_cast<long long>(p.B) * (ex.by() + 1) / p.nchunks);
     constexpr int TOTAL = 3 * T::NC;
+    constexpr bool RT = P::REG_TW;
+    float2 wreg[RT ? P::R1 : 1];                 // the lane's twiddles, in registers for the whole chunk (see cols_conv)
 
-    float2* stage = smem + S::STAGE_OFF;                 // [2 operands][COLS][N]
-    auto column = [&](const float2* base, int b, int cu) {
-        return base + (static_cast<size_t>(b * 3 + cu / T::NC) * T::NC + cu % T::NC) * N;
-    };
     ex.warp_phase([&](int tid) {
         AccumState<N>& s = st[ex.slot(tid)];
 #pragma unroll
         for (int i = 0; i < P::R2; ++i) s.acc[i] = make_float2(0.f, 0.f);
-        const int jc = tid / P::LANES, a = tid % P::LANES;
-        const int cu = cu0 + jc;
-        if (S::STAGED && cu < TOTAL && b0 < b1) {
-            stage_column<N>(stage + jc * N, column(p.stx, b0, cu), a);
-            stage_column<N>(stage + (S::COLS + jc) * N, column(p.stg, b0, cu), a);
-        }
-        if (S::STAGED) async_wait_all();
+        if constexpr (RT && !Exec::IS_HOST) P::load_tw(wreg, p.tw, tid % P::LANES);
     });
     for (int b = b0; b < b1; ++b) {
         ex.warp_phase([&](int tid) {
             const int jc = tid / P::LANES, a = tid % P::LANES;
             const int cu = cu0 + jc;
             if (cu < TOTAL && a < P::R2) {
-                const float2* sx = S::STAGED ? stage + jc * N : column(p.stx, b, cu);
-                const float2* sg = S::STAGED ? stage + (S::COLS + jc) * N : column(p.stg, b, cu);
-                float2 v[P::R1];
+                const int c = cu / T::NC, u = cu % T::NC;
+                const size_t off = (static_cast<size_t>(b * 3 + c) * T::NC + u) * N;
+                float2 vx[P::R1], vg[P::R1];
 #pragma unroll
-                for (int i = 0; i < P::R1; ++i) v[i] = S::STAGED ? sx[P::R2 * i + a] : ld_ro(sx + P::R2 * i + a);
-                P::stepA(v, a, Ex + jc * P::E_SIZE, p.tw);
+                for (int i = 0; i < P::R1; ++i) vx[i] = ld_ro(p.stx + off + P::R2 * i + a);
 #pragma unroll
-                for (int i = 0; i < P::R1; ++i) v[i] = S::STAGED ? sg[P::R2 * i + a] : ld_ro(sg + P::R2 * i + a);
-                P::stepA(v, a, Eg + jc * P::E_SIZE, p.tw);
+                for (int i = 0; i < P::R1; ++i) vg[i] = ld_ro(p.stg + off + P::R2 * i + a);
+                if constexpr (RT) {
+                    if constexpr (Exec::IS_HOST) P::load_tw(wreg, p.tw, a);
+                    P::stepA(vx, a, Ex + jc * P::E_SIZE, wreg);
+                    P::stepA(vg, a, Eg + jc * P::E_SIZE, wreg);
+                } else {
+                    P::stepA(vx, a, Ex + jc * P::E_SIZE, p.tw);
+                    P::stepA(vg, a, Eg + jc * P::E_SIZE, p.tw);
+                }
             }
         });
-        if (S::STAGED && b + 1 < b1) {
-            ex.warp_phase([&](int tid) {               // both staged columns are in registers / E: refill the lines
-                const int jc = tid / P::LANES, a = tid % P::LANES;
-                const int cu = cu0 + jc;
-                if (cu < TOTAL) {
-                    stage_column<N>(stage + jc * N, column(p.stx, b + 1, cu), a);
-                    stage_column<N>(stage + (S::COLS + jc) * N, column(p.stg, b + 1, cu), a);
-                }
-            });
-        }
         ex.warp_phase([&](int tid) {
             const int jc = tid / P::LANES, bb = tid % P::LANES;
             const int cu = cu0 + jc;
@@ -591,7 +551,6 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
                     p.dot_lanes[(static_cast<size_t>(b) * TOTAL + cu) * P::R1 + bb] = wt * (d2.x + d2.y);
                 }
             }
-            if (S::STAGED) async_wait_all();
         });
     }
     ex.warp_phase([&](int tid) {
