@@ -786,25 +786,37 @@ B200_HD void tie_term_img_body(Exec& ex, const TieTermImgParams& p, int grid_x) 
 // =============================================================================================
 
 // loaders / epilogues of the complex row passes
+// Loaders are split in two stages - fetch() only issues the global loads, make() does the arithmetic - so that a
+// row's 16/32 elements are all in flight before the first one is used (the PSF chain is a latency chain).
 struct PupilLoad {     // V = A * exp(i*kappa_l*h)   (Optics.py:89-100)
     const float2* A;   // [3][N][N] constant pupil table (aperture, lens, defocus and pre-phase)
     const float* h;    // [N][N]
     float kappa[3];
     int N;
+    struct Raw { float2 a; float h; };
+    // selects instead of kappa[l]: a dynamically indexed kernel-parameter array is copied to local memory
+    B200_HD float kap(int l) const { return l == 0 ? kappa[0] : (l == 1 ? kappa[1] : kappa[2]); }
     B200_HD void bind(float*) {}
     template <class Exec>
     B200_HD void prologue(Exec&, float*) const {}
-    B200_HD float2 operator()(int l, int y, int x) const {
+    B200_HD Raw fetch(int l, int y, int x) const {
         const size_t i = static_cast<size_t>(y) * N + x;
-        const float phi = kappa[l] * ld_ro(h + i);
+        return Raw{ld_ro(A + static_cast<size_t>(l) * N * N + i), ld_ro(h + i)};
+    }
+    B200_HD float2 make(int l, const Raw& r) const {
         float s, c;
 #if defined(__CUDA_ARCH__)
-        sincosf(phi, &s, &c);
+        // exp(i phi) through sincospi: exact range reduction, straight-line code (sincosf carries a Payne-Hanek slow
+        // path with a stack frame, which keeps the 16 evaluations of a row from overlapping).  phi/pi costs one
+        // rounding of the argument: |error| <= 6e-8 |phi| rad.
+        sincospif((kap(l) * r.h) * 0.31830988618379067154f, &s, &c);
 #else
+        const float phi = kap(l) * r.h;
         s = sinf(phi); c = cosf(phi);
 #endif
-        return cmul(ld_ro(A + static_cast<size_t>(l) * N * N + i), make_float2(c, s));
+        return cmul(r.a, make_float2(c, s));
     }
+    B200_HD float2 operator()(int l, int y, int x) const { return make(l, fetch(l, y, x)); }
 };
 
 struct GradFieldLoad {  // GU = 2 * (gtot - dot)/S * U      (adjoint of |U|^2 / sum, Optics.py:109-110)
@@ -812,9 +824,10 @@ struct GradFieldLoad {  // GU = 2 * (gtot - dot)/S * U      (adjoint of |U|^2 / 
     const float* gtot;     // [3][N][N]
     const float* scal;     // device scalars: [0]=S
     const float* partial;  // [npartial] partial sums of gtot*psf written by psf_grad_prepare
-    float* dot_smem;       // one float of shared memory: dot = sum(partial), reduced by every CTA in the same order
+    float* dot_smem;       // two floats of shared memory: dot = sum(partial) (reduced by every CTA in the same order), 2/S
     int npartial;
     int N;
+    struct Raw { float2 u; float g; };
     B200_HD void bind(float* scratch) { dot_smem = scratch; }
     template <class Exec>
     B200_HD void prologue(Exec& ex, float* red) const {
@@ -828,15 +841,16 @@ struct GradFieldLoad {  // GU = 2 * (gtot - dot)/S * U      (adjoint of |U|^2 / 
             if (tid == 0) {
                 float s = 0.f;
                 for (int t = 0; t < nt; ++t) s += red[t];
-                *dot_smem = s;
+                dot_smem[0] = s;
+                dot_smem[1] = 2.0f / ld_ro(scal + 0);
             }
         });
     }
-    B200_HD float2 operator()(int l, int y, int x) const {
+    B200_HD Raw fetch(int l, int y, int x) const {
         const size_t i = (static_cast<size_t>(l) * N + y) * N + x;
-        const float gi = 2.0f * (ld_ro(gtot + i) - *dot_smem) / ld_ro(scal + 0);
-        return cscale(ld_ro(U + i), gi);
+        return Raw{ld_ro(U + i), ld_ro(gtot + i)};
     }
+    B200_HD float2 make(int, const Raw& r) const { return cscale(r.u, (r.g - dot_smem[0]) * dot_smem[1]); }
 };
 
 // P1  crows_fwd : complex rows -> transposed full spectrum.  grid (N/CROWS, 3), block CROWS*LANES
@@ -871,9 +885,12 @@ B200_HD void crows_fwd_body(Exec& ex, const CRowsFwdParams& p, Load load, float2
     ex.phase([&](int tid) {
         const int j = tid / P::LANES, a = tid % P::LANES;
         if (a < P::R2) {
+            typename Load::Raw raw[P::R1];
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) raw[i] = load.fetch(l, y0 + j, P::R2 * i + a);
             float2 v[P::R1];
 #pragma unroll
-            for (int i = 0; i < P::R1; ++i) v[i] = load(l, y0 + j, P::R2 * i + a);
+            for (int i = 0; i < P::R1; ++i) v[i] = load.make(l, raw[i]);
             P::stepA(v, a, E + j * P::E_SIZE, p.tw);
         }
     });
@@ -1038,7 +1055,7 @@ struct HeightGradEpilogue {
     B200_HD float operator()(int l, int y, int x, float2 gv) const {
         const float2 v = pupil(l, y, x);
         const float2 t = cmulc(gv, v);
-        gh3[(static_cast<size_t>(l) * N + y) * N + x] = pupil.kappa[l] * t.y;
+        gh3[(static_cast<size_t>(l) * N + y) * N + x] = pupil.kap(l) * t.y;
         return 0.f;
     }
     B200_HD void finish(int, int, int, float) const {}
@@ -1137,13 +1154,16 @@ B200_HD void crows_inv_hgrad_body(Exec& ex, const CRowsInvParams& p, const Pupil
         const int j = t / P::LANES, a = t % P::LANES;
         const float2* E = smem + l * H::PART + S::E_OFF;
         if (a < P::R2) {
+            PupilLoad::Raw raw[P::R1];               // issue the pupil loads before the transform needs its registers
+#pragma unroll
+            for (int i = 0; i < P::R1; ++i) raw[i] = pupil.fetch(l, y0 + j, P::R2 * i + a);
             float2 v[P::R1];
             P::stepD(v, a, E + j * P::E_SIZE);
 #pragma unroll
             for (int i = 0; i < P::R1; ++i) {
                 const int x = P::R2 * i + a;
-                const float2 pv = pupil(l, y0 + j, x);
-                const float g = pupil.kappa[l] * cmulc(v[i], pv).y;
+                const float2 pv = pupil.make(l, raw[i]);
+                const float g = pupil.kap(l) * cmulc(v[i], pv).y;
                 if (l > 0) sum[((l - 1) * T::CROWS + j) * N + x] = g;
                 else v[i].x = g;
             }
