@@ -920,7 +920,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
         RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
     LAUNCH_CHECK();
     {   // arg-max term of the amax backward (spatial form), ties of channel c handled by the CTAs of row c
-        const int per_ch = N * N / EW_THREADS < 592 ? N * N / EW_THREADS : 592;   // N <= 256: one output element per thread
+        const int per_ch = N * N / 2 / EW_THREADS < 592 ? N * N / 2 / EW_THREADS : 592;   // two adjacent pixels per thread
         k_tie_term<<<dim3(per_ch, 3), EW_THREADS, 0, s>>>(TieTermParams{grad_psf, img, tie_count, tie_pos, ws.coef, B, N});
         LAUNCH_CHECK();
     }

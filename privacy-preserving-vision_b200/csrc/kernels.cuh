@@ -315,17 +315,31 @@ B200_HD void rows_c2r_body(Exec& ex, const RowsC2RParams& p, float2* smem) {
     RowState<N> st[Exec::IS_HOST ? S::THREADS : 1];
 
     ex.phase([&](int tid) {
-        for (int w = tid; w < T::NP * T::NC; w += S::THREADS) {
-            const int u = w / T::NP, j = w % T::NP;
-            const float4 q = ld_ro(reinterpret_cast<const float4*>(
-                p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0 + 2 * j));
-            // Z = X_even + i X_odd ; Z[N-u] = conj(X_even[u]) + i conj(X_odd[u])
-            float2* F = smem + j * S::PA;
-            if (u == 0 || u == N / 2) {
-                F[u] = make_float2(q.x, q.z);   // irfft ignores Im at DC/Nyquist
-            } else {
-                F[u] = make_float2(q.x - q.w, q.y + q.z);
-                F[N - u] = make_float2(q.x + q.w, q.z - q.y);
+        // all of the thread's 16-byte loads are issued before the first one is consumed (latency, not bandwidth, bounds
+        // this gather of 128-byte segments)
+        constexpr int ITEMS = (T::NP * T::NC + S::THREADS - 1) / S::THREADS;
+        float4 q[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int w = tid + k * S::THREADS;
+            if (w < T::NP * T::NC) {
+                const int u = w / T::NP, j = w % T::NP;
+                q[k] = ld_ro(reinterpret_cast<const float4*>(p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0 + 2 * j));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int w = tid + k * S::THREADS;
+            if (w < T::NP * T::NC) {
+                const int u = w / T::NP, j = w % T::NP;
+                // Z = X_even + i X_odd ; Z[N-u] = conj(X_even[u]) + i conj(X_odd[u])
+                float2* F = smem + j * S::PA;
+                if (u == 0 || u == N / 2) {
+                    F[u] = make_float2(q[k].x, q[k].z);   // irfft ignores Im at DC/Nyquist
+                } else {
+                    F[u] = make_float2(q[k].x - q[k].w, q[k].y + q[k].z);
+                    F[N - u] = make_float2(q[k].x + q[k].w, q[k].z - q[k].y);
+                }
             }
         }
     });
@@ -720,26 +734,35 @@ B200_HD void tie_term_body(Exec& ex, const TieTermParams& p, int grid_x, float* 
         ex.phase([&](int tid) {
             const int k = s_cnt[TIE_PASS];
             if (k > 0) {
+                // a thread owns two adjacent pixels; 16 ties x 2 pixels = 32 gathers in flight (they miss L2: the images
+                // were last read a whole step ago).  Tail entries are clamped to the last valid one and skipped in the
+                // sum: same additions, fixed order.
                 const int stride = grid_x * ex.nthreads();
-                for (int idx = ex.bx() * ex.nthreads() + tid; idx < NN; idx += stride) {
-                    const int py = idx / N, px = idx % N;
-                    float acc = 0.f;
-                    // the gathers are DRAM-latency bound: always 16 in flight per thread (tail entries are clamped to
-                    // the last valid one and weighted 0, which adds exact zeros: same sum, fixed order)
+                for (int idx = ex.bx() * ex.nthreads() + tid; idx < NN / 2; idx += stride) {
+                    const int py = idx / (N / 2), px = 2 * (idx % (N / 2));
+                    float acc0 = 0.f, acc1 = 0.f;
                     for (int e = 0; e < k; e += 16) {
-                        float v[16];
+                        float v0[16], v1[16];
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
                             const int ee = e + q < k ? e + q : k - 1;
                             const int sy = (s_meta[3 * ee + 1] - py + N / 2 + N) & (N - 1);
                             const int sx = (s_meta[3 * ee + 2] - px + N / 2 + N) & (N - 1);
-                            v[q] = ld_ro(p.x + (static_cast<size_t>(s_meta[3 * ee]) * 3 + c) * NN + sy * N + sx);
+                            const float* row = p.x + (static_cast<size_t>(s_meta[3 * ee]) * 3 + c) * NN + sy * N;
+                            v0[q] = ld_ro(row + sx);
+                            v1[q] = ld_ro(row + ((sx - 1) & (N - 1)));
                         }
 #pragma unroll
-                        for (int q = 0; q < 16; ++q)
-                            if (e + q < k) acc += s_coef[e + q] * v[q];
+                        for (int q = 0; q < 16; ++q) {
+                            if (e + q < k) {
+                                acc0 += s_coef[e + q] * v0[q];
+                                acc1 += s_coef[e + q] * v1[q];
+                            }
+                        }
                     }
-                    p.gpsf[c * NN + idx] -= acc;
+                    float2* dst = reinterpret_cast<float2*>(p.gpsf + c * NN + py * N + px);
+                    const float2 old = *dst;
+                    *dst = make_float2(old.x - acc0, old.y - acc1);
                 }
             }
         });
@@ -976,6 +999,9 @@ B200_HD void ccols_mix_body(Exec& ex, const CColsMixParams& p, float2* smem) {
         if (u < N && b < P::R1) {
             const float2 wa = (m == 0) ? make_float2(1.f, 0.f) : (m == 1 ? w3 : cconj(w3));   // w3^m
             const float2 wb = (m == 0) ? make_float2(1.f, 0.f) : (m == 1 ? cconj(w3) : w3);   // w3^(2m)
+            float2 h[P::R2];                        // the transfer function is not in L2 any more: all loads first
+#pragma unroll
+            for (int i = 0; i < P::R2; ++i) h[i] = ld_ro(p.H + (static_cast<size_t>(m) * N + u) * N + b + P::R1 * i);
 #pragma unroll
             for (int i = 0; i < P::R2; ++i) {
                 const int k = b + P::R1 * i;
@@ -983,8 +1009,7 @@ B200_HD void ccols_mix_body(Exec& ex, const CColsMixParams& p, float2* smem) {
                 const float2 a1 = G1[(jc * 3 + 1) * S::GP + k];
                 const float2 a2 = G1[(jc * 3 + 2) * S::GP + k];
                 const float2 s = cadd(a0, cadd(cmul(a1, wa), cmul(a2, wb)));
-                const float2 h = ld_ro(p.H + (static_cast<size_t>(m) * N + u) * N + k);
-                G2[f * S::GP + k] = p.conj_h ? cmulc(s, h) : cmul(s, h);
+                G2[f * S::GP + k] = p.conj_h ? cmulc(s, h[i]) : cmul(s, h[i]);
             }
         }
     });
@@ -1072,9 +1097,17 @@ B200_HD void crows_inv_body(Exec& ex, const CRowsInvParams& p, const Epi& epi, f
     float2* F = smem + S::F_OFF;
     float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
     ex.phase([&](int tid) {
-        for (int w = tid; w < T::CROWS * N; w += S::THREADS) {
-            const int u = w / T::CROWS, j = w % T::CROWS;
-            F[j * T::FP_CROW + u] = ld_ro(p.st + (static_cast<size_t>(l) * N + u) * N + y0 + j);
+        constexpr int ITEMS = T::CROWS * N / S::THREADS;         // loads first, stores after (latency chain)
+        float2 q[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int w = tid + k * S::THREADS;
+            q[k] = ld_ro(p.st + (static_cast<size_t>(l) * N + w / T::CROWS) * N + y0 + w % T::CROWS);
+        }
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int w = tid + k * S::THREADS;
+            F[(w % T::CROWS) * T::FP_CROW + w / T::CROWS] = q[k];
         }
     });
     ex.phase([&](int tid) {
@@ -1132,9 +1165,17 @@ B200_HD void crows_inv_hgrad_body(Exec& ex, const CRowsInvParams& p, const Pupil
     ex.phase([&](int tid) {
         const int l = tid / S::THREADS, t = tid % S::THREADS;
         float2* F = smem + l * H::PART + S::F_OFF;
-        for (int w = t; w < T::CROWS * N; w += S::THREADS) {
-            const int u = w / T::CROWS, j = w % T::CROWS;
-            F[j * T::FP_CROW + u] = ld_ro(p.st + (static_cast<size_t>(l) * N + u) * N + y0 + j);
+        constexpr int ITEMS = T::CROWS * N / S::THREADS;         // loads first, stores after (latency chain)
+        float2 q[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int w = t + k * S::THREADS;
+            q[k] = ld_ro(p.st + (static_cast<size_t>(l) * N + w / T::CROWS) * N + y0 + w % T::CROWS);
+        }
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int w = t + k * S::THREADS;
+            F[(w % T::CROWS) * T::FP_CROW + w / T::CROWS] = q[k];
         }
     });
     ex.phase([&](int tid) {

@@ -135,7 +135,7 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
         rows_c2r_body<N>(ex, RowsC2RParams{stp.data(), grad_psf, tw.data(), nullptr, 1.0f}, smem.data());
     });
     {
-        const int per_ch = N * N / EW_THREADS < 592 ? N * N / EW_THREADS : 592;   // N <= 256: one output element per thread
+        const int per_ch = N * N / 2 / EW_THREADS < 592 ? N * N / 2 / EW_THREADS : 592;   // two adjacent pixels per thread
         std::vector<float> s_coef(TIE_PASS * MAX_TIES);
         std::vector<int> s_meta(3 * TIE_PASS * MAX_TIES), s_cnt(TIE_PASS + 1);
         grid2(per_ch, 3, EW_THREADS, [&](HostExec& ex) {
