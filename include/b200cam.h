@@ -64,6 +64,20 @@ int b200cam_psf_fwd(const float* h, const float* A, const float* Ht, const float
                     const float* kappa, float* psf, float* field, float* stats,
                     void* workspace, size_t workspace_bytes, int N, void* stream);
 
+/* The same PSF synthesis in two calls, so that a caller can put work between them: after b200cam_psf_field the
+ * workspace holds |U|^2 and the partial sums of it, which is all the OTF needs (b200cam_psf_otf_early, on the same
+ * stream) - the sensor pipeline can then start while b200cam_psf_finish still writes psf and the two regularisers
+ * (Optics.py:110,113,124-125).  b200cam_psf_fwd == b200cam_psf_field + b200cam_psf_finish. */
+/* has_dependent != 0: `dependent_stream` (a cudaStream_t, 0 = the legacy default stream) is made to wait until the
+ * FIRST kernel of the chain has finished, so that a large batch kernel enqueued there afterwards does not occupy every SM
+ * before the chain's next (higher-priority) kernel is resident. */
+int b200cam_psf_field(const float* h, const float* A, const float* Ht, const float* kappa, float* field,
+                      void* workspace, size_t workspace_bytes, int N, void* stream, void* dependent_stream,
+                      int has_dependent);
+int b200cam_psf_otf_early(float* otf, void* workspace, size_t workspace_bytes, int N, void* stream);
+int b200cam_psf_finish(const float* rho, float* psf, float* stats, void* workspace, size_t workspace_bytes, int N,
+                       void* stream);
+
 /* PSF synthesis, backward (autograd through Optics.py:89-125 in closed form).
  *   grad_psf     [3][N][N] or NULL   dL/dpsf
  *   grad_rad     [1] or NULL         dL/dloss_rad        (device scalars: the two regularisers are separate autograd

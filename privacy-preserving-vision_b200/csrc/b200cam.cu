@@ -390,10 +390,16 @@ inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 struct DeviceState {
     float2* tw[11] = {nullptr}; int sms = 0; int coop_grid[11] = {0}; unsigned* bar = nullptr;
     int conv_slots[11] = {0}, accum_slots[11] = {0};     // resident CTAs of the persistent column kernels
+    cudaEvent_t chain_ev = nullptr;                      // orders a caller stream behind the first PSF-chain kernel
 };
 static DeviceState g_state[MAX_DEV];
 static std::mutex g_mutex;
 
+static cudaEvent_t chain_event() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    return g_state[dev].chain_ev;
+}
 static int sm_count() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 0;
@@ -594,38 +600,66 @@ static std::atomic<unsigned long long> g_launches{0};
 // ------------------------------------------------------------------------------------------
 // launch sequences
 // ------------------------------------------------------------------------------------------
+// first part of the PSF synthesis: pupil -> propagated field U, |U|^2 (workspace) and S = sum |U|^2 (stats[0])
+template <int N>
+static int psf_field_impl(const float* h, const float2* A, const float2* Ht, const float* kappa, float2* field,
+                          void* ws_ptr, cudaStream_t s, cudaStream_t dependent = nullptr, bool has_dependent = false) {
+    using T = Tile<N>;
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    PsfWs ws(ws_ptr, N);
+    PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
+    const dim3 rgrid(N / T::CROWS, 3);
+    k_crows_fwd<N, PupilLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsFwdParams{ws.st, tw}, load);
+    LAUNCH_CHECK();
+    if (has_dependent) {
+        // The caller's big batch kernel (image row pass) is held back until this first small kernel is done: both it and
+        // our next kernel then become ready together and the higher-priority one (ours) takes its SMs first.  Launched
+        // earlier, the batch kernel fills every SM and each kernel of this chain waits a wave (~7 us) for room.
+        cudaEvent_t ev = chain_event();
+        if (ev == nullptr) return B200CAM_E_NOT_INIT;
+        CK(cudaEventRecord(ev, s));
+        CK(cudaStreamWaitEvent(dependent, ev, 0));
+    }
+    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(
+        CColsMixParams{ws.st, Ht, tw, 0, 1.0f / (3.0f * N * N)});
+    LAUNCH_CHECK();
+    k_crows_inv<N, IntensityEpilogue><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(
+        CRowsInvParams{ws.st, tw}, IntensityEpilogue{field, ws.I, ws.part_rows, ws.arrive, N});
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// second part: psf = |U|^2 / S and the two regularisers
+template <int N>
+static int psf_finish_impl(const float* rho, float* psf, float* stats, void* ws_ptr, cudaStream_t s) {
+    PsfWs ws(ws_ptr, N);
+    k_psf_finalise<<<EW_GRID, EW_THREADS, 0, s>>>(PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, 3 * (N / Tile<N>::CROWS), N});
+    LAUNCH_CHECK();
+    return 0;
+}
+
 template <int N>
 static int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const float* rho, const float* kappa,
                         float* psf, float2* field, float* stats, void* ws_ptr, cudaStream_t s) {
     using T = Tile<N>;
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
-    PsfWs ws(ws_ptr, N);
-    PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
-    const int nrow = 3 * (N / T::CROWS);
-    CRowsFwdParams rf{ws.st, tw};
-    CColsMixParams mix{ws.st, Ht, tw, 0, 1.0f / (3.0f * N * N)};
-    CRowsInvParams ri{ws.st, tw};
-    IntensityEpilogue epi{field, ws.I, ws.part_rows, ws.arrive, N};
-    PsfFinaliseParams fin{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, nrow, N};
     if (const int G = coop_grid(N, s)) {
-        PsfFwdArgs args{rf, load, mix, ri, epi, fin, coop_barrier(0)};
+        PsfWs ws(ws_ptr, N);
+        PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
+        PsfFwdArgs args{CRowsFwdParams{ws.st, tw}, load, CColsMixParams{ws.st, Ht, tw, 0, 1.0f / (3.0f * N * N)},
+                        CRowsInvParams{ws.st, tw}, IntensityEpilogue{field, ws.I, ws.part_rows, ws.arrive, N},
+                        PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, 3 * (N / Tile<N>::CROWS), N}, coop_barrier(0)};
         void* kargs[] = {&args};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_psf_fwd_coop<N>), dim3(G), dim3(COOP_THREADS), kargs,
                                        coop_smem_bytes<N>(), s));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
-    const dim3 rgrid(N / T::CROWS, 3);
-    k_crows_fwd<N, PupilLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(rf, load);
-    LAUNCH_CHECK();
-    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(mix);
-    LAUNCH_CHECK();
-    k_crows_inv<N, IntensityEpilogue><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(ri, epi);
-    LAUNCH_CHECK();
-    k_psf_finalise<<<EW_GRID, EW_THREADS, 0, s>>>(fin);
-    LAUNCH_CHECK();
-    return 0;
+    int rc = psf_field_impl<N>(h, A, Ht, kappa, field, ws_ptr, s);
+    if (rc) return rc;
+    return psf_finish_impl<N>(rho, psf, stats, ws_ptr, s);
 }
 
 template <int N>
@@ -666,14 +700,15 @@ static int psf_bwd_impl(const float* gpsf, const float* g_rad, const float* g_ce
 }
 
 template <int N>
-static int otf_impl(const float* psf, float2* otf, const float2* tw, float scale, cudaStream_t s) {
+static int otf_impl(const float* src, float2* otf, const float2* tw, float scale, cudaStream_t s,
+                    const float* sum_partials = nullptr, int npartials = 0) {
     using T = Tile<N>;
     k_rows_r2c<N><<<dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsR2CParams{psf, otf, tw, nullptr, nullptr});
+        RowsR2CParams{src, otf, tw, nullptr, nullptr});
     LAUNCH_CHECK();
     const int total = 3 * T::NC;
     k_cols_fwd<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsFwdParams{otf, tw, total, 1, scale});
+        ColsFwdParams{otf, tw, total, 1, scale, sum_partials, npartials});
     LAUNCH_CHECK();
     return 0;
 }
@@ -987,6 +1022,7 @@ int b200cam_init(int N) {
     std::lock_guard<std::mutex> lock(g_mutex);
     const int l = log2i(N);
     if (g_state[dev].tw[l] != nullptr) return 0;
+    if (g_state[dev].chain_ev == nullptr) CK(cudaEventCreateWithFlags(&g_state[dev].chain_ev, cudaEventDisableTiming));
     if (g_state[dev].bar == nullptr) {
         unsigned* bar = nullptr;
         CK(cudaMalloc(&bar, 4 * sizeof(unsigned)));
@@ -1069,6 +1105,43 @@ int b200cam_psf_fwd(const float* h, const float* A, const float* Ht, const float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DISPATCH_N(N, (psf_fwd_impl<NN_>(h, reinterpret_cast<const float2*>(A), reinterpret_cast<const float2*>(Ht), rho,
                                      kappa, psf, reinterpret_cast<float2*>(field), stats, workspace, s)));
+}
+
+int b200cam_psf_field(const float* h, const float* A, const float* Ht, const float* kappa, float* field,
+                      void* workspace, size_t workspace_bytes, int N, void* stream, void* dependent_stream,
+                      int has_dependent) {
+    if (!b200cam_supported(N)) return B200CAM_E_BAD_SIZE;
+    if (!h || !A || !Ht || !kappa || !field || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_psf_workspace_bytes(N)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(A) || !aligned16(Ht) || !aligned16(field) || !aligned16(workspace)) return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (psf_field_impl<NN_>(h, reinterpret_cast<const float2*>(A), reinterpret_cast<const float2*>(Ht), kappa,
+                                       reinterpret_cast<float2*>(field), workspace, s,
+                                       static_cast<cudaStream_t>(dependent_stream), has_dependent != 0)));
+}
+
+int b200cam_psf_otf_early(float* otf, void* workspace, size_t workspace_bytes, int N, void* stream) {
+    if (!b200cam_supported(N)) return B200CAM_E_BAD_SIZE;
+    if (!otf || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_psf_workspace_bytes(N)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(otf) || !aligned16(workspace)) return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const float2* tw = twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    // |U|^2 / S is the PSF: the OTF does not have to wait for psf_finish to write it out
+    DISPATCH_N(N, (otf_impl<NN_>(PsfWs(workspace, NN_).I, reinterpret_cast<float2*>(otf), tw,
+                                 1.0f / (static_cast<float>(NN_) * NN_), s, PsfWs(workspace, NN_).part_rows,
+                                 3 * (NN_ / Tile<NN_>::CROWS))));
+}
+
+int b200cam_psf_finish(const float* rho, float* psf, float* stats, void* workspace, size_t workspace_bytes, int N,
+                       void* stream) {
+    if (!b200cam_supported(N)) return B200CAM_E_BAD_SIZE;
+    if (!rho || !psf || !stats || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_psf_workspace_bytes(N)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(workspace)) return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DISPATCH_N(N, (psf_finish_impl<NN_>(rho, psf, stats, workspace, s)));
 }
 
 int b200cam_psf_bwd(const float* grad_psf, const float* grad_rad, const float* grad_cen, const float* h, const float* A,

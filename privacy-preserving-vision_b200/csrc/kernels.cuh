@@ -245,6 +245,10 @@ struct ColsFwdParams {
     int total_cols;
     int checker_sign;    // multiply by (-1)^(u+v)
     float scale;
+    // optional: divide by S = sum(partials) as well - the OTF of psf = |U|^2 / S taken straight from |U|^2, so that it
+    // does not have to wait for psf_finalise.  Every CTA adds the same values in the same order.
+    const float* sum_partials;
+    int npartials;
 };
 
 template <int N, class Exec>
@@ -253,7 +257,23 @@ B200_HD void cols_fwd_body(Exec& ex, const ColsFwdParams& p, float2* smem) {
     using T = Tile<N>;
     using S = ColsSmem<N>;
     float2* E1 = smem;
+    float* red = reinterpret_cast<float*>(smem + S::COLS * P::E_SIZE);      // second exchange buffer: unused here
     const int col0 = ex.bx() * S::COLS;
+    if (p.sum_partials != nullptr) {
+        ex.phase([&](int tid) {
+            float acc = 0.f;
+            for (int i = tid; i < p.npartials; i += S::THREADS) acc += p.sum_partials[i];
+            red[tid] = acc;
+        });
+        ex.phase([&](int tid) {
+            if (tid == 0) {
+                float tot = 0.f;
+                for (int t = 0; t < S::THREADS; ++t) tot += red[t];
+                red[S::THREADS] = tot;
+            }
+        });
+    }
+    const float scale = p.sum_partials != nullptr ? p.scale / red[S::THREADS] : p.scale;
     ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, a = tid % P::LANES;
         const int col = col0 + jc;
@@ -276,7 +296,7 @@ B200_HD void cols_fwd_body(Exec& ex, const ColsFwdParams& p, float2* smem) {
 #pragma unroll
             for (int i = 0; i < P::R2; ++i) {
                 const int k = b + P::R1 * i;
-                const float s = (p.checker_sign && ((u + k) & 1)) ? -p.scale : p.scale;
+                const float s = (p.checker_sign && ((u + k) & 1)) ? -scale : scale;
                 dst[k] = cscale(v[i], s);
             }
         }

@@ -47,6 +47,7 @@ class DevicePlan:
         self.average_grads = True
         self.peer_comm = None          # parallel.PeerComm: fused NVLink all-reduce instead of the NCCL call
         self.otf_cache = None          # (psf tensor, its OTF) left by the last asynchronous psf_synth
+        self.otf_event = None          # recorded on the side stream once that OTF is complete
         self._side_stream = None       # runs the PSF-independent half of the sensor forward beside the PSF chain
 
     def side_stream(self) -> torch.cuda.Stream:
@@ -95,14 +96,23 @@ class PsfSynth(torch.autograd.Function):
             stream.wait_stream(torch.cuda.current_stream(plan.device))
         launch = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _stream()
         with torch.cuda.device(plan.index):
-            _lib.check(plan.lib.b200cam_psf_fwd(
-                _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho), plan.kappa,
-                _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), N, launch))
-            if stream is not None:
-                # the OTF only depends on the PSF: compute it here, beside the image row pass, and hand it to sensor_conv
+            if stream is None:
+                _lib.check(plan.lib.b200cam_psf_fwd(
+                    _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), _lib.ptr(plan.rho), plan.kappa,
+                    _lib.ptr(psf), _lib.ptr(field), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), N, launch))
+            else:
+                # field -> OTF -> (event) -> psf + regularisers: the OTF only needs |U|^2 and its sum, so the sensor
+                # pipeline that waits for `plan.otf_event` does not wait for the PSF to be written out
+                _lib.check(plan.lib.b200cam_psf_field(
+                    _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), plan.kappa, _lib.ptr(field),
+                    _lib.ptr(ws), ws.numel(), N, launch, _stream(), 1))
                 otf = torch.empty(plan.otf_floats, dtype=torch.float32, device=plan.device)
-                _lib.check(plan.lib.b200cam_psf_otf(_lib.ptr(psf), _lib.ptr(otf), N, launch))
+                _lib.check(plan.lib.b200cam_psf_otf_early(_lib.ptr(otf), _lib.ptr(ws), ws.numel(), N, launch))
+                plan.otf_event = torch.cuda.Event()
+                plan.otf_event.record(stream)
                 plan.otf_cache = (psf.data_ptr(), otf)
+                _lib.check(plan.lib.b200cam_psf_finish(
+                    _lib.ptr(plan.rho), _lib.ptr(psf), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), N, launch))
         ctx.plan = plan
         ctx.h_shape = h.shape
         ctx.save_for_backward(hc, psf, field, stats)

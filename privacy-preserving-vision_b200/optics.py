@@ -151,6 +151,16 @@ class Camera(nn.Module):
         side = plan.side_stream()
         psf = self.get_psf(_stream=side)                       # enqueued on `side`, not joined yet
         rows = F.sensor_rows(img, plan) if psf.device == img.device else None
-        torch.cuda.current_stream(psf.device).wait_stream(side)
+        cur = torch.cuda.current_stream(psf.device)
+        if rows is not None and plan.otf_event is not None:
+            # the spectral product only needs the OTF; the PSF itself and the regularisers are still being written on
+            # the side stream while the sensor kernels run - join after they are enqueued
+            cur.wait_event(plan.otf_event)
+            plan.otf_event = None
+            self.centering_loss = self._pending_centering
+            y = F.sensor_conv(img, psf, self._plan(psf.device), rows)
+            cur.wait_stream(side)
+            return y
+        cur.wait_stream(side)
         self.centering_loss = self._pending_centering
         return F.sensor_conv(img, psf, self._plan(psf.device), rows)

@@ -52,7 +52,7 @@ void otf_impl(const float* psf, float2* otf, const float2* tw) {
     });
     const int total = 3 * T::NC;
     grid2((total + T::COLS - 1) / T::COLS, 1, ColsSmem<N>::THREADS, [&](HostExec& ex) {
-        cols_fwd_body<N>(ex, ColsFwdParams{otf, tw, total, 1, 1.0f / (static_cast<float>(N) * N)}, smem.data());
+        cols_fwd_body<N>(ex, ColsFwdParams{otf, tw, total, 1, 1.0f / (static_cast<float>(N) * N), nullptr, 0}, smem.data());
     });
 }
 
