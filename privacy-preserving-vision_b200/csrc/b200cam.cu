@@ -24,6 +24,17 @@ __global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_r2c(RowsR2CPar
     DeviceExec ex;
     rows_r2c_body<N>(ex, p, SMEM2);
 }
+// the same row pass as a persistent grid of `gridDim.x` CTAs walking the tiles: the number of resident CTAs per SM is
+// then the launch's choice, not the occupancy limit - used for the image rows that run BESIDE the PSF chain, whose
+// small high-priority kernels need free registers / shared memory on every SM the moment they are launched
+template <int N>
+__global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_r2c_persist(RowsR2CParams p, int tiles_total) {
+    constexpr int TILES = N / Tile<N>::ROWS;
+    for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+        VirtualExec ex{t % TILES, t / TILES, RowsR2CSmem<N>::THREADS};
+        rows_r2c_body<N>(ex, p, SMEM2);
+    }
+}
 template <int N>
 __global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 4 : 1) k_cols_conv(ColsConvParams p) {
     DeviceExec ex;
@@ -455,6 +466,7 @@ static cudaError_t init_kernels() {
     cudaError_t e;
     if ((e = optin(k_rows_r2c<N>, RowsR2CSmem<N>::BYTES))) return e;
     if ((e = optin(k_rows_c2r<N>, RowsR2CSmem<N>::BYTES))) return e;
+    if ((e = optin(k_rows_r2c_persist<N>, RowsR2CSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_conv<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_fwd<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_accum<N>, ColsSmem<N>::BYTES))) return e;
@@ -747,9 +759,13 @@ static int sensor_rows_impl(const float* img, float2* srow, float* img_max, int*
     using T = Tile<N>;
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
-    const dim3 rgrid(N / T::ROWS, 3 * B);
-    k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsR2CParams{img, srow, tw, img_max, tie_count});
+    // B200CAM_ROWS_PER_SM resident CTAs per SM (default 3 of the 4 that fit): see k_rows_r2c_persist
+    static const int per_sm = [] { const char* e = getenv("B200CAM_ROWS_PER_SM"); const int v = e ? atoi(e) : 3; return v > 0 ? v : 3; }();
+    const int total = (N / T::ROWS) * 3 * B;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int grid = total < sms * per_sm ? total : sms * per_sm;
+    k_rows_r2c_persist<N><<<grid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        RowsR2CParams{img, srow, tw, img_max, tie_count}, total);
     LAUNCH_CHECK();
     return 0;
 }

@@ -49,6 +49,8 @@ class DevicePlan:
         self.otf_cache = None          # (psf tensor, its OTF) left by the last asynchronous psf_synth
         self.otf_event = None          # recorded on the side stream once that OTF is complete
         self._side_stream = None       # runs the PSF-independent half of the sensor forward beside the PSF chain
+        self._aux_stream = None
+        self.pending_finish = None     # (psf, stats) still to be written by finish_psf()
 
     def side_stream(self) -> torch.cuda.Stream:
         """High-priority stream for the PSF chain: its small kernels must be dispatched ahead of the thousands of
@@ -56,6 +58,24 @@ class DevicePlan:
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=self.device, priority=-1)
         return self._side_stream
+
+    def aux_stream(self) -> torch.cuda.Stream:
+        """Normal-priority stream for work that only has to be finished by the end of forward()."""
+        if self._aux_stream is None:
+            self._aux_stream = torch.cuda.Stream(device=self.device)
+        return self._aux_stream
+
+    def finish_psf(self, stream: torch.cuda.Stream) -> None:
+        """Second half of an asynchronous psf_synth (b200cam_psf_finish) on `stream`, ordered after the OTF."""
+        if self.pending_finish is None:
+            return
+        psf, stats = self.pending_finish
+        self.pending_finish = None
+        ws = self._psf_ws
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.b200cam_psf_finish(
+                _lib.ptr(self.rho), _lib.ptr(psf), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), self.N,
+                ctypes.c_void_p(stream.cuda_stream)))
 
     def psf_workspace(self) -> torch.Tensor:
         return self._psf_ws
@@ -111,8 +131,9 @@ class PsfSynth(torch.autograd.Function):
                 plan.otf_event = torch.cuda.Event()
                 plan.otf_event.record(stream)
                 plan.otf_cache = (psf.data_ptr(), otf)
-                _lib.check(plan.lib.b200cam_psf_finish(
-                    _lib.ptr(plan.rho), _lib.ptr(psf), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), N, launch))
+                # psf and the regularisers are written by `plan.finish_psf(stream)`, which the caller enqueues where it
+                # does not delay the sensor pipeline (Camera.forward: low-priority stream, after the spectral product)
+                plan.pending_finish = (psf, stats)
         ctx.plan = plan
         ctx.h_shape = h.shape
         ctx.save_for_backward(hc, psf, field, stats)

@@ -153,14 +153,19 @@ class Camera(nn.Module):
         rows = F.sensor_rows(img, plan) if psf.device == img.device else None
         cur = torch.cuda.current_stream(psf.device)
         if rows is not None and plan.otf_event is not None:
-            # the spectral product only needs the OTF; the PSF itself and the regularisers are still being written on
-            # the side stream while the sensor kernels run - join after they are enqueued
-            cur.wait_event(plan.otf_event)
-            plan.otf_event = None
+            # the spectral product only needs the OTF: the PSF itself and the two regularisers are written on a
+            # normal-priority stream while the sensor kernels run, and joined at the end
+            ev, plan.otf_event = plan.otf_event, None
+            cur.wait_event(ev)
             self.centering_loss = self._pending_centering
             y = F.sensor_conv(img, psf, self._plan(psf.device), rows)
+            aux = plan.aux_stream()
+            aux.wait_event(ev)
+            plan.finish_psf(aux)
+            cur.wait_stream(aux)
             cur.wait_stream(side)
             return y
+        plan.finish_psf(side)
         cur.wait_stream(side)
         self.centering_loss = self._pending_centering
         return F.sensor_conv(img, psf, self._plan(psf.device), rows)
