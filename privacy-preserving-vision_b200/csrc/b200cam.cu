@@ -28,12 +28,14 @@ __global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_r2c(RowsR2CPar
 // then the launch's choice, not the occupancy limit - used for the image rows that run BESIDE the PSF chain, whose
 // small high-priority kernels need free registers / shared memory on every SM the moment they are launched
 template <int N>
-__global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_r2c_persist(RowsR2CParams p, int tiles_total) {
-    constexpr int TILES = N / Tile<N>::ROWS;
-    for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
-        VirtualExec ex{t % TILES, t / TILES, RowsR2CSmem<N>::THREADS};
-        rows_r2c_body<N>(ex, p, SMEM2);
-    }
+__global__ void __launch_bounds__(RowsStreamSmem<N>::THREADS) k_rows_r2c_persist(RowsR2CParams p, int tiles_total) {
+    DeviceExec ex;
+    rows_r2c_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
+}
+template <int N>
+__global__ void __launch_bounds__(RowsC2RStreamSmem<N>::THREADS) k_rows_c2r_persist(RowsC2RParams p, int tiles_total) {
+    DeviceExec ex;
+    rows_c2r_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
 }
 template <int N>
 __global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 4 : 1) k_cols_conv(ColsConvParams p) {
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_normalise(NormaliseParams p) {
     normalise_body(ex, p, gridDim.x);
 }
 template <int N>
-__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_accum(ColsAccumParams p) {
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 4 : 1) k_cols_accum(ColsAccumParams p) {
     DeviceExec ex;
     AccumState<N> st;
     cols_accum_body<N>(ex, p, SMEM2, &st);
@@ -466,7 +468,8 @@ static cudaError_t init_kernels() {
     cudaError_t e;
     if ((e = optin(k_rows_r2c<N>, RowsR2CSmem<N>::BYTES))) return e;
     if ((e = optin(k_rows_c2r<N>, RowsR2CSmem<N>::BYTES))) return e;
-    if ((e = optin(k_rows_r2c_persist<N>, RowsR2CSmem<N>::BYTES))) return e;
+    if ((e = optin(k_rows_r2c_persist<N>, RowsStreamSmem<N>::BYTES))) return e;
+    if ((e = optin(k_rows_c2r_persist<N>, RowsC2RStreamSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_conv<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_fwd<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_accum<N>, ColsSmem<N>::BYTES))) return e;
@@ -764,7 +767,7 @@ static int sensor_rows_impl(const float* img, float2* srow, float* img_max, int*
     const int total = (N / T::ROWS) * 3 * B;
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const int grid = total < sms * per_sm ? total : sms * per_sm;
-    k_rows_r2c_persist<N><<<grid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+    k_rows_r2c_persist<N><<<grid, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES, s>>>(
         RowsR2CParams{img, srow, tw, img_max, tie_count}, total);
     LAUNCH_CHECK();
     return 0;
@@ -788,8 +791,19 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
         ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f});
     LAUNCH_CHECK();
-    k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0});
+    {
+        static const int per_sm = [] { const char* e = getenv("B200CAM_C2R_PER_SM"); const int v = e ? atoi(e) : 4; return v; }();
+        if (per_sm > 0) {
+            const int total = (N / T::ROWS) * planes;
+            const int sms = sm_count() > 0 ? sm_count() : 148;
+            const int grid = total < sms * per_sm ? total : sms * per_sm;
+            k_rows_c2r_persist<N><<<grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s>>>(
+                RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0}, total);
+        } else {
+            k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+                RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0});
+        }
+    }
     LAUNCH_CHECK();
     const long long n4 = static_cast<long long>(planes) * N * N / 4;
     const int grid = static_cast<int>(n4 / EW_THREADS < 148 * 8 ? (n4 + EW_THREADS - 1) / EW_THREADS : 148 * 8);
@@ -956,7 +970,18 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     // upstream gradient rows; sum(g*conv) of the amax term comes out of the accumulate kernel (Parseval), so the
     // sensor image is not read again
     (void)sensor;
-    k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
+    {
+        static const int per_sm = [] { const char* e = getenv("B200CAM_GROWS_PER_SM"); return e ? atoi(e) : 3; }();
+        if (per_sm > 0) {
+            const int total = tiles * planes;
+            const int sms = sm_count() > 0 ? sm_count() : 148;
+            const int grid = total < sms * per_sm ? total : sms * per_sm;
+            k_rows_r2c_persist<N><<<grid, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES, s>>>(
+                RowsR2CParams{g, ws.stg, tw, nullptr, nullptr}, total);
+        } else {
+            k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
+        }
+    }
     LAUNCH_CHECK();
     const int nchunks = accum_chunks(N, B);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;

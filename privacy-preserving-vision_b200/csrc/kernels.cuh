@@ -117,6 +117,110 @@ B200_HD void rows_r2c_body(Exec& ex, const RowsR2CParams& p, float2* smem) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1s rows_r2c_stream : the same row pass as a PERSISTENT grid with TMA-staged image tiles.
+//      CTA k walks tiles k, k + nctas, ...; a tile (ROWS image rows) is one contiguous ROWS*N*4-byte block in global
+//      memory, fetched by a single 1-D bulk copy (cp.async.bulk + mbarrier) into one of two staging buffers while
+//      the previous tile is being transformed.  Compared with K1: no 4-byte strided global loads (each 128-byte line
+//      was fetched by two different instructions), the loads are asynchronous, and - the kernel being persistent - the
+//      lane's twiddles stay in registers.  grid = any (the launch picks the resident CTAs per SM), block NP*LANES.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct RowsStreamSmem {
+    using R = RowsR2CSmem<N>;
+    using T = Tile<N>;
+    static constexpr int TILE_FLOATS = T::ROWS * N;
+    static constexpr int TILE_BYTES = TILE_FLOATS * 4;
+    static constexpr int STAGE_OFF = (R::RED_OFF + 15) / 16 * 16;            // float2 units, 128-byte aligned
+    static constexpr int BAR_OFF = STAGE_OFF + TILE_FLOATS;                   // two tiles of floats = TILE_FLOATS float2
+    static constexpr int FLOAT2S = BAR_OFF + 2;                               // two 8-byte mbarriers
+    static constexpr int BYTES = FLOAT2S * 8;
+    static constexpr int THREADS = R::THREADS;
+};
+
+template <int N, class Exec>
+B200_HD void rows_r2c_stream_body(Exec& ex, const RowsR2CParams& p, float2* smem, int total_tiles, int nctas) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = RowsR2CSmem<N>;
+    using Q = RowsStreamSmem<N>;
+    constexpr int TILES = N / T::ROWS;
+    constexpr bool RT = P::REG_TW;
+    float* stage = reinterpret_cast<float*>(smem + Q::STAGE_OFF);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Q::BAR_OFF);
+    RowState<N> st[Exec::IS_HOST ? S::THREADS : 1];
+    float2 wreg[RT ? P::R1 : 1];
+    const int first = ex.bx();
+    auto tile_src = [&](int t) { return p.x + static_cast<size_t>(t) * Q::TILE_FLOATS; };   // tiles are contiguous in x
+
+    ex.phase([&](int tid) {
+        if (tid == 0) {
+            ex.bulk_init(bars + 0);
+            ex.bulk_init(bars + 1);
+            ex.bulk_fence_init();
+            if (first < total_tiles) {
+                ex.bulk_expect(bars + 0, Q::TILE_BYTES);
+                ex.bulk_load(stage, tile_src(first), Q::TILE_BYTES, bars + 0);
+            }
+        }
+        if constexpr (RT && !Exec::IS_HOST) P::load_tw(wreg, p.tw, tid % P::LANES);
+    });
+    int it = 0;
+    for (int t = first; t < total_tiles; t += nctas, ++it) {
+        const int buf = it & 1;
+        const int plane = t / TILES, tile = t % TILES;
+        const int y0 = tile * T::ROWS;
+        ex.warp_phase([&](int tid) {
+            // the other buffer was last read two block barriers ago: refill it with this CTA's next tile
+            if (tid == 0 && t + nctas < total_tiles) {
+                ex.bulk_expect(bars + (buf ^ 1), Q::TILE_BYTES);
+                ex.bulk_load(stage + (buf ^ 1) * Q::TILE_FLOATS, tile_src(t + nctas), Q::TILE_BYTES, bars + (buf ^ 1));
+            }
+            ex.bulk_wait(bars + buf, (it >> 1) & 1);
+            const int j = tid / P::LANES, a = tid % P::LANES;
+            if (a < P::R2) {
+                const float* r0 = stage + buf * Q::TILE_FLOATS + (2 * j) * N;
+                const float* r1 = r0 + N;
+                float2 v[P::R1];
+#pragma unroll
+                for (int i = 0; i < P::R1; ++i) v[i] = make_float2(r0[P::R2 * i + a], r1[P::R2 * i + a]);
+                if constexpr (RT) {
+                    if constexpr (Exec::IS_HOST) P::load_tw(wreg, p.tw, a);
+                    P::stepA(v, a, smem + j * S::PA, wreg);
+                } else {
+                    P::stepA(v, a, smem + j * S::PA, p.tw);
+                }
+            }
+            if (tid == 0 && tile == 0 && plane % 3 == 0) {
+                if (p.init_max != nullptr) p.init_max[plane / 3] = neg_inf();
+                if (p.init_count != nullptr) p.init_count[plane / 3] = 0;
+            }
+        });
+        ex.warp_phase([&](int tid) {
+            const int j = tid / P::LANES, b = tid % P::LANES;
+            if (b < P::R1) P::stepB(st[ex.slot(tid)].v, b, smem + j * S::PA);
+        });
+        ex.phase([&](int tid) {
+            const int j = tid / P::LANES, b = tid % P::LANES;
+            if (b < P::R1) {
+                const RowState<N>& s = st[ex.slot(tid)];
+#pragma unroll
+                for (int i = 0; i < P::R2; ++i) smem[j * S::PA + b + P::R1 * i] = s.v[i];
+            }
+        });
+        ex.phase([&](int tid) {
+            for (int w = tid; w < T::NP * T::NC; w += S::THREADS) {
+                const int u = w / T::NP, j = w % T::NP;
+                const float2 z1 = smem[j * S::PA + u];
+                const float2 z2 = smem[j * S::PA + ((N - u) & (N - 1))];
+                const float4 o = make_float4(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y),    // X_even[u]
+                                             0.5f * (z1.y + z2.y), -0.5f * (z1.x - z2.x));  // X_odd[u]
+                *reinterpret_cast<float4*>(p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0 + 2 * j) = o;
+            }
+        });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2  cols_conv : per spectral column  FFT_v -> x OTF -> IFFT_v, in place on ST
 //      (second half of rfftn, the multiply Utils.py:10 and first half of irfftn Utils.py:11)
 //      grid ceil(planes*NC / COLS), block COLS*LANES.  OTF layout [3][NC][N] (column = channel,u),
@@ -423,6 +527,135 @@ B200_HD void rows_c2r_body(Exec& ex, const RowsC2RParams& p, float2* smem) {
                 atomic_max_float(p.img_max + plane / 3, mx);
             }
         });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3s rows_c2r_stream : K3 (norm = 0) as a persistent grid with TMA-staged spectrum tiles.  A tile is NC segments of
+//      ROWS*8 bytes (one per spectral column u, 8N bytes apart): thread u issues the bulk copy of segment u, all on
+//      one mbarrier; two staging buffers, so the next tile lands while this one is transformed.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct RowsC2RStreamSmem {
+    using R = RowsR2CSmem<N>;
+    using T = Tile<N>;
+    static constexpr int SEG = T::ROWS;                                       // float2 per segment
+    static constexpr int TILE_FLOAT2S = T::NC * SEG;
+    static constexpr int STAGE_OFF = (R::FLOAT2S + 15) / 16 * 16;             // float2 units, 128-byte aligned
+    static constexpr int BAR_OFF = STAGE_OFF + 2 * ((TILE_FLOAT2S + 15) / 16 * 16);
+    static constexpr int FLOAT2S = BAR_OFF + 2;
+    static constexpr int BYTES = FLOAT2S * 8;
+    static constexpr int THREADS = R::THREADS;
+};
+
+template <int N, class Exec>
+B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem, int total_tiles, int nctas) {
+    using P = Plan<N>;
+    using T = Tile<N>;
+    using S = RowsR2CSmem<N>;
+    using Q = RowsC2RStreamSmem<N>;
+    constexpr int TILES = N / T::ROWS;
+    constexpr bool RT = P::REG_TW;
+    constexpr int STAGE_STRIDE = (Q::TILE_FLOAT2S + 15) / 16 * 16;
+    float2* stage = smem + Q::STAGE_OFF;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Q::BAR_OFF);
+    float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
+    RowState<N> st[Exec::IS_HOST ? S::THREADS : 1];
+    float2 wreg[RT ? P::R1 : 1];
+    const int first = ex.bx();
+    // thread tid copies segments tid, tid + THREADS, ... of tile t into staging buffer `buf`
+    auto issue = [&](int tid, int t, int buf) {
+        const int plane = t / TILES, y0 = (t % TILES) * T::ROWS;
+        for (int u = tid; u < T::NC; u += S::THREADS)
+            ex.bulk_load(stage + buf * STAGE_STRIDE + u * Q::SEG, p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0,
+                         Q::SEG * 8, bars + buf);
+    };
+
+    ex.phase([&](int tid) {
+        if (tid == 0) {
+            ex.bulk_init(bars + 0);
+            ex.bulk_init(bars + 1);
+            ex.bulk_fence_init();
+        }
+        if constexpr (RT && !Exec::IS_HOST) P::load_tw(wreg, p.tw, tid % P::LANES);
+    });
+    ex.phase([&](int tid) {
+        if (first < total_tiles) {
+            if (tid == 0) ex.bulk_expect(bars + 0, T::NC * Q::SEG * 8);
+            issue(tid, first, 0);
+        }
+    });
+    int it = 0;
+    for (int t = first; t < total_tiles; t += nctas, ++it) {
+        const int buf = it & 1;
+        const int plane = t / TILES, y0 = (t % TILES) * T::ROWS;
+        ex.phase([&](int tid) {
+            if (t + nctas < total_tiles) {        // the other buffer was consumed before the last block barrier
+                if (tid == 0) ex.bulk_expect(bars + (buf ^ 1), T::NC * Q::SEG * 8);
+                issue(tid, t + nctas, buf ^ 1);
+            }
+            ex.bulk_wait(bars + buf, (it >> 1) & 1);
+            const float2* sg = stage + buf * STAGE_STRIDE;
+            for (int w = tid; w < T::NP * T::NC; w += S::THREADS) {
+                const int u = w / T::NP, j = w % T::NP;
+                const float4 q = *reinterpret_cast<const float4*>(sg + u * Q::SEG + 2 * j);
+                // Z = X_even + i X_odd ; Z[N-u] = conj(X_even[u]) + i conj(X_odd[u])
+                float2* F = smem + j * S::PA;
+                if (u == 0 || u == N / 2) {
+                    F[u] = make_float2(q.x, q.z);   // irfft ignores Im at DC/Nyquist
+                } else {
+                    F[u] = make_float2(q.x - q.w, q.y + q.z);
+                    F[N - u] = make_float2(q.x + q.w, q.z - q.y);
+                }
+            }
+        });
+        ex.warp_phase([&](int tid) {
+            const int j = tid / P::LANES, b = tid % P::LANES;
+            if (b < P::R1) {
+                RowState<N>& s = st[ex.slot(tid)];
+#pragma unroll
+                for (int i = 0; i < P::R2; ++i) s.v[i] = smem[j * S::PA + b + P::R1 * i];
+            }
+        });
+        ex.warp_phase([&](int tid) {
+            const int j = tid / P::LANES, b = tid % P::LANES;
+            if (b < P::R1) {
+                if constexpr (RT) {
+                    if constexpr (Exec::IS_HOST) P::load_tw(wreg, p.tw, b);
+                    P::stepC(st[ex.slot(tid)].v, b, smem + j * S::PA, wreg);
+                } else {
+                    P::stepC(st[ex.slot(tid)].v, b, smem + j * S::PA, p.tw);
+                }
+            }
+        });
+        ex.phase([&](int tid) {
+            const int j = tid / P::LANES, a = tid % P::LANES;
+            float mx = neg_inf();
+            if (a < P::R2) {
+                float2 v[P::R1];
+                P::stepD(v, a, smem + j * S::PA);
+                const size_t row = (static_cast<size_t>(plane) * N + y0 + 2 * j) * N;
+#pragma unroll
+                for (int i = 0; i < P::R1; ++i) {
+                    const float e = v[i].x * p.scale, o = v[i].y * p.scale;
+                    if (p.out != nullptr) {
+                        p.out[row + P::R2 * i + a] = e;
+                        p.out[row + N + P::R2 * i + a] = o;
+                    }
+                    mx = fmaxf(mx, fmaxf(e, o));
+                }
+            }
+            red[tid] = mx;
+        });
+        if (p.img_max != nullptr) {
+            ex.phase([&](int tid) {
+                if (tid == 0) {
+                    float mx = red[0];
+                    for (int k = 1; k < S::THREADS; ++k) mx = fmaxf(mx, red[k]);
+                    atomic_max_float(p.img_max + plane / 3, mx);
+                }
+            });
+        }
     }
 }
 

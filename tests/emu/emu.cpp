@@ -75,18 +75,27 @@ int sensor_fwd_impl(int B, const float* img, const float* psf, float* sensor, fl
     std::vector<float2> stx(static_cast<size_t>(planes) * T::NC * N), st2(static_cast<size_t>(planes) * T::NC * N);
     float2* srow = spectrum != nullptr ? spectrum : stx.data();
     std::vector<float2> smem(RowsR2CSmem<N>::FLOAT2S > ColsSmem<N>::FLOAT2S ? RowsR2CSmem<N>::FLOAT2S : ColsSmem<N>::FLOAT2S);
-    grid2(N / T::ROWS, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_r2c_body<N>(ex, RowsR2CParams{img, srow, tw.data(), img_max, tie_count}, smem.data());
-    });
+    {   // the library runs the image rows as a persistent, TMA-staged grid: same here with a small odd grid
+        const int total = (N / T::ROWS) * planes, nctas = 5;
+        std::vector<float2> ssmem(RowsStreamSmem<N>::FLOAT2S);
+        grid2(nctas, 1, RowsStreamSmem<N>::THREADS, [&](HostExec& ex) {
+            rows_r2c_stream_body<N>(ex, RowsR2CParams{img, srow, tw.data(), img_max, tie_count}, ssmem.data(), total, nctas);
+        });
+    }
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int nchunks = conv_chunks(N, B);
     std::vector<ConvState<N>> cst(ColsSmem<N>::THREADS);
     grid2(colgroups, nchunks, ColsSmem<N>::THREADS, [&](HostExec& ex) {
         cols_conv_body<N>(ex, ColsConvParams{srow, st2.data(), otf, tw.data(), nullptr, B, nchunks, 0, 1.0f}, smem.data(), cst.data());
     });
-    grid2(N / T::ROWS, planes, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
-        rows_c2r_body<N>(ex, RowsC2RParams{st2.data(), sensor, tw.data(), img_max, 1.0f, nullptr, nullptr, 0}, smem.data());
-    });
+    {
+        const int total = (N / T::ROWS) * planes, nctas = 7;
+        std::vector<float2> ssmem(RowsC2RStreamSmem<N>::FLOAT2S);
+        grid2(nctas, 1, RowsC2RStreamSmem<N>::THREADS, [&](HostExec& ex) {
+            rows_c2r_stream_body<N>(ex, RowsC2RParams{st2.data(), sensor, tw.data(), img_max, 1.0f, nullptr, nullptr, 0},
+                                    ssmem.data(), total, nctas);
+        });
+    }
     const long long n4 = static_cast<long long>(planes) * N * N / 4;
     grid2(EW_GRID, 1, EW_THREADS, [&](HostExec& ex) {
         normalise_body(ex, NormaliseParams{sensor, img_max, tie_count, tie_pos, n4, 3 * N * N / 4}, EW_GRID);
