@@ -323,6 +323,41 @@ def run_b200(args) -> None:
             os._exit(0)
         return
 
+    # ---- per-kernel durations of the replayed step (CUPTI activity records through torch.profiler; a separate pass
+    #      AFTER the timed region - nothing above was measured under it).  Bytes = what that kernel must read + write.
+    kernel_table = None
+    if graphs is not None and rank == 0:
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            reps = 8
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for i in range(reps):
+                    run_step(i)
+                torch.cuda.synchronize()
+            P = B * 3 * N * N * 4                       # one batch of real planes
+            S = B * 3 * (N // 2 + 1) * N * 8            # one batch of half spectra
+            model = {"k_rows_r2c_persist": P + S, "k_cols_conv": 2 * S, "k_rows_c2r_persist": S + P, "k_normalise": 2 * P,
+                     "k_cols_accum": 2 * S}
+            agg = {}
+            for e in prof.events():
+                if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None and "k_" in e.name:
+                    name = e.name.replace("void ", "").replace("b200cam::", "").split("(")[0]
+                    a = agg.setdefault(name, [0, 0.0])
+                    a[0] += 1
+                    a[1] += e.time_range.end - e.time_range.start
+            kernel_table = []
+            for name, (cnt, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                us = tot / cnt
+                row = {"kernel": name, "launches_per_step": round(cnt / reps, 2), "avg_us": round(us, 2)}
+                key = name.split("<")[0]
+                if key in model and cnt / reps < 2.5:
+                    nbytes = model[key]
+                    row["bytes"] = nbytes
+                    row["GBps"] = round(nbytes / us * 1e-3, 1)
+                kernel_table.append(row)
+        except Exception as exc:    # CUPTI not available: the table is optional
+            kernel_table = [{"error": str(exc)[:200]}]
+
     # ---- per-call breakdown (each C-ABI call timed alone over the same rotating inputs) -----------------
     from b200cam import functional as F
     plan = cam._plan(dev)
@@ -438,7 +473,8 @@ def run_b200(args) -> None:
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "scope": "whole step: every kernel of fwd+bwd (algorithmic bytes 48*N^2 per image, SURVEY 8d)",
-                     "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()}},
+                     "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()},
+                     "kernels_cupti": kernel_table},
         "clocks": clocks,
     }
     if cpu is not None:

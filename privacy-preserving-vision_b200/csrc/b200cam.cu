@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_normalise(NormaliseParams p) {
     normalise_body(ex, p, gridDim.x);
 }
 template <int N>
-__global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 4 : 1) k_cols_accum(ColsAccumParams p) {
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_accum(ColsAccumParams p) {
     DeviceExec ex;
     AccumState<N> st;
     cols_accum_body<N>(ex, p, SMEM2, &st);
