@@ -470,7 +470,7 @@ static cudaError_t init_kernels() {
     if ((e = optin(k_rows_c2r<N>, RowsR2CSmem<N>::BYTES))) return e;
     if ((e = optin(k_rows_r2c_persist<N>, RowsStreamSmem<N>::BYTES))) return e;
     if ((e = optin(k_rows_c2r_persist<N>, RowsC2RStreamSmem<N>::BYTES))) return e;
-    if ((e = optin(k_cols_conv<N>, ColsSmem<N>::BYTES))) return e;
+    if ((e = optin(k_cols_conv<N>, ColsSmem<N>::BYTES_CONV))) return e;
     if ((e = optin(k_cols_fwd<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_accum<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_reduce_inv<N>, ReduceInvSmem<N>::BYTES))) return e;
@@ -506,7 +506,7 @@ template <int N>
 static cudaError_t column_slots(int sms, int* conv, int* accum) {
     int nc = 0, na = 0;
     cudaError_t e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nc, k_cols_conv<N>, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES))) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nc, k_cols_conv<N>, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV))) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&na, k_cols_accum<N>, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES))) return e;
     *conv = sms * nc;
     *accum = sms * na;
@@ -788,7 +788,7 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     const dim3 rgrid(N / T::ROWS, planes);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int nchunks = conv_chunks(N, B);
-    k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+    k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
         ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f});
     LAUNCH_CHECK();
     {
@@ -830,7 +830,7 @@ static int conv_fwd_impl(const float* img, const float* kern, float* out, float2
     const int planes = 3 * B;
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int nchunks = conv_chunks(N, B);
-    k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+    k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
         ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f});
     LAUNCH_CHECK();
     k_rows_c2r<N><<<dim3(N / T::ROWS, planes), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
@@ -871,7 +871,7 @@ static int conv_bwd_impl(const float* g, const float* img, const float2* otf, co
     LAUNCH_CHECK();
     if (grad_img != nullptr) {
         const int cchunks = conv_chunks(N, B);
-        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
             ColsConvParams{ws.stg, ws.stg, otf, tw, nullptr, B, cchunks, 1, 1.0f});
         LAUNCH_CHECK();
         k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
@@ -933,7 +933,7 @@ static int fused_bwd(const float* g, const float* img, const float* img_max, con
         LAUNCH_CHECK();
         const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
         const int cchunks = conv_chunks(N, B);
-        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
             ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunks, 1, 2.0f});
         LAUNCH_CHECK();
         k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
@@ -1002,7 +1002,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     }
     if (grad_img != nullptr) {
         const int cchunks = conv_chunks(N, B);
-        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
             ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunks, 1, 1.0f});
         LAUNCH_CHECK();
         k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
