@@ -326,10 +326,10 @@ def run_b200(args) -> None:
     # ---- per-kernel durations of the replayed step (CUPTI activity records through torch.profiler; a separate pass
     #      AFTER the timed region - nothing above was measured under it).  Bytes = what that kernel must read + write.
     kernel_table = None
-    if graphs is not None and rank == 0:
+    if graphs is not None:
         try:
             from torch.profiler import ProfilerActivity, profile
-            reps = 8
+            reps = 8                                    # every rank replays them (the step holds a collective)
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
                 for i in range(reps):
                     run_step(i)
