@@ -49,6 +49,17 @@ size_t b200cam_sensor_workspace_bytes(int N, int B, int want_img_grad);
 /* size of the optional saved forward spectrum (row-transformed rfft of every image plane) */
 size_t b200cam_spectrum_bytes(int N, int B);
 
+/* Zernike projection (the step in front of the PSF synthesis in a training loop).
+ *   h[p] = sum_j coef[j] * Z[j][p]      replaces `get_Heith_Map`, Face-DeId/Camera/Optics.py:79-83 and
+ *                                        Image_Caption/Camera/Lens.py:176 (torch.sum(coef * volume, 0))
+ *   grad_coef[j] = sum_p Z[j][p] * grad_h[p]   its adjoint (what autograd computes for the line above)
+ * Z is [T][NN] fp32 (NN = N*N, a multiple of 4), one pass over it each way.  The forward's workspace
+ * (b200cam_zernike_workspace_bytes) must be ZERO-FILLED once before the first call; the library leaves it reusable. */
+size_t b200cam_zernike_workspace_bytes(int T, long long NN);
+int b200cam_zernike_fwd(const float* coef, const float* Z, float* h, void* workspace, size_t workspace_bytes, int T,
+                        long long NN, void* stream);
+int b200cam_zernike_bwd(const float* grad_h, const float* Z, float* grad_coef, int T, long long NN, void* stream);
+
 /* PSF synthesis, forward.  Replaces Camera.get_psf + the regularisers
  * (Face-DeId/Camera/Optics.py:89-120 and :124-125):
  *   V_l = A_l * exp(i*kappa_l*h);  U = ifftn(fftn(V) * H) over (lambda,y,x);  psf = |U|^2 / sum.

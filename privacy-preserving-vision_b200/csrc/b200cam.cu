@@ -384,6 +384,17 @@ static_assert(HGradSmem<1024>::BYTES <= 227 * 1024 && HGradSmem<512>::BYTES <= 2
 static_assert(HGradSmem<1024>::THREADS <= COOP_THREADS && HGradSmem<512>::THREADS <= COOP_THREADS && CColsSmem<1024>::THREADS <= COOP_THREADS && EW_THREADS <= COOP_THREADS,
               "cooperative block too small for a body");
 
+__global__ void __launch_bounds__(EW_THREADS) k_zernike_fwd(ZernikeFwdParams p) {
+    __shared__ int flag;
+    DeviceExec ex;
+    zernike_fwd_body(ex, p, &flag);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_zernike_bwd(ZernikeBwdParams p) {
+    __shared__ float red[EW_THREADS];
+    DeviceExec ex;
+    zernike_bwd_body(ex, p, red);
+}
+
 __global__ void k_fill_twiddle(float2* tw, int N) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < N) {
@@ -1146,6 +1157,53 @@ int b200cam_psf_fwd(const float* h, const float* A, const float* Ht, const float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DISPATCH_N(N, (psf_fwd_impl<NN_>(h, reinterpret_cast<const float2*>(A), reinterpret_cast<const float2*>(Ht), rho,
                                      kappa, psf, reinterpret_cast<float2*>(field), stats, workspace, s)));
+}
+
+// ---- Zernike projection ----------------------------------------------------------------------
+static int zernike_ks(int T, long long NN4) {
+    const long long xblocks = (NN4 + EW_THREADS - 1) / EW_THREADS;
+    long long ks = (148 * 4 + xblocks - 1) / xblocks;        // about four CTAs per SM in total
+    if (ks > T) ks = T;
+    if (ks > 32) ks = 32;
+    if (ks < 1) ks = 1;
+    return static_cast<int>(ks);
+}
+
+size_t b200cam_zernike_workspace_bytes(int T, long long NN) {
+    if (T < 1 || NN < 4 || NN % 4 != 0) return 0;
+    const long long NN4 = NN / 4;
+    const long long xblocks = (NN4 + EW_THREADS - 1) / EW_THREADS;
+    return static_cast<size_t>(zernike_ks(T, NN4)) * NN4 * sizeof(float4) + static_cast<size_t>(xblocks) * sizeof(int) + 256;
+}
+
+int b200cam_zernike_fwd(const float* coef, const float* Z, float* h, void* workspace, size_t workspace_bytes, int T,
+                        long long NN, void* stream) {
+    if (T < 1 || NN < 4 || NN % 4 != 0 || NN / 4 > 0x7fffffffLL) return B200CAM_E_BAD_SIZE;
+    if (!coef || !Z || !h || !workspace) return B200CAM_E_NULL;
+    if (workspace_bytes < b200cam_zernike_workspace_bytes(T, NN)) return B200CAM_E_WORKSPACE;
+    if (!aligned16(Z) || !aligned16(h) || !aligned16(workspace)) return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int NN4 = static_cast<int>(NN / 4);
+    const int xblocks = (NN4 + EW_THREADS - 1) / EW_THREADS, ks = zernike_ks(T, NN4);
+    Carver c(workspace);
+    int* arrive = c.take<int>(xblocks);                       // zero on entry (caller zero-fills the workspace once), left zero
+    float4* partial = c.take<float4>(static_cast<size_t>(ks) * NN4);
+    k_zernike_fwd<<<dim3(xblocks, ks), EW_THREADS, 0, s>>>(
+        ZernikeFwdParams{coef, reinterpret_cast<const float4*>(Z), partial, reinterpret_cast<float4*>(h), arrive, T, NN4, ks});
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int b200cam_zernike_bwd(const float* grad_h, const float* Z, float* grad_coef, int T, long long NN, void* stream) {
+    if (T < 1 || NN < 4 || NN % 4 != 0 || NN / 4 > 0x7fffffffLL) return B200CAM_E_BAD_SIZE;
+    if (!grad_h || !Z || !grad_coef) return B200CAM_E_NULL;
+    if (!aligned16(Z) || !aligned16(grad_h)) return B200CAM_E_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    k_zernike_bwd<<<T, EW_THREADS, 0, s>>>(ZernikeBwdParams{reinterpret_cast<const float4*>(grad_h),
+                                                            reinterpret_cast<const float4*>(Z), grad_coef,
+                                                            static_cast<int>(NN / 4)});
+    LAUNCH_CHECK();
+    return 0;
 }
 
 int b200cam_psf_field(const float* h, const float* A, const float* Ht, const float* kappa, float* field,

@@ -1720,4 +1720,114 @@ B200_HD void sum3_body(Exec& ex, const Sum3Params& p, int grid_x) {
     });
 }
 
+// =============================================================================================
+//        Zernike projection  h = sum_j coef_j * Z_j   and its adjoint   
+//        (Face-DeId/Camera/Optics.py:79-83 `get_Heith_Map`, Image_Caption/Camera/Lens.py:158-177)
+// =============================================================================================
+// A GEMV over the T x (N*N) basis volume (78.6 MB at T=300, N=256): one pass over Z each way, nothing materialised
+// (torch's  sum(coef * volume, 0)  writes and re-reads the product).
+//
+// Z1  zernike_fwd : grid (ceil(NN4/EW_THREADS), KS), block EW_THREADS.  CTA (x, k) adds terms [T*k/KS, T*(k+1)/KS) for
+//      its EW_THREADS pixel quads into partial[k]; the last of the KS CTAs of a pixel block to finish adds the partials
+//      in order k = 0..KS-1 (deterministic) and writes h.  arrive[x] must be zero on entry and is left zero.
+struct ZernikeFwdParams {
+    const float* coef;     // [T]
+    const float4* Z;       // [T][NN4]
+    float4* partial;       // [KS][NN4]
+    float4* h;             // [NN4]
+    int* arrive;           // [gridDim.x]
+    int T, NN4, KS;
+};
+
+template <class Exec>
+B200_HD void zernike_fwd_body(Exec& ex, const ZernikeFwdParams& p, int* flag) {
+    const int k = ex.by();
+    const int j0 = static_cast<int>(static_cast<long long>(p.T) * k / p.KS);
+    const int j1 = static_cast<int>(static_cast<long long>(p.T) * (k + 1) / p.KS);
+    ex.phase([&](int tid) {
+        const int q = ex.bx() * EW_THREADS + tid;
+        if (q < p.NN4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int j = j0;
+            for (; j + 8 <= j1; j += 8) {                 // eight independent 16-byte loads in flight per thread
+                float4 z[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[i] = ld_ro(p.Z + static_cast<size_t>(j + i) * p.NN4 + q);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float c = ld_ro(p.coef + j + i);
+                    acc.x += c * z[i].x; acc.y += c * z[i].y; acc.z += c * z[i].z; acc.w += c * z[i].w;
+                }
+            }
+            for (; j < j1; ++j) {
+                const float4 z = ld_ro(p.Z + static_cast<size_t>(j) * p.NN4 + q);
+                const float c = ld_ro(p.coef + j);
+                acc.x += c * z.x; acc.y += c * z.y; acc.z += c * z.z; acc.w += c * z.w;
+            }
+            p.partial[static_cast<size_t>(k) * p.NN4 + q] = acc;
+        }
+    });
+    ex.phase([&](int tid) {
+        if (tid == 0) {
+            ex.threadfence();
+            *flag = (atomic_add_int(p.arrive + ex.bx(), 1) == p.KS - 1) ? 1 : 0;
+        }
+    });
+    if (*flag) {
+        ex.phase([&](int tid) {
+            ex.threadfence();
+            const int q = ex.bx() * EW_THREADS + tid;
+            if (q < p.NN4) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int kk = 0; kk < p.KS; ++kk) {
+                    const float4 v = ex.load_cg4(p.partial + static_cast<size_t>(kk) * p.NN4 + q);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                p.h[q] = acc;
+            }
+            if (tid == 0) p.arrive[ex.bx()] = 0;
+        });
+    }
+}
+
+// Z2  zernike_bwd : gcoef_j = sum_p Z_j[p] * gh[p].  grid T (one term per CTA), block EW_THREADS; fixed-order tree.
+struct ZernikeBwdParams {
+    const float4* gh;      // [NN4]
+    const float4* Z;       // [T][NN4]
+    float* gcoef;          // [T]
+    int NN4;
+};
+
+template <class Exec>
+B200_HD void zernike_bwd_body(Exec& ex, const ZernikeBwdParams& p, float* red) {
+    const int j = ex.bx();
+    ex.phase([&](int tid) {
+        const float4* z = p.Z + static_cast<size_t>(j) * p.NN4;
+        float acc = 0.f;
+        int q = tid;
+        for (; q + 7 * EW_THREADS < p.NN4; q += 8 * EW_THREADS) {
+            float4 a[8], g[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = ld_ro(z + q + i * EW_THREADS);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = ld_ro(p.gh + q + i * EW_THREADS);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc += (a[i].x * g[i].x + a[i].y * g[i].y) + (a[i].z * g[i].z + a[i].w * g[i].w);
+        }
+        for (; q < p.NN4; q += EW_THREADS) {
+            const float4 a = ld_ro(z + q), g = ld_ro(p.gh + q);
+            acc += (a.x * g.x + a.y * g.y) + (a.z * g.z + a.w * g.w);
+        }
+        red[tid] = acc;
+    });
+    for (int half = EW_THREADS / 2; half > 0; half /= 2) {
+        ex.phase([&](int tid) {
+            if (tid < half) red[tid] += red[tid + half];
+        });
+    }
+    ex.phase([&](int tid) {
+        if (tid == 0) p.gcoef[j] = red[0];
+    });
+}
+
 }  // namespace b200cam

@@ -42,6 +42,7 @@ class DevicePlan:
             self.kappa_list = list(t.kappa)
             self._psf_ws = torch.empty(self.lib.b200cam_psf_workspace_bytes(N), dtype=torch.uint8, device=device)
         self._sensor_ws: dict[int, torch.Tensor] = {}
+        self._zernike_ws: dict[tuple[int, int], torch.Tensor] = {}
         self.otf_floats = self.lib.b200cam_otf_bytes(N) // 4
         self.process_group = None      # set by Camera.data_parallel(): all-reduce dL/dh over ranks
         self.average_grads = True
@@ -79,6 +80,15 @@ class DevicePlan:
 
     def psf_workspace(self) -> torch.Tensor:
         return self._psf_ws
+
+    def zernike_workspace(self, T: int, NN: int) -> torch.Tensor:
+        """Zero-filled once (arrival counters live in it); the kernel leaves it reusable."""
+        key = (T, NN)
+        ws = self._zernike_ws.get(key)
+        if ws is None:
+            ws = torch.zeros(self.lib.b200cam_zernike_workspace_bytes(T, NN), dtype=torch.uint8, device=self.device)
+            self._zernike_ws = {key: ws}
+        return ws
 
     def sensor_workspace(self, B: int) -> torch.Tensor:
         ws = self._sensor_ws.get(B)
@@ -171,6 +181,41 @@ class PsfSynth(torch.autograd.Function):
             from .parallel import allreduce_height_grad
             allreduce_height_grad(grad_h, plan.process_group, plan.average_grads)
         return grad_h.reshape(ctx.h_shape), None, None
+
+
+class ZernikeProject(torch.autograd.Function):
+    """h = sum_j coef_j * Z_j (``get_Heith_Map``, ``Face-DeId/Camera/Optics.py:79-83``; ``Image_Caption/Camera/Lens.py:176``)
+    and its adjoint, one pass over the basis volume each way."""
+
+    @staticmethod
+    def forward(ctx, coef: torch.Tensor, volume: torch.Tensor, plan: DevicePlan):
+        T = volume.shape[0]
+        NN = volume[0].numel()
+        c = _as_f32(coef.detach(), plan.device).reshape(T)
+        Z = _as_f32(volume.detach(), plan.device)
+        h = torch.empty(volume.shape[1:], dtype=torch.float32, device=plan.device)
+        ws = plan.zernike_workspace(T, NN)
+        with torch.cuda.device(plan.index):
+            _lib.check(plan.lib.b200cam_zernike_fwd(_lib.ptr(c), _lib.ptr(Z), _lib.ptr(h), _lib.ptr(ws), ws.numel(), T, NN, _stream()))
+        ctx.plan = plan
+        ctx.coef_shape = coef.shape
+        ctx.save_for_backward(Z)
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        plan: DevicePlan = ctx.plan
+        (Z,) = ctx.saved_tensors
+        T, NN = Z.shape[0], Z[0].numel()
+        g = _as_f32(gh, plan.device)
+        gc = torch.empty(T, dtype=torch.float32, device=plan.device)
+        with torch.cuda.device(plan.index):
+            _lib.check(plan.lib.b200cam_zernike_bwd(_lib.ptr(g), _lib.ptr(Z), _lib.ptr(gc), T, NN, _stream()))
+        return gc.reshape(ctx.coef_shape), None, None
+
+
+def zernike_project(coef: torch.Tensor, volume: torch.Tensor, plan: DevicePlan) -> torch.Tensor:
+    return ZernikeProject.apply(coef, volume, plan)
 
 
 def _check_img(img: torch.Tensor, N: int) -> None:

@@ -116,7 +116,10 @@ class Camera(nn.Module):
         volume = self.zernike_volume
         if volume.device != zernike_coeffs_concat.device:
             volume = self.zernike_volume = volume.to(zernike_coeffs_concat.device)
-        height_map = torch.sum(zernike_coeffs_concat * volume, dim=0)
+        if zernike_coeffs_concat.is_cuda and volume.dtype == torch.float32 and volume.is_contiguous() and (self.N * self.N) % 4 == 0:
+            # one pass over the basis volume (b200cam_zernike_fwd / _bwd) instead of materialising coef * volume
+            return F.zernike_project(zernike_coeffs_concat, volume, self._plan(volume.device)).unsqueeze(0)
+        height_map = torch.sum(zernike_coeffs_concat * volume, dim=0)     # CPU tensors: the reference's expression
         return height_map.unsqueeze(0)
 
     def load_ckpt(self):

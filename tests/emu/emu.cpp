@@ -315,4 +315,23 @@ int emu_sensor_bwd(int N, int B, const float* g, const float* img, const float* 
                                         grad_psf, grad_img)));
 }
 
+// Zernike projection bodies: forward with an odd K split, adjoint
+int emu_zernike(int T, int NN, const float* coef, const float* Z, float* h, const float* gh, float* gcoef) {
+    const int NN4 = NN / 4, xblocks = (NN4 + EW_THREADS - 1) / EW_THREADS, KS = T < 3 ? 1 : 3;
+    std::vector<float4> partial(static_cast<size_t>(KS) * NN4);
+    std::vector<int> arrive(xblocks, 0);
+    int flag = 0;
+    grid2(xblocks, KS, EW_THREADS, [&](HostExec& ex) {
+        zernike_fwd_body(ex, ZernikeFwdParams{coef, reinterpret_cast<const float4*>(Z), partial.data(),
+                                              reinterpret_cast<float4*>(h), arrive.data(), T, NN4, KS}, &flag);
+    });
+    for (int a : arrive) if (a != 0) return -9;      // counters must be left at zero
+    std::vector<float> red(EW_THREADS);
+    grid2(T, 1, EW_THREADS, [&](HostExec& ex) {
+        zernike_bwd_body(ex, ZernikeBwdParams{reinterpret_cast<const float4*>(gh), reinterpret_cast<const float4*>(Z), gcoef, NN4},
+                         red.data());
+    });
+    return 0;
+}
+
 }  // extern "C"

@@ -99,3 +99,13 @@ def sensor_bwd(g, img, sensor, img_max, tie_count, tie_pos, psf, otf, want_img_g
                               _p(tie_pos), _p(psf.contiguous()), _p(otf), _p(spectrum), _p(gpsf), _p(gimg))
     assert rc == 0
     return gpsf, gimg
+
+
+def zernike(coef, Z, gh):
+    """(h, gcoef) through the emulated projection bodies."""
+    T, NN = Z.shape[0], Z[0].numel()
+    h = torch.empty(Z.shape[1:])
+    gc = torch.empty(T)
+    rc = lib().emu_zernike(T, NN, _p(coef.contiguous()), _p(Z.contiguous()), _p(h), _p(gh.contiguous()), _p(gc))
+    assert rc == 0
+    return h, gc

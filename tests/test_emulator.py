@@ -74,3 +74,15 @@ def test_emulated_tie_splitting():
     assert sorted(tp[0, :2].tolist()) == sorted([0 * N * N + 5 * N + 7, 2 * N * N + 40 * N + 9])
     assert rel_l2(gpsf, gpsf_o[0]) <= 1e-5
     assert rel_l2(gimg, gimg_o) <= 1e-5
+
+
+@pytest.mark.parametrize("T,N", [(7, 16), (40, 64)])
+def test_emulated_zernike_projection(T, N):
+    """h = sum_j coef_j Z_j (Optics.py:79-83) and its adjoint, kernel bodies on the CPU emulator."""
+    g = torch.Generator().manual_seed(3)
+    Z = torch.randn(T, N, N, generator=g)
+    c = torch.randn(T, generator=g)
+    gh = torch.randn(N, N, generator=g)
+    h, gc = emu.zernike(c, Z, gh)
+    assert rel_l2(h, (c[:, None, None] * Z).sum(0)) <= 1e-6
+    assert rel_l2(gc, (Z * gh).sum((1, 2))) <= 1e-6

@@ -289,3 +289,42 @@ def test_fused_kernels_forced(B):
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("REL")][-1].split()
     e_sensor, e_grad, e_img = float(line[1]), float(line[2]), float(line[3])
     assert e_sensor <= TOL_SENSOR and e_grad <= TOL_GRAD and e_img <= TOL_GRAD
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,N", [(12, 64), (300, 256), (37, 128)])
+def test_zernike_projection_matches_torch(T, N):
+    """h = sum_j coef_j Z_j (Optics.py:79-83) and its adjoint through the C ABI vs the reference's
+    torch expression and autograd.  Tolerance: rel-L2 <= 1e-5 (fp32 sums of T / N*N terms in a different order)."""
+    from b200cam import functional as F
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    Z = (torch.randn(T, N, N, generator=g) * 1e-6).to(dev)
+    c_ref = torch.randn(T, 1, 1, generator=g).to(dev).requires_grad_(True)
+    c_new = c_ref.detach().clone().requires_grad_(True)
+    w = torch.randn(N, N, generator=g).to(dev)
+    plan = F.DevicePlan(N, dev)
+    h_ref = torch.sum(c_ref * Z, dim=0)
+    h_new = F.zernike_project(c_new, Z, plan)
+    assert rel_l2(h_new, h_ref) <= 1e-5
+    (h_ref * w).sum().backward()
+    (h_new * w).sum().backward()
+    assert c_new.grad.shape == c_ref.grad.shape
+    assert rel_l2(c_new.grad, c_ref.grad) <= 1e-5
+    # second call reuses the workspace (arrival counters must have been left at zero)
+    assert torch.equal(F.zernike_project(c_new, Z, plan), h_new)
+
+
+@pytest.mark.gpu
+def test_camera_height_map_uses_projection_kernel_and_trains():
+    """The module's own get_Heith_Map (learned Zernike coefficients) -> forward -> backward reaches Zer_train."""
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    cam = Camera(device=dev, N=64, zernike_terms=20)
+    img = synth.images(2, 64).to(dev)
+    y = cam(img)
+    (y.sum() + cam.loss_rad + cam.centering_loss).backward()
+    assert cam.Zer_train.grad is not None and torch.isfinite(cam.Zer_train.grad).all()
+    assert float(cam.Zer_train.grad.abs().max()) > 0
+    h_ref = torch.sum(torch.cat((cam.Zer_no_train, cam.Zer_train), 0) * cam.zernike_volume, dim=0)
+    assert rel_l2(cam.get_Heith_Map()[0], h_ref) <= 1e-5
