@@ -128,13 +128,18 @@ template <int N>
 struct RowsStreamSmem {
     using R = RowsR2CSmem<N>;
     using T = Tile<N>;
-    static constexpr int TILE_FLOATS = T::ROWS * N;
-    static constexpr int TILE_BYTES = TILE_FLOATS * 4;
+    // Each image row is copied by its own bulk copy into a staging row of pitch N + 8 floats: the two row pairs that
+    // share a warp then read from banks 16 apart (with contiguous rows, 2N floats = 0 mod 32 banks put them on the SAME
+    // banks: ncu showed a quarter of this kernel's shared-memory wavefronts to be such conflicts).
+    static constexpr int ROW_PITCH = N + 8;                                   // floats; 4*ROW_PITCH is a multiple of 16 bytes
+    static constexpr int TILE_FLOATS = T::ROWS * ROW_PITCH;
+    static constexpr int TILE_BYTES = T::ROWS * N * 4;                        // bytes that arrive per tile
     static constexpr int STAGE_OFF = (R::RED_OFF + 15) / 16 * 16;            // float2 units, 128-byte aligned
     static constexpr int BAR_OFF = STAGE_OFF + TILE_FLOATS;                   // two tiles of floats = TILE_FLOATS float2
     static constexpr int FLOAT2S = BAR_OFF + 2;                               // two 8-byte mbarriers
     static constexpr int BYTES = FLOAT2S * 8;
     static constexpr int THREADS = R::THREADS;
+    static_assert(T::ROWS <= R::THREADS, "one issuing thread per row");
 };
 
 template <int N, class Exec>
@@ -150,19 +155,24 @@ B200_HD void rows_r2c_stream_body(Exec& ex, const RowsR2CParams& p, float2* smem
     RowState<N> st[Exec::IS_HOST ? S::THREADS : 1];
     float2 wreg[RT ? P::R1 : 1];
     const int first = ex.bx();
-    auto tile_src = [&](int t) { return p.x + static_cast<size_t>(t) * Q::TILE_FLOATS; };   // tiles are contiguous in x
+    // thread r < ROWS copies row r of tile t (tiles are contiguous in x) into staging buffer `buf`; thread 0 arms the barrier
+    auto issue = [&](int tid, int t, int buf) {
+        if (tid == 0) ex.bulk_expect(bars + buf, Q::TILE_BYTES);
+        if (tid < T::ROWS)
+            ex.bulk_load(stage + buf * Q::TILE_FLOATS + tid * Q::ROW_PITCH, p.x + (static_cast<size_t>(t) * T::ROWS + tid) * N, N * 4,
+                         bars + buf);
+    };
 
     ex.phase([&](int tid) {
         if (tid == 0) {
             ex.bulk_init(bars + 0);
             ex.bulk_init(bars + 1);
             ex.bulk_fence_init();
-            if (first < total_tiles) {
-                ex.bulk_expect(bars + 0, Q::TILE_BYTES);
-                ex.bulk_load(stage, tile_src(first), Q::TILE_BYTES, bars + 0);
-            }
         }
         if constexpr (RT && !Exec::IS_HOST) P::load_tw(wreg, p.tw, tid % P::LANES);
+    });
+    ex.phase([&](int tid) {
+        if (first < total_tiles) issue(tid, first, 0);
     });
     int it = 0;
     for (int t = first; t < total_tiles; t += nctas, ++it) {
@@ -171,15 +181,12 @@ B200_HD void rows_r2c_stream_body(Exec& ex, const RowsR2CParams& p, float2* smem
         const int y0 = tile * T::ROWS;
         ex.warp_phase([&](int tid) {
             // the other buffer was last read two block barriers ago: refill it with this CTA's next tile
-            if (tid == 0 && t + nctas < total_tiles) {
-                ex.bulk_expect(bars + (buf ^ 1), Q::TILE_BYTES);
-                ex.bulk_load(stage + (buf ^ 1) * Q::TILE_FLOATS, tile_src(t + nctas), Q::TILE_BYTES, bars + (buf ^ 1));
-            }
+            if (t + nctas < total_tiles) issue(tid, t + nctas, buf ^ 1);
             ex.bulk_wait(bars + buf, (it >> 1) & 1);
             const int j = tid / P::LANES, a = tid % P::LANES;
             if (a < P::R2) {
-                const float* r0 = stage + buf * Q::TILE_FLOATS + (2 * j) * N;
-                const float* r1 = r0 + N;
+                const float* r0 = stage + buf * Q::TILE_FLOATS + (2 * j) * Q::ROW_PITCH;
+                const float* r1 = r0 + Q::ROW_PITCH;
                 float2 v[P::R1];
 #pragma unroll
                 for (int i = 0; i < P::R1; ++i) v[i] = make_float2(r0[P::R2 * i + a], r1[P::R2 * i + a]);
