@@ -808,8 +808,9 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
             const int total = (N / T::ROWS) * planes;
             const int sms = sm_count() > 0 ? sm_count() : 148;
             const int grid = total < sms * per_sm ? total : sms * per_sm;
+            static const int discard = [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }();
             k_rows_c2r_persist<N><<<grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s>>>(
-                RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0}, total);
+                RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0, discard}, total);
         } else {
             k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
                 RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0});
@@ -997,7 +998,8 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     const int nchunks = accum_chunks(N, B);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     k_cols_accum<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
-        ColsAccumParams{srow, ws.stg, ws.partial, tw, img_max, otf, ws.dot_lanes, B, nchunks});
+        ColsAccumParams{srow, ws.stg, ws.partial, tw, img_max, otf, ws.dot_lanes, B, nchunks,
+                        grad_img == nullptr ? [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }() : 0});
     LAUNCH_CHECK();
     k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
         ColsReduceInvParams{ws.partial, ws.stp, tw, nchunks, 1.0f / (static_cast<float>(N) * N),

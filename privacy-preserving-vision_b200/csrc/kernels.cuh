@@ -449,6 +449,7 @@ struct RowsC2RParams {
     int* tie_count;      // [planes/3], zero on entry
     int* tie_pos;        // [planes/3][MAX_TIES] flat index into (3,N,N)
     int norm;
+    int discard_input;   // stream kernel: `st` is dead after this pass - drop its lines from L2 instead of writing them back
 };
 
 template <int N, class Exec>
@@ -618,6 +619,9 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
                 issue(tid, t + nctas, buf ^ 1);
             }
             ex.bulk_wait(bars + buf, (it >> 1) & 1);
+            if (p.discard_input && Q::SEG * 8 == 128)
+                for (int u = tid; u < T::NC; u += S::THREADS)
+                    discard_line(p.st + (static_cast<size_t>(plane) * T::NC + u) * N + y0);
             const float2* sg = stage + buf * STAGE_STRIDE;
             for (int w = tid; w < T::NP * T::NC; w += S::THREADS) {
                 const int u = w / T::NP, j = w % T::NP;
@@ -764,6 +768,7 @@ struct ColsAccumParams {
     float* dot_lanes;       // [B][3*NC][R1]
     int B;
     int nchunks;            // = gridDim.y: chunk y owns images [B*y/nchunks, B*(y+1)/nchunks) (balanced split)
+    int discard_stg;        // stg is dead after this pass: drop its lines from L2 instead of writing them back
 };
 
 template <int N>
@@ -817,7 +822,15 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
             const int jc = tid / P::LANES, a = tid % P::LANES;
             const int cu = cu0 + jc;
             if constexpr (S::STAGED_ACCUM) {
-                if (cu0 + (tid / 32) * S::WCOLS < TOTAL) ex.bulk_wait(bars + tid / 32, (b - b0) & 1);
+                if (cu0 + (tid / 32) * S::WCOLS < TOTAL) {
+                    ex.bulk_wait(bars + tid / 32, (b - b0) & 1);
+                    if (p.discard_stg) {             // the warp's WCOLS columns = WCOLS*N*8 bytes, one 128-byte line per lane and pass
+                        const int wcu = cu0 + (tid / 32) * S::WCOLS;
+                        const int ncols = TOTAL - wcu < S::WCOLS ? TOTAL - wcu : S::WCOLS;
+                        const char* base = reinterpret_cast<const char*>(p.stg + (static_cast<size_t>(b) * TOTAL + wcu) * N);
+                        for (int ln = tid % 32; ln < ncols * N * 8 / 128; ln += 32) discard_line(base + ln * 128);
+                    }
+                }
             }
             if (cu < TOTAL && a < P::R2) {
                 const size_t off = (static_cast<size_t>(b) * TOTAL + cu) * N;
