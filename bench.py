@@ -201,6 +201,11 @@ def run_b200(args) -> None:
     N, B, R = args.size, args.batch, max(1, args.input_sets)
     lib = _lib.load_library()
 
+    # the camera's PSF chain runs on a side stream by design; autograd's advisory about it is not an error
+    try:
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    except AttributeError:
+        pass
     torch.manual_seed(0)
     cam = Camera(device=dev, N=N, zernike_terms=12)
     h = synth.height_map(N).to(dev).requires_grad_(True)     # "random height map" (configs[0..1])

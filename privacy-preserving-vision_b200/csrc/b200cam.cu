@@ -415,6 +415,7 @@ struct DeviceState {
     float2* tw[11] = {nullptr}; int sms = 0; int coop_grid[11] = {0}; unsigned* bar = nullptr;
     int conv_slots[11] = {0}, accum_slots[11] = {0};     // resident CTAs of the persistent column kernels
     cudaEvent_t chain_ev = nullptr;                      // orders a caller stream behind the first PSF-chain kernel
+    int r2c_fit[11] = {0}, c2r_fit[11] = {0};            // resident CTAs per SM of the persistent row kernels
 };
 static DeviceState g_state[MAX_DEV];
 static std::mutex g_mutex;
@@ -514,6 +515,12 @@ static cudaError_t coop_grid_size(int dev, int sms, int* out) {
 
 // resident CTAs (one wave) of the persistent column kernels on this device
 template <int N>
+static cudaError_t row_fits(int* r2c, int* c2r) {
+    cudaError_t e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(r2c, k_rows_r2c_persist<N>, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES))) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(c2r, k_rows_c2r_persist<N>, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES);
+}
+template <int N>
 static cudaError_t column_slots(int sms, int* conv, int* accum) {
     int nc = 0, na = 0;
     cudaError_t e;
@@ -522,6 +529,22 @@ static cudaError_t column_slots(int sms, int* conv, int* accum) {
     *conv = sms * nc;
     *accum = sms * na;
     return cudaSuccess;
+}
+
+// grid of a persistent row kernel: `want` CTAs per SM, never more than fit at once (a persistent grid larger than one
+// wave runs its surplus CTAs after the first ones have finished ALL their tiles), never more than there are tiles.
+// `fit` = resident CTAs per SM of that kernel, measured at init.
+static int persistent_grid(int fit, int want_per_sm, int total_tiles) {
+    if (fit < 1) fit = 1;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int per_sm = want_per_sm < fit ? want_per_sm : fit;
+    const long long cap = static_cast<long long>(sms) * per_sm;
+    return static_cast<int>(total_tiles < cap ? total_tiles : cap);
+}
+static int rows_fit(int N, bool inverse) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 1;
+    return inverse ? g_state[dev].c2r_fit[log2i(N)] : g_state[dev].r2c_fit[log2i(N)];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -776,8 +799,7 @@ static int sensor_rows_impl(const float* img, float2* srow, float* img_max, int*
     // B200CAM_ROWS_PER_SM resident CTAs per SM (default 3 of the 4 that fit): see k_rows_r2c_persist
     static const int per_sm = [] { const char* e = getenv("B200CAM_ROWS_PER_SM"); const int v = e ? atoi(e) : 3; return v > 0 ? v : 3; }();
     const int total = (N / T::ROWS) * 3 * B;
-    const int sms = sm_count() > 0 ? sm_count() : 148;
-    const int grid = total < sms * per_sm ? total : sms * per_sm;
+    const int grid = persistent_grid(rows_fit(N, false), per_sm, total);
     k_rows_r2c_persist<N><<<grid, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES, s>>>(
         RowsR2CParams{img, srow, tw, img_max, tie_count}, total);
     LAUNCH_CHECK();
@@ -806,8 +828,7 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
         static const int per_sm = [] { const char* e = getenv("B200CAM_C2R_PER_SM"); const int v = e ? atoi(e) : 4; return v; }();
         if (per_sm > 0) {
             const int total = (N / T::ROWS) * planes;
-            const int sms = sm_count() > 0 ? sm_count() : 148;
-            const int grid = total < sms * per_sm ? total : sms * per_sm;
+            const int grid = persistent_grid(rows_fit(N, true), per_sm, total);
             static const int discard = [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }();
             k_rows_c2r_persist<N><<<grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s>>>(
                 RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0, discard}, total);
@@ -986,8 +1007,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
         static const int per_sm = [] { const char* e = getenv("B200CAM_GROWS_PER_SM"); return e ? atoi(e) : 3; }();
         if (per_sm > 0) {
             const int total = tiles * planes;
-            const int sms = sm_count() > 0 ? sm_count() : 148;
-            const int grid = total < sms * per_sm ? total : sms * per_sm;
+            const int grid = persistent_grid(rows_fit(N, false), per_sm, total);
             k_rows_r2c_persist<N><<<grid, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES, s>>>(
                 RowsR2CParams{g, ws.stg, tw, nullptr, nullptr}, total);
         } else {
@@ -1123,6 +1143,17 @@ int b200cam_init(int N) {
             case 256: e = column_slots<256>(sms, cs, as); break;
             case 512: e = column_slots<512>(sms, cs, as); break;
             case 1024: e = column_slots<1024>(sms, cs, as); break;
+        }
+    }
+    if (e == cudaSuccess) {
+        int* rf = &g_state[dev].r2c_fit[l];
+        int* cf = &g_state[dev].c2r_fit[l];
+        switch (N) {
+            case 64: e = row_fits<64>(rf, cf); break;
+            case 128: e = row_fits<128>(rf, cf); break;
+            case 256: e = row_fits<256>(rf, cf); break;
+            case 512: e = row_fits<512>(rf, cf); break;
+            case 1024: e = row_fits<1024>(rf, cf); break;
         }
     }
     if (e != cudaSuccess) {

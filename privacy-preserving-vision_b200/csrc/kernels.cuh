@@ -19,7 +19,7 @@ namespace b200cam {
 
 template <int N>
 struct Tile {
-    static constexpr int ROWS = (N <= 256) ? 16 : 8;   // image rows per CTA in the row passes
+    static constexpr int ROWS = (N <= 512) ? 16 : 8;   // image rows per CTA in the row passes (16 rows = 128-byte spectrum segments)
     static constexpr int NP = ROWS / 2;                // real rows are transformed in pairs
     static constexpr int NC = N / 2 + 1;
     static constexpr int FP_PAIR = N + 16 / NP;        // natural-order smem row pitch (float2)

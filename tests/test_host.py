@@ -49,6 +49,16 @@ def test_abi_rejects_bad_arguments_before_touching_the_gpu(library):
     assert library.b200cam_psf_fwd(null, null, null, null, kappa, null, null, null, null, 0, 100, null) == -1
     assert library.b200cam_psf_fwd(null, null, null, null, kappa, null, null, null, null, 0, 256, null) == -2
     assert library.b200cam_sensor_fwd(null, null, null, null, null, null, null, null, null, 0, 0, 256, null) == -1
+    # the split PSF entry points and the Zernike projection validate the same way
+    assert library.b200cam_psf_field(null, null, null, kappa, null, null, 0, 100, null, null, 0) == -1
+    assert library.b200cam_psf_field(null, null, null, kappa, null, null, 0, 256, null, null, 0) == -2
+    assert library.b200cam_psf_otf_early(null, null, 0, 256, null) == -2
+    assert library.b200cam_psf_finish(null, null, null, null, 0, 256, null) == -2
+    assert library.b200cam_zernike_workspace_bytes(300, 256 * 256) >= 256 * 256 * 4
+    assert library.b200cam_zernike_workspace_bytes(300, 6) == 0                 # N*N must be a multiple of 4
+    assert library.b200cam_zernike_fwd(null, null, null, null, 0, 300, 6, null) == -1
+    assert library.b200cam_zernike_fwd(null, null, null, null, 0, 300, 65536, null) == -2
+    assert library.b200cam_zernike_bwd(null, null, null, 0, 65536, null) == -1
 
 
 def test_no_cpu_fallback():
