@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(RowsC2RStreamSmem<N>::THREADS) k_rows_c2r_pers
     rows_c2r_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
 }
 template <int N>
-__global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 4 : 1) k_cols_conv(ColsConvParams p) {
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 4 : (N == 512 ? 2 : 1)) k_cols_conv(ColsConvParams p) {
     DeviceExec ex;
     ConvState<N> st;
     cols_conv_body<N>(ex, p, SMEM2, &st);
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_normalise(NormaliseParams p) {
     normalise_body(ex, p, gridDim.x);
 }
 template <int N>
-__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_accum(ColsAccumParams p) {
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 3 : 1) k_cols_accum(ColsAccumParams p) {
     DeviceExec ex;
     AccumState<N> st;
     cols_accum_body<N>(ex, p, SMEM2, &st);

@@ -23,7 +23,7 @@ template <int N> struct Factor;
 template <> struct Factor<64> { static constexpr int R1 = 8, R2 = 8; };
 template <> struct Factor<128> { static constexpr int R1 = 8, R2 = 16; };
 template <> struct Factor<256> { static constexpr int R1 = 16, R2 = 16; };
-template <> struct Factor<512> { static constexpr int R1 = 16, R2 = 32; };
+template <> struct Factor<512> { static constexpr int R1 = 32, R2 = 16; };   // R2 sizes the per-thread state of the point-wise stage
 template <> struct Factor<1024> { static constexpr int R1 = 32, R2 = 32; };
 
 template <int N>
