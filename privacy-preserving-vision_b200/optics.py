@@ -140,6 +140,11 @@ class Camera(nn.Module):
         return self.psfs
 
     def forward(self, img):
+        # uint8 images (what a decoder produces; the reference's loader turns them into fp32 in [0,1] with ToTensor on the
+        # host, Face-DeId/core/data_loader.py:118-124) may be passed as they are: the division by 255 then happens on the
+        # GPU and the host->device copy is a quarter of the fp32 one.
+        if torch.is_tensor(img) and img.dtype == torch.uint8 and img.is_cuda:
+            img = img.to(torch.float32).div_(255.0)
         # The PSF synthesis is a chain of small latency-bound kernels and the row transforms of the images do not
         # depend on it: put the chain on a high-priority side stream, run the row pass on the current stream meanwhile
         # and join before the spectral product.

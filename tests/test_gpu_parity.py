@@ -328,3 +328,15 @@ def test_camera_height_map_uses_projection_kernel_and_trains():
     assert float(cam.Zer_train.grad.abs().max()) > 0
     h_ref = torch.sum(torch.cat((cam.Zer_no_train, cam.Zer_train), 0) * cam.zernike_volume, dim=0)
     assert rel_l2(cam.get_Heith_Map()[0], h_ref) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_uint8_images_are_scaled_on_the_gpu():
+    """uint8 input == the reference loader's ToTensor (x/255, Face-DeId/core/data_loader.py:118-124) followed by forward."""
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    cam = Camera(device=dev, N=64, zernike_terms=12)
+    u8 = (synth.images(3, 64) * 255).round().to(torch.uint8).to(dev)
+    y8 = cam(u8)
+    yf = cam(u8.float() / 255.0)
+    assert torch.equal(y8, yf)
