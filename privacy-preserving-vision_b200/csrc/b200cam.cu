@@ -94,11 +94,6 @@ __global__ void __launch_bounds__(CRowsSmem<N>::THREADS) k_crows_inv(CRowsInvPar
     DeviceExec ex;
     crows_inv_body<N>(ex, p, epi, SMEM2);
 }
-__global__ void __launch_bounds__(EW_THREADS) k_reduce(ReduceParams p) {
-    __shared__ float red[3 * EW_THREADS];
-    DeviceExec ex;
-    reduce_body(ex, p, red);
-}
 template <int N>
 __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad(CRowsInvParams p, PupilLoad pupil, float* gh) {
     DeviceExec ex;
@@ -178,10 +173,6 @@ __global__ void __launch_bounds__(EW_THREADS) k_psf_grad_prepare(PsfGradPrepPara
     __shared__ float red[EW_THREADS];
     DeviceExec ex;
     psf_grad_prepare_body(ex, p, gridDim.x, red);
-}
-__global__ void __launch_bounds__(EW_THREADS) k_sum3(Sum3Params p) {
-    DeviceExec ex;
-    sum3_body(ex, p, gridDim.x);
 }
 __global__ void __launch_bounds__(f256::THREADS, 1) k_f256_fwd(f256::FwdParams p) { f256::fwd_kernel_body(p, SMEM2); }
 __global__ void __launch_bounds__(EW_THREADS) k_f256_norm(f256::NormParams p) { f256::norm_kernel_body(p); }

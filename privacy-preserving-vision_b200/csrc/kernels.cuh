@@ -1389,20 +1389,6 @@ struct IntensityEpilogue {
     }
 };
 
-// backward epilogue: dL/dh contribution of one wavelength: kappa_l * Im(GV * conj(V)), V recomputed
-struct HeightGradEpilogue {
-    PupilLoad pupil;
-    float* gh3;         // [3][N][N]
-    int N;
-    B200_HD float operator()(int l, int y, int x, float2 gv) const {
-        const float2 v = pupil(l, y, x);
-        const float2 t = cmulc(gv, v);
-        gh3[(static_cast<size_t>(l) * N + y) * N + x] = pupil.kap(l) * t.y;
-        return 0.f;
-    }
-    B200_HD void finish(int, int, int, float) const {}
-};
-
 template <int N, class Epi, class Exec>
 B200_HD void crows_inv_body(Exec& ex, const CRowsInvParams& p, const Epi& epi, float2* smem) {
     using P = Plan<N>;
@@ -1548,43 +1534,6 @@ B200_HD void crows_inv_hgrad_body(Exec& ex, const CRowsInvParams& p, const Pupil
 // ---------------------------------------------------------------------------------------------
 constexpr int EW_THREADS = 256;
 
-struct ReduceParams {
-    const float* partial;  // [count]
-    float* scal;
-    int count;
-    int mode;              // 0: scal[0] = sum ; 1: PSF losses from 3 interleaved partial sets ; 2: scal[3] = sum
-    int N;
-};
-
-// single CTA, deterministic tree (fixed thread->element map, fixed tree)
-template <class Exec>
-B200_HD void reduce_body(Exec& ex, const ReduceParams& p, float* red) {
-    const int nsets = (p.mode == 1) ? 3 : 1;
-    ex.phase([&](int tid) {
-        for (int s = 0; s < nsets; ++s) {
-            float acc = 0.f;
-            for (int i = tid; i < p.count; i += EW_THREADS) acc += p.partial[s * p.count + i];
-            red[s * EW_THREADS + tid] = acc;
-        }
-    });
-    for (int half = EW_THREADS / 2; half > 0; half /= 2) {
-        ex.phase([&](int tid) {
-            if (tid < half)
-                for (int s = 0; s < nsets; ++s) red[s * EW_THREADS + tid] += red[s * EW_THREADS + tid + half];
-        });
-    }
-    ex.phase([&](int tid) {
-        if (tid == 0) {
-            if (p.mode == 0) p.scal[0] = red[0];
-            else if (p.mode == 2) p.scal[3] = red[0];
-            else {
-                p.scal[1] = sqrtf(red[0]);                                                     // Optics.py:113
-                p.scal[2] = red[EW_THREADS] / (3.0f * p.N * p.N) + red[2 * EW_THREADS] / (3.0f * p.N * p.N);  // :124-125
-            }
-        }
-    });
-}
-
 // P4  psf_finalise: psf = I/S (Optics.py:110); partial sums for loss_rad (:113) and the centering loss (:124-125)
 struct PsfFinaliseParams {
     const float* I;        // [3][N][N]
@@ -1725,20 +1674,6 @@ B200_HD void psf_grad_prepare_body(Exec& ex, const PsfGradPrepParams& p, int gri
     });
 }
 
-// Q5  sum3: gh = gh3[0] + gh3[1] + gh3[2]   (sum over wavelengths of Optics.py:89-90's adjoint)
-struct Sum3Params {
-    const float* gh3;
-    float* gh;
-    int NN;
-};
-template <class Exec>
-B200_HD void sum3_body(Exec& ex, const Sum3Params& p, int grid_x) {
-    ex.phase([&](int tid) {
-        const int stride = grid_x * EW_THREADS;
-        for (int i = ex.bx() * EW_THREADS + tid; i < p.NN; i += stride)
-            p.gh[i] = (p.gh3[i] + p.gh3[p.NN + i]) + p.gh3[2 * p.NN + i];
-    });
-}
 
 // =============================================================================================
 //        Zernike projection  h = sum_j coef_j * Z_j   and its adjoint   
