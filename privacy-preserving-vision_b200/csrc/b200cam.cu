@@ -577,7 +577,7 @@ static int accum_chunks(int N, int B) {
 }
 
 struct PsfWs {
-    float2* st; float* I; float* gtot; float* gh3; float* part_rows; float* part_ew; int* arrive;
+    float2* st; float* I; float* gtot; float* part_rows; float* part_ew; int* arrive;
     size_t bytes;
     PsfWs(void* p, int N) {
         Carver c(p);
@@ -585,7 +585,6 @@ struct PsfWs {
         st = c.take<float2>(3 * NN);
         I = c.take<float>(3 * NN);
         gtot = c.take<float>(3 * NN);
-        gh3 = c.take<float>(3 * NN);
         part_rows = c.take<float>(3 * N);
         part_ew = c.take<float>(3 * 1024);          // element-wise partials: grid <= 1024 CTAs
         arrive = c.take<int>(1);
