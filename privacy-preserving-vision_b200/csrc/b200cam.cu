@@ -399,7 +399,12 @@ __global__ void k_fill_twiddle(float2* tw, int N) {
 // per-device state: twiddle tables (the only thing the library owns)
 // ------------------------------------------------------------------------------------------
 constexpr int MAX_DEV = 64;
-constexpr int EW_GRID = 296;   // 2 x 148 SMs for the element-wise / reduction kernels
+// grid of the element-wise PSF kernels: one pass of 256-thread CTAs over the 3*N*N elements, at most 1024 CTAs (the size
+// of their partial-sum slices in the workspace).  These kernels are latency chains: one element per thread where possible.
+static int ew_grid(int N) {
+    const long long want = (3LL * N * N + EW_THREADS - 1) / EW_THREADS;
+    return static_cast<int>(want < 1024 ? want : 1024);
+}
 
 inline int log2i(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
 struct DeviceState {
@@ -673,7 +678,7 @@ static int psf_field_impl(const float* h, const float2* A, const float2* Ht, con
 template <int N>
 static int psf_finish_impl(const float* rho, float* psf, float* stats, void* ws_ptr, cudaStream_t s) {
     PsfWs ws(ws_ptr, N);
-    k_psf_finalise<<<EW_GRID, EW_THREADS, 0, s>>>(PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, 3 * (N / Tile<N>::CROWS), N});
+    k_psf_finalise<<<ew_grid(N), EW_THREADS, 0, s>>>(PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, 3 * (N / Tile<N>::CROWS), N});
     LAUNCH_CHECK();
     return 0;
 }
@@ -723,10 +728,10 @@ static int psf_bwd_impl(const float* gpsf, const float* g_rad, const float* g_ce
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
-    k_psf_grad_prepare<<<EW_GRID, EW_THREADS, 0, s>>>(PsfGradPrepParams{gpsf, g_rad, g_cen, psf, rho, stats, ws.gtot, ws.part_ew, N});
+    k_psf_grad_prepare<<<ew_grid(N), EW_THREADS, 0, s>>>(PsfGradPrepParams{gpsf, g_rad, g_cen, psf, rho, stats, ws.gtot, ws.part_ew, N});
     LAUNCH_CHECK();
     k_crows_fwd<N, GradFieldLoad><<<dim3(N / T::CROWS, 3), CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(
-        rf, GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, EW_GRID, N});
+        rf, GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, ew_grid(N), N});
     LAUNCH_CHECK();
     k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(mix);
     LAUNCH_CHECK();
