@@ -1016,7 +1016,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
         ColsAccumParams{srow, ws.stg, ws.partial, tw, img_max, otf, ws.dot_lanes, B, nchunks,
                         grad_img == nullptr ? [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }() : 0});
     LAUNCH_CHECK();
-    k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
+    k_cols_reduce_inv<N><<<3 * T::NC + B, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
         ColsReduceInvParams{ws.partial, ws.stp, tw, nchunks, 1.0f / (static_cast<float>(N) * N),
                             ws.dot_lanes, img_max, tie_count, ws.coef, B});
     LAUNCH_CHECK();

@@ -906,7 +906,7 @@ struct ColsReduceInvParams {
     const float2* tw;
     int nchunks;
     float scale;
-    // side job (dot_lanes != nullptr): CTA i also reduces image i's partials of sum(g*conv) written by K6 into
+    // side job (dot_lanes != nullptr, grid = 3*NC + B): CTA 3*NC + b reduces image b's partials of sum(g*conv) written by K6 into
     //   coef[b] = sum(g_b*y_b) / (n_b m_b) = sum(g_b*conv_b) / (n_b m_b^2)     (weight of the arg-max term, Optics.py:128)
     const float* dot_lanes;  // nullable [B][3*NC*R1]
     const float* img_max;    // [B]
@@ -934,33 +934,43 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
     const int cu = ex.bx();
     constexpr int TOTAL = 3 * T::NC;
     const int u = cu % T::NC;
-    if (p.dot_lanes != nullptr) {
+    if (cu >= TOTAL) {
+        // extra CTAs (grid = 3*NC + B when dot_lanes is given): CTA TOTAL + b reduces image b's Parseval partials, beside -
+        // not in front of - the column work of the other CTAs
         constexpr int PER_IMAGE = TOTAL * P::R1;
-        float* red = reinterpret_cast<float*>(E);            // N floats of scratch (E is free until the second phase below)
-        for (int b = cu; b < p.B; b += TOTAL) {
-            ex.phase([&](int t) {
-                const float* src = p.dot_lanes + static_cast<size_t>(b) * PER_IMAGE;
+        float* red = reinterpret_cast<float*>(E);
+        const int b = cu - TOTAL;
+        ex.phase([&](int t) {
+            const float* src = p.dot_lanes + static_cast<size_t>(b) * PER_IMAGE;
+            float s = 0.f;
+            int i = t;
+            for (; i + 7 * N < PER_IMAGE; i += 8 * N) {              // eight loads in flight; fixed order: deterministic
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = src[i + k * N];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s += v[k];
+            }
+            for (; i < PER_IMAGE; i += N) s += src[i];
+            red[t] = s;
+        });
+        ex.phase([&](int t) {
+            if (t < 16) {
                 float s = 0.f;
-                for (int i = t; i < PER_IMAGE; i += N) s += src[i];      // fixed order: deterministic
-                red[t] = s;
-            });
-            ex.phase([&](int t) {
-                if (t < 16) {
-                    float s = 0.f;
-                    for (int i = t; i < N; i += 16) s += red[i];
-                    red[N + t] = s;
-                }
-            });
-            ex.phase([&](int t) {
-                if (t == 0) {
-                    float s = 0.f;
-                    for (int i = 0; i < 16; ++i) s += red[N + i];
-                    const int n = p.tie_count[b] > 0 ? p.tie_count[b] : 1;
-                    const float m = p.img_max[b];
-                    p.coef[b] = s / (static_cast<float>(n) * m * m);
-                }
-            });
-        }
+                for (int i = t; i < N; i += 16) s += red[i];
+                red[N + t] = s;
+            }
+        });
+        ex.phase([&](int t) {
+            if (t == 0) {
+                float s = 0.f;
+                for (int i = 0; i < 16; ++i) s += red[N + i];
+                const int n = p.tie_count[b] > 0 ? p.tie_count[b] : 1;
+                const float m = p.img_max[b];
+                p.coef[b] = s / (static_cast<float>(n) * m * m);
+            }
+        });
+        return;
     }
     ex.phase([&](int v) {
         const float2* src = p.partial + static_cast<size_t>(cu) * N + v;

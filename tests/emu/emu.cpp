@@ -135,7 +135,7 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
                                                dot_lanes.data(), B, nchunks}, smem.data(), states.data());
     });
     std::vector<float2> rsmem(ReduceInvSmem<N>::FLOAT2S);
-    grid2(3 * T::NC, 1, ReduceInvSmem<N>::THREADS, [&](HostExec& ex) {
+    grid2(3 * T::NC + B, 1, ReduceInvSmem<N>::THREADS, [&](HostExec& ex) {
         cols_reduce_inv_body<N>(ex, ColsReduceInvParams{partial.data(), stp.data(), tw.data(), used_chunks,
                                                         1.0f / (static_cast<float>(N) * N), dot_lanes.data(), img_max,
                                                         tie_count, coef.data(), B}, rsmem.data());
