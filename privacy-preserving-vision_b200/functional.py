@@ -12,6 +12,7 @@ PyTorch owns every buffer (outputs, saved tensors, scratch); the library only en
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -99,6 +100,11 @@ class DevicePlan:
         return ws
 
 
+# 1: the caller's image row pass is ordered behind the first PSF kernel (see b200cam_psf_field); B200CAM_HOLD_ROWS=0 lets
+# both start together (A/B switch)
+_HOLD_ROWS = 0 if os.environ.get("B200CAM_HOLD_ROWS", "1") == "0" else 1
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -135,7 +141,7 @@ class PsfSynth(torch.autograd.Function):
                 # pipeline that waits for `plan.otf_event` does not wait for the PSF to be written out
                 _lib.check(plan.lib.b200cam_psf_field(
                     _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), plan.kappa, _lib.ptr(field),
-                    _lib.ptr(ws), ws.numel(), N, launch, _stream(), 1))
+                    _lib.ptr(ws), ws.numel(), N, launch, _stream(), _HOLD_ROWS))
                 otf = torch.empty(plan.otf_floats, dtype=torch.float32, device=plan.device)
                 _lib.check(plan.lib.b200cam_psf_otf_early(_lib.ptr(otf), _lib.ptr(ws), ws.numel(), N, launch))
                 plan.otf_event = torch.cuda.Event()
