@@ -344,3 +344,29 @@ class OpticsZernike(nn.Module):
         import os
         ckpt = torch.load(os.path.expanduser(path), map_location=self.device)
         self.state_dict()['zernike_coeffs_train'].copy_(ckpt['model_state_dict']['optics.zernike_coeffs_train'])
+
+    def load_reference_state_dict(self, state: dict, strict: bool = True):
+        """Load a camera checkpoint in EITHER of the reference's two parameterisations:
+
+        * shipped module (``Lens.py:92-96``): ``zernike_coeffs_no_train`` (3,1,1), ``zernike_coeffs_train`` (1,1) - the
+          defocus term only - and ``zernike_coeffs_no_train2`` (T-4,1,1);
+        * ``Camera/Model.pth`` as ``train.py:71-78`` reads it (the commented-out layout of ``Lens.py:99-101``):
+          ``[optics.]zernike_coeffs_no_train`` (3,1,1) and ``[optics.]zernike_coeffs_train`` (T-3,1,1), i.e. every term
+          from the defocus on in one tensor.  The reference's own ``load_state_dict`` rejects this one; here its first
+          entry becomes the trainable defocus and the rest ``zernike_coeffs_no_train2``.
+
+        A leading ``optics.`` on the keys and a wrapping ``{'model': ...}`` / ``{'model_state_dict': ...}`` are accepted."""
+        for wrap in ("model", "model_state_dict"):
+            if isinstance(state, dict) and wrap in state and isinstance(state[wrap], dict):
+                state = state[wrap]
+        sd = {(k[len("optics."):] if k.startswith("optics.") else k): v for k, v in state.items()}
+        if "zernike_coeffs_no_train2" not in sd and "zernike_coeffs_train" in sd:
+            tr = torch.as_tensor(sd["zernike_coeffs_train"])
+            T = self.zernike_coeffs_no_train2.shape[0] + 4
+            if tr.dim() == 3 and tr.shape[0] == T - 3:                  # legacy 3 + (T-3) layout
+                sd = dict(sd)
+                sd["zernike_coeffs_train"] = tr[0].reshape(self.zernike_coeffs_train.shape)
+                sd["zernike_coeffs_no_train2"] = tr[1:]
+        keys = ("zernike_coeffs_no_train", "zernike_coeffs_train", "zernike_coeffs_no_train2")
+        return self.load_state_dict({k: sd[k] for k in keys if k in sd}, strict=strict)
+

@@ -118,3 +118,22 @@ def test_state_dict_roundtrip(tmp_path):
     b = Camera(N=64, zernike_terms=8)
     b.load_state_dict(torch.load(tmp_path / "cam.pth")["Camera"])  # solver.py:46-48
     assert torch.equal(a.Zer_train, b.Zer_train) and torch.equal(a.ca, b.ca)
+
+
+def test_caption_camera_loads_both_reference_checkpoint_layouts():
+    """the shipped 3+1+(T-4) layout (Lens.py:92-96) and Model.pth's 3+(T-3) layout with `optics.` keys
+    (train.py:71-78, Lens.py:99-101) load into the same module."""
+    from b200cam.lens import OpticsZernike
+    T = 12
+    cam = OpticsZernike(input_shape=[None, 16, 16, 3], device="cpu", zernike_terms=T, patch_size=16,
+                        wave_resolution=[32, 32], sample_interval=3e-6, height_tolerance=None)
+    g = torch.Generator().manual_seed(1)
+    full = torch.randn(T, 1, 1, generator=g)
+    legacy = {"model": {"optics.zernike_coeffs_no_train": full[:3].clone(), "optics.zernike_coeffs_train": full[3:].clone()}}
+    cam.load_reference_state_dict(legacy)
+    got = torch.cat((cam.zernike_coeffs_no_train, cam.zernike_coeffs_train.unsqueeze(0), cam.zernike_coeffs_no_train2), 0)
+    assert torch.equal(got.detach(), full)
+    assert cam.zernike_coeffs_train.shape == (1, 1) and cam.zernike_coeffs_train.requires_grad
+    shipped = {k: v.detach().clone() + 1.0 for k, v in cam.state_dict().items()}
+    cam.load_reference_state_dict(shipped)
+    assert torch.equal(cam.zernike_coeffs_no_train2.detach(), full[4:] + 1.0)
