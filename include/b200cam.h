@@ -49,6 +49,13 @@ size_t b200cam_sensor_workspace_bytes(int N, int B, int want_img_grad);
 /* size of the optional saved forward spectrum (row-transformed rfft of every image plane) */
 size_t b200cam_spectrum_bytes(int N, int B);
 
+/* Image_Caption sensor epilogue (img_psf_conv, Image_Caption/Camera/Utils.py:289-295): out = nearest-resize(crop(|conv|))
+ *   out[pl][i][j] = | conv[pl][off + max(i-1,0)][off + max(j-1,0)] |,  i, j < P;   conv is [planes][n][n]
+ * and its adjoint (grad_conv is written everywhere: zero outside the window; d|v|/dv = 0 at v == 0 as torch.abs). */
+int b200cam_crop_abs_resize_fwd(const float* conv, float* out, int planes, int n, int P, int off, void* stream);
+int b200cam_crop_abs_resize_bwd(const float* grad_out, const float* conv, float* grad_conv, int planes, int n, int P, int off,
+                                void* stream);
+
 /* Zernike projection (the step in front of the PSF synthesis in a training loop).
  *   h[p] = sum_j coef[j] * Z[j][p]      replaces `get_Heith_Map`, Face-DeId/Camera/Optics.py:79-83 and
  *                                        Image_Caption/Camera/Lens.py:176 (torch.sum(coef * volume, 0))

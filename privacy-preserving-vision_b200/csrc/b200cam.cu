@@ -386,6 +386,15 @@ __global__ void __launch_bounds__(EW_THREADS) k_zernike_bwd(ZernikeBwdParams p) 
     zernike_bwd_body(ex, p, red);
 }
 
+__global__ void __launch_bounds__(EW_THREADS) k_crop_abs_resize_fwd(CropAbsResizeParams p) {
+    DeviceExec ex;
+    crop_abs_resize_fwd_body(ex, p, gridDim.x);
+}
+__global__ void __launch_bounds__(EW_THREADS) k_crop_abs_resize_bwd(CropAbsResizeBwdParams p) {
+    DeviceExec ex;
+    crop_abs_resize_bwd_body(ex, p, gridDim.x);
+}
+
 __global__ void k_fill_twiddle(float2* tw, int N) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < N) {
@@ -1185,6 +1194,33 @@ int b200cam_psf_fwd(const float* h, const float* A, const float* Ht, const float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DISPATCH_N(N, (psf_fwd_impl<NN_>(h, reinterpret_cast<const float2*>(A), reinterpret_cast<const float2*>(Ht), rho,
                                      kappa, psf, reinterpret_cast<float2*>(field), stats, workspace, s)));
+}
+
+// ---- Image_Caption sensor epilogue -------------------------------------------------------------------------
+static int ew_blocks(long long elems) {
+    const long long want = (elems + EW_THREADS - 1) / EW_THREADS;
+    return static_cast<int>(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16);
+}
+
+int b200cam_crop_abs_resize_fwd(const float* conv, float* out, int planes, int n, int P, int off, void* stream) {
+    if (planes < 1 || n < 2 || P < 2 || off < 0 || off + P - 1 > n) return B200CAM_E_BAD_SIZE;
+    if (!conv || !out) return B200CAM_E_NULL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    k_crop_abs_resize_fwd<<<ew_blocks(static_cast<long long>(planes) * P * P), EW_THREADS, 0, s>>>(
+        CropAbsResizeParams{conv, out, planes, n, P, off});
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int b200cam_crop_abs_resize_bwd(const float* grad_out, const float* conv, float* grad_conv, int planes, int n, int P, int off,
+                                void* stream) {
+    if (planes < 1 || n < 2 || P < 2 || off < 0 || off + P - 1 > n) return B200CAM_E_BAD_SIZE;
+    if (!grad_out || !conv || !grad_conv) return B200CAM_E_NULL;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    k_crop_abs_resize_bwd<<<ew_blocks(static_cast<long long>(planes) * n * n), EW_THREADS, 0, s>>>(
+        CropAbsResizeBwdParams{grad_out, conv, grad_conv, planes, n, P, off});
+    LAUNCH_CHECK();
+    return 0;
 }
 
 // ---- Zernike projection ----------------------------------------------------------------------

@@ -1795,4 +1795,63 @@ B200_HD void zernike_bwd_body(Exec& ex, const ZernikeBwdParams& p, float* red) {
     });
 }
 
+// =============================================================================================
+//   Image_Caption sensor epilogue:  |.|, crop and nearest 255 -> 256 resize in one pass
+//   (img_psf_conv, Image_Caption/Camera/Utils.py:289-295:  abs -> [129:-128] crop -> nearest resize
+//    out[i] = crop[max(i-1, 0)])  and its adjoint.  Replaces five element-wise / gather torch kernels over the
+//    (B,3,2P,2P) convolution output (and seven in the backward) by one read of the P x P window.
+// =============================================================================================
+struct CropAbsResizeParams {
+    const float* conv;     // [planes][n][n]
+    float* out;            // [planes][P][P]
+    int planes, n, P, off; // window origin (off, off); source row of output row i is off + max(i - 1, 0)
+};
+
+template <class Exec>
+B200_HD void crop_abs_resize_fwd_body(Exec& ex, const CropAbsResizeParams& p, int grid_x) {
+    ex.phase([&](int tid) {
+        const long long total = static_cast<long long>(p.planes) * p.P * p.P;
+        const long long stride = static_cast<long long>(grid_x) * ex.nthreads();
+        for (long long idx = static_cast<long long>(ex.bx()) * ex.nthreads() + tid; idx < total; idx += stride) {
+            const int j = static_cast<int>(idx % p.P), i = static_cast<int>((idx / p.P) % p.P);
+            const long long pl = idx / (static_cast<long long>(p.P) * p.P);
+            const int r = p.off + (i > 0 ? i - 1 : 0), c = p.off + (j > 0 ? j - 1 : 0);
+            p.out[idx] = fabsf(ld_ro(p.conv + (pl * p.n + r) * p.n + c));
+        }
+    });
+}
+
+struct CropAbsResizeBwdParams {
+    const float* g_out;    // [planes][P][P]
+    const float* conv;     // [planes][n][n]  (sign of the forward's argument)
+    float* g_conv;         // [planes][n][n]  every element is written (zero outside the window)
+    int planes, n, P, off;
+};
+
+template <class Exec>
+B200_HD void crop_abs_resize_bwd_body(Exec& ex, const CropAbsResizeBwdParams& p, int grid_x) {
+    ex.phase([&](int tid) {
+        const long long total = static_cast<long long>(p.planes) * p.n * p.n;
+        const long long stride = static_cast<long long>(grid_x) * ex.nthreads();
+        for (long long idx = static_cast<long long>(ex.bx()) * ex.nthreads() + tid; idx < total; idx += stride) {
+            const int c = static_cast<int>(idx % p.n), r = static_cast<int>((idx / p.n) % p.n);
+            const long long pl = idx / (static_cast<long long>(p.n) * p.n);
+            const int rr = r - p.off, cc = c - p.off;          // position in the (P-1)^2 crop
+            float g = 0.f;
+            if (rr >= 0 && rr < p.P - 1 && cc >= 0 && cc < p.P - 1) {
+                // crop row rr feeds output row rr+1, and output row 0 as well when rr == 0 (same for columns)
+                const float* go = p.g_out + pl * p.P * p.P;
+                const int i1 = rr + 1, j1 = cc + 1;
+                g = ld_ro(go + i1 * p.P + j1);
+                if (rr == 0) g += ld_ro(go + j1);
+                if (cc == 0) g += ld_ro(go + i1 * p.P);
+                if (rr == 0 && cc == 0) g += ld_ro(go);
+                const float v = ld_ro(p.conv + idx);
+                g = v > 0.f ? g : (v < 0.f ? -g : 0.f);      // d|v|/dv, 0 at v == 0 as torch.abs
+            }
+            p.g_conv[idx] = g;
+        }
+    });
+}
+
 }  // namespace b200cam

@@ -98,6 +98,37 @@ class CircConv(torch.autograd.Function):
         return grad_img, grad_k.reshape(ctx.kshape), None
 
 
+class CropAbsResize(torch.autograd.Function):
+    """``abs`` -> ``[off : off+P-1]`` crop -> nearest resize back to P (``out[i] = crop[max(i-1, 0)]``) of the padded
+    convolution output, ``Image_Caption/Camera/Utils.py:289-295``, in one kernel each way (b200cam_crop_abs_resize_*)."""
+
+    @staticmethod
+    def forward(ctx, conv: torch.Tensor, P: int, off: int, plan: F.DevicePlan):
+        c = F._as_f32(conv.detach(), plan.device)
+        B, C, n, _ = c.shape
+        out = torch.empty(B, C, P, P, dtype=torch.float32, device=plan.device)
+        if B * C > 0:
+            with torch.cuda.device(plan.index):
+                _lib.check(plan.lib.b200cam_crop_abs_resize_fwd(_lib.ptr(c), _lib.ptr(out), B * C, n, P, off, F._stream()))
+        ctx.plan, ctx.geom = plan, (P, off)
+        ctx.save_for_backward(c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan: F.DevicePlan = ctx.plan
+        (c,) = ctx.saved_tensors
+        P, off = ctx.geom
+        B, C, n, _ = c.shape
+        gc = torch.empty_like(c)
+        if B * C > 0:
+            go = F._as_f32(g, plan.device)
+            with torch.cuda.device(plan.index):
+                _lib.check(plan.lib.b200cam_crop_abs_resize_bwd(_lib.ptr(go), _lib.ptr(c), _lib.ptr(gc), B * C, n, P, off,
+                                                                F._stream()))
+        return gc, None, None, None
+
+
 class GlobalMaxNormalise(torch.autograd.Function):
     """y = x / max(x) over the whole batch (``Lens.py:312``); with a process group the max is taken over all ranks
     and the backward's arg-max term (-sum(g*y)/m at the arg-max) is routed to the rank that owns it."""
@@ -305,10 +336,9 @@ class OpticsZernike(nn.Module):
         else:
             kt, kb = int(pad) + 1, int(pad) - 1
         k = TF.pad(psf[0].permute(2, 0, 1).to(torch.float32), [kt, kb, kt, kb])          # (3, n, n)
-        res = torch.abs(CircConv.apply(x, k, self._plan(img.device, n)))
-        res = res[:, :, pt + 1:n - pb, pt + 1:n - pb]                                     # (P-1)^2
-        idx = torch.clamp(torch.arange(P, device=img.device) - 1, min=0)                  # nearest resize to P
-        return res.index_select(2, idx).index_select(3, idx)
+        plan = self._plan(img.device, n)
+        # |.|, the [pt+1 : n-pb] crop to (P-1)^2 and the nearest resize back to P (out[i] = crop[max(i-1,0)]) in one pass
+        return CropAbsResize.apply(CircConv.apply(x, k, plan), P, pt + 1, plan)
 
     # ------------------------------------------------------------------ reference API
     def forward(self, input_img, new_zernike=None, prueba=None, psf_lab=None, enfoco=None):

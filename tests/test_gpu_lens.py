@@ -81,3 +81,31 @@ def test_state_dict_and_signature_match_reference():
     assert [p for p, v in fresh.named_parameters() if v.requires_grad] == ["zernike_coeffs_train"]
     with pytest.raises(NotImplementedError):
         fresh(torch.rand(1, 3, 64, 64).cuda(), psf_lab=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,B", [(16, 2), (64, 3), (256, 2)])
+def test_crop_abs_resize_matches_torch_expression(P, B):
+    """The fused epilogue vs the reference's own ops (abs, [129:-128]-style crop, nearest resize; Utils.py:289-295),
+    forward and backward.  Bit-exact: no arithmetic besides |.| and sums of at most four gradient terms."""
+    from b200cam import functional as F
+    from b200cam.lens import CropAbsResize
+    dev = torch.device("cuda", 0)
+    n = 2 * P
+    pad = (n - P) / 2
+    pt, pb = int(np.ceil(pad)), int(np.floor(pad))
+    g = torch.Generator(device="cpu").manual_seed(9)
+    conv = torch.randn(B, 3, n, n, generator=g).to(dev)
+    conv[0, 0, pt + 1, pt + 1] = 0.0                      # d|v|/dv at 0
+    w = torch.randn(B, 3, P, P, generator=g).to(dev)
+    a = conv.clone().requires_grad_(True)
+    ref = torch.abs(a)[:, :, pt + 1:n - pb, pt + 1:n - pb]
+    idx = torch.clamp(torch.arange(P, device=dev) - 1, min=0)
+    ref = ref.index_select(2, idx).index_select(3, idx)
+    (ref * w).sum().backward()
+    b = conv.clone().requires_grad_(True)
+    plan = F.DevicePlan(256, dev, tables=False)
+    out = CropAbsResize.apply(b, P, pt + 1, plan)
+    (out * w).sum().backward()
+    assert torch.equal(out, ref)
+    assert torch.allclose(b.grad, a.grad, rtol=0, atol=1e-6)
