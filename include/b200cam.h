@@ -107,7 +107,8 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_rad, const float* g
                     void* workspace, size_t workspace_bytes, int N, void* stream);
 
 /* Data parallel (one process per GPU, batch sharded): b200cam_psf_bwd whose last kernel also all-reduces
- * dL/dh over NVLink peer memory - every rank pushes its rows into all peers' buffers, per-tile flags, rank-ordered sum,
+ * dL/dh over NVLink peer memory - every rank pushes its rows into all peers' buffers as (value, epoch) 8-byte words (data
+ * and flag in one store: no fence, no remote atomic), polls its own buffer for the peers' words, rank-ordered sum,
  * result * scale (1/world for the mean) in grad_h on every rank, bit-identical.  Replaces the framework-level gradient
  * all-reduce a DDP wrapper would issue for the reference's Camera parameters.
  *   peer_bufs  HOST array [world] of device pointers: rank r's symmetric buffer of b200cam_comm_bytes(N, world) bytes as

@@ -101,16 +101,19 @@ __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad(CRows
 }
 // ------------------------------------------------------------------------------------------
 // dL/dh tile + all-reduce over NVLink peer memory in ONE kernel (data parallel: SURVEY 8e).
-// Every rank owns a symmetric buffer  [flags 4 KB][epochs 4 KB][2 parities][world][N*N floats].
-// CTA t computes its CROWS rows of the local dL/dh (same body as k_crows_inv_hgrad), PUSHES them into slot[rank] of
-// every peer's buffer (plain P2P stores), bumps flag t on every peer (system-scope atomic), waits until its own
-// flag t shows `world` arrivals for this epoch, and sums the `world` slots in rank order - so all ranks hold the
-// bit-identical sum.  No grid-wide barrier: tile t only ever waits for tile t of the peers.  Flags and epochs are
-// monotone counters kept in the buffer itself (CUDA-graph replays reuse the frozen kernel arguments); data slots
-// are double buffered by epoch parity (a peer can be at most one step ahead).
+// Every rank owns a symmetric buffer  [epochs 8 KB][2 parities][world][N*N] of 8-byte words  (value, epoch).
+// CTA t computes its CROWS rows of the local dL/dh (same body as k_crows_inv_hgrad) and PUSHES them into slot[rank] of
+// every peer's buffer as (value, epoch) words - data and flag travel in ONE 8-byte store (delivered atomically over
+// NVLink), so there is no fence, no remote atomic and no separate flag: the receiver polls each word until its epoch
+// half shows the current step (the low-latency protocol of collective libraries; half the link bandwidth, which a
+// 256 KB gradient does not need).  Each thread then sums the `world` slots of its elements in rank order - every rank
+// holds the bit-identical sum.  No grid-wide barrier: an element only ever waits for the same element of the peers.
+// Epochs are monotone per-tile counters kept in the buffer itself (CUDA-graph replays reuse the frozen kernel
+// arguments); slots are double buffered by epoch parity (a peer can be at most one step ahead), so a word carrying
+// epoch e-2 is recognisably stale.
 // ------------------------------------------------------------------------------------------
 constexpr int COMM_MAX_WORLD = 16;
-constexpr size_t COMM_FLAG_BYTES = 4096, COMM_HEADER_BYTES = 8192;
+constexpr size_t COMM_HEADER_BYTES = 8192;
 struct CommDev {
     unsigned char* buf[COMM_MAX_WORLD];     // every rank's buffer, as mapped in this process
     int rank, world;
@@ -121,46 +124,66 @@ template <int N>
 __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad_allreduce(CRowsInvParams p, PupilLoad pupil,
                                                                                      float* gh, CommDev c) {
     DeviceExec ex;
-    crows_inv_hgrad_body<N>(ex, p, pupil, gh, SMEM2);            // local dL/dh rows of this tile -> gh
+    crows_inv_hgrad_body<N>(ex, p, pupil, gh, SMEM2);            // local dL/dh rows of this tile -> gh (ends with a barrier)
     __shared__ unsigned s_epoch;
-    constexpr int COUNT4 = Tile<N>::CROWS * N / 4;
+    constexpr int COUNT = Tile<N>::CROWS * N;
     const int tile = blockIdx.x, tid = threadIdx.x;
-    const size_t NN = static_cast<size_t>(N) * N, base = static_cast<size_t>(tile) * Tile<N>::CROWS * N;
+    const size_t NN = static_cast<size_t>(N) * N, base = static_cast<size_t>(tile) * COUNT;
     if (tid == 0) {
-        unsigned* ep = reinterpret_cast<unsigned*>(c.buf[c.rank] + COMM_FLAG_BYTES) + tile;
+        unsigned* ep = reinterpret_cast<unsigned*>(c.buf[c.rank]) + tile;
         s_epoch = *ep + 1;
         *ep = s_epoch;
     }
     __syncthreads();
     const unsigned epoch = s_epoch;
     const size_t parity_off = static_cast<size_t>(epoch & 1) * c.world * NN;
-    const float4* mine = reinterpret_cast<const float4*>(gh + base);
-    for (int i = tid; i < COUNT4; i += blockDim.x) {
-        const float4 v = mine[i];
+    for (int i = tid; i < COUNT; i += blockDim.x) {
+        const uint2 word = make_uint2(__float_as_uint(gh[base + i]), epoch);
         for (int r = 0; r < c.world; ++r) {
-            float* slot = reinterpret_cast<float*>(c.buf[r] + COMM_HEADER_BYTES) + parity_off + c.rank * NN + base;
-            reinterpret_cast<float4*>(slot)[i] = v;
+            uint2* slot = reinterpret_cast<uint2*>(c.buf[r] + COMM_HEADER_BYTES) + parity_off + c.rank * NN + base;
+            slot[i] = word;                                      // one 8-byte store: value and flag together
         }
     }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence_system();
-        for (int r = 0; r < c.world; ++r) atomicAdd_system(reinterpret_cast<unsigned*>(c.buf[r]) + tile, 1u);
-        const volatile unsigned* flag = reinterpret_cast<const volatile unsigned*>(c.buf[c.rank]) + tile;
-        const unsigned target = epoch * static_cast<unsigned>(c.world);
-        const long long t0 = clock64();                       // never hang the device if a peer died (~2 s)
-        while (*flag < target && clock64() - t0 < 4000000000LL) {}
-        __threadfence_system();
+    // receive: a thread's elements x four ranks are polled as ONE batch of loads (each volatile load is an L2 round trip;
+    // polled one after the other they cost more than the exchange itself), summed in rank order once all have arrived
+    const uint2* slots = reinterpret_cast<const uint2*>(c.buf[c.rank] + COMM_HEADER_BYTES) + parity_off + base;
+    constexpr int THREADS = HGradSmem<N>::THREADS;
+    constexpr int K = (COUNT + THREADS - 1) / THREADS;
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+    const long long t0 = clock64();                             // never hang the device if a peer died (~1 s)
+    for (int r0 = 0; r0 < c.world; r0 += 4) {
+        uint2 w[K][4];
+        bool ok;
+        do {
+            ok = true;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = tid + k * THREADS;
+                    w[k][q] = make_uint2(0u, epoch);
+                    if (i < COUNT && r0 + q < c.world) {
+                        const uint2* src = slots + static_cast<size_t>(r0 + q) * NN + i;
+                        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];\n" : "=r"(w[k][q].x), "=r"(w[k][q].y) : "l"(src) : "memory");
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ok = ok && (w[k][q].y == epoch);
+        } while (!ok && clock64() - t0 < 2000000000LL);
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[k] += __uint_as_float(w[k][q].x);      // rank order; absent ranks add +0
     }
-    __syncthreads();
-    const float* slots = reinterpret_cast<const float*>(c.buf[c.rank] + COMM_HEADER_BYTES) + parity_off + base;
-    for (int i = tid; i < COUNT4; i += blockDim.x) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < c.world; ++r) {                    // rank order: identical on every rank
-            const float4 v = __ldcv(reinterpret_cast<const float4*>(slots + r * NN) + i);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        reinterpret_cast<float4*>(gh + base)[i] = make_float4(acc.x * c.scale, acc.y * c.scale, acc.z * c.scale, acc.w * c.scale);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int i = tid + k * THREADS;
+        if (i < COUNT) gh[base + i] = acc[k] * c.scale;
     }
 }
 
@@ -1322,7 +1345,7 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_rad, const float* g
 
 size_t b200cam_comm_bytes(int N, int world) {
     if (!b200cam_supported(N) || world < 1 || world > COMM_MAX_WORLD) return 0;
-    return COMM_HEADER_BYTES + static_cast<size_t>(2) * world * N * N * sizeof(float);
+    return COMM_HEADER_BYTES + static_cast<size_t>(2) * world * N * N * sizeof(uint2);
 }
 
 int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_rad, const float* grad_cen, const float* h, const float* A,
@@ -1330,7 +1353,7 @@ int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_rad, cons
                               float* stats, float* grad_h, void* workspace, size_t workspace_bytes, int N, void* stream,
                               void* const* peer_bufs, int rank, int world, float scale) {
     if (!b200cam_supported(N) || world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world) return B200CAM_E_BAD_SIZE;
-    if (N / Tile<64>::CROWS > static_cast<int>(COMM_FLAG_BYTES / sizeof(unsigned))) return B200CAM_E_BAD_SIZE;
+    if (N / 2 > static_cast<int>(COMM_HEADER_BYTES / sizeof(unsigned))) return B200CAM_E_BAD_SIZE;   // one epoch word per tile
     if (!h || !A || !Ht || !rho || !kappa || !psf || !field || !stats || !grad_h || !workspace || !peer_bufs) return B200CAM_E_NULL;
     if (workspace_bytes < b200cam_psf_workspace_bytes(N)) return B200CAM_E_WORKSPACE;
     if (!aligned16(A) || !aligned16(Ht) || !aligned16(field) || !aligned16(workspace) || !aligned16(grad_h)) return B200CAM_E_ALIGN;

@@ -25,9 +25,20 @@ def main():
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 12
     out = sys.argv[4] if len(sys.argv) > 4 else None
     R = 4
-    dev = torch.device("cuda", 0)
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:               # under torchrun: data-parallel step (fused all-reduce of dL/dh in the last kernel)
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     cam = Camera(device=dev, N=N, zernike_terms=12)
+    if world > 1:
+        cam.data_parallel(average=True)
     h = synth.height_map(N).to(dev).requires_grad_(True)
     cam.get_Heith_Map = lambda: h
     imgs = [synth.images(B, N, seed=1000 + r).to(dev) for r in range(R)]
@@ -70,6 +81,9 @@ def main():
             graphs[i % R].replay()
         torch.cuda.synchronize()
 
+    if rank != 0:
+        torch.cuda.synchronize()
+        os._exit(0)
     evs = []
     for e in prof.events():
         if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None:
@@ -123,6 +137,9 @@ def main():
           f"sum of kernel durations {sum(t - s for s, t, _ in one_step):.1f} us")
     for g, n in gaps:
         print(f"   gap {g:5.1f} us before {n.replace('b200cam::', '')[:70]}")
+    if world > 1:
+        sys.stdout.flush()
+        os._exit(0)
     if out:
         Path(out).write_text(json.dumps({"B": B, "N": N, "median_period_us": med_period, "span_us": span, "busy_us": busy,
                                          "kernels": rows}, indent=1))
