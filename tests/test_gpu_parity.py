@@ -341,3 +341,22 @@ def test_uint8_images_are_scaled_on_the_gpu():
     y8 = cam(u8)
     yf = cam(u8.float() / 255.0)
     assert torch.equal(y8, yf)
+
+
+@pytest.mark.gpu
+def test_fused_peer_allreduce_matches_nccl_when_two_gpus_are_visible():
+    """Data parallel: the all-reduce of dL/dh fused into the last PSF-backward kernel (NVLink peer memory,
+    (value, epoch) words) against the NCCL path, eagerly and through a CUDA graph.  Needs two GPUs: skipped otherwise."""
+    import re
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    repo = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", str(repo / "tools" / "check_peer_allreduce.py")],
+                         capture_output=True, text=True, timeout=300)
+    m = re.search(r"PEER_ALLREDUCE world=2 rel_vs_nccl=([0-9.e+-]+) rel_graph=([0-9.e+-]+)", res.stdout + res.stderr)
+    assert m, (res.stdout + res.stderr)[-2000:]
+    assert float(m.group(1)) <= 1e-5 and float(m.group(2)) <= 1e-6
