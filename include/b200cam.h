@@ -113,7 +113,7 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_rad, const float* g
  * all-reduce a DDP wrapper would issue for the reference's Camera parameters.
  *   peer_bufs  HOST array [world] of device pointers: rank r's symmetric buffer of b200cam_comm_bytes(N, world) bytes as
  *              mapped in THIS process (e.g. torch.distributed._symmetric_memory buffer_ptrs); zero-filled once before
- *              the first call, then owned by the library (flags / epochs / double-buffered slots live in it).
+ *              the first call, then owned by the library (per-tile epochs and the double-buffered slots live in it).
  * All ranks must call it the same number of times (it is a collective). */
 size_t b200cam_comm_bytes(int N, int world);
 int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_rad, const float* grad_cen, const float* h, const float* A,
