@@ -32,6 +32,17 @@ extern "C" {
 #define B200CAM_E_WORKSPACE  (-3)      /* workspace too small */
 #define B200CAM_E_NOT_INIT   (-4)      /* b200cam_init(N) not called on this device */
 #define B200CAM_E_ALIGN      (-5)      /* pointer not 16-byte aligned */
+#define B200CAM_E_DEVICE     (-6)      /* a kernel reported a device-side error (see b200cam_device_error) */
+
+/* Device-side error word.  Three kernels wait for other CTAs / ranks (the per-image maximum exchanged between the clusters
+ * of an image, the grid barrier of the cooperative PSF kernels, the peer all-reduce of dL/dh).  A wait that outlives its
+ * deadline is never turned into a result: the kernel stores one of these codes in a per-device word (mapped host memory)
+ * and the next call of b200cam_device_error on that device returns it (0 = none; `clear` != 0 resets it).  The Python
+ * wrappers check it after the backward of a step and raise. */
+#define B200CAM_DEVERR_IMAGE_MAX_WAIT 1
+#define B200CAM_DEVERR_ALLREDUCE_WAIT 2
+#define B200CAM_DEVERR_GRID_BARRIER   3
+int b200cam_device_error(int clear);
 
 int b200cam_version(void);
 const char* b200cam_error_string(int code);

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "b200cam_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "b200cam_supported": (ctypes.c_int, [ctypes.c_int]),
     "b200cam_launch_count": (ctypes.c_ulonglong, []),
+    "b200cam_device_error": (ctypes.c_int, [ctypes.c_int]),
     "b200cam_init": (ctypes.c_int, [ctypes.c_int]),
     "b200cam_otf_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "b200cam_psf_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
@@ -126,6 +127,23 @@ def ensure_init(N: int, device_index: int) -> None:
     with torch.cuda.device(device_index):
         check(lib.b200cam_init(N))
     _inited.add(key)
+
+
+_DEVERR = {1: "the per-image maximum exchange of the sensor kernel timed out (clusters of one image not co-resident?)",
+           2: "the peer-memory all-reduce of dL/dh timed out waiting for another rank (ranks out of step, or a rank died)",
+           3: "the grid barrier of a cooperative PSF kernel timed out"}
+
+
+def raise_on_device_error(device_index: int) -> None:
+    """Surface a device-side error word (include/b200cam.h: B200CAM_DEVERR_*) as a RuntimeError and clear it.
+    Reading it is one load from mapped host memory: cheap enough to do once per forward / backward."""
+    import torch
+    lib = load_library()
+    with torch.cuda.device(device_index):
+        code = lib.b200cam_device_error(1)
+    if code:
+        raise RuntimeError(f"b200cam device error {code}: {_DEVERR.get(code, 'unknown')}; the results of the step that "
+                           "reported it are invalid")
 
 
 def ptr(t) -> ctypes.c_void_p:

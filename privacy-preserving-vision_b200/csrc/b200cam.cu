@@ -8,8 +8,8 @@
 #include <mutex>
 
 #include "../../include/b200cam.h"
-#include "f256.cuh"
 #include "kernels.cuh"
+#include "plane.cuh"
 
 namespace b200cam {
 
@@ -197,88 +197,96 @@ __global__ void __launch_bounds__(EW_THREADS) k_psf_grad_prepare(PsfGradPrepPara
     DeviceExec ex;
     psf_grad_prepare_body(ex, p, gridDim.x, red);
 }
-__global__ void __launch_bounds__(f256::THREADS, 1) k_f256_fwd(f256::FwdParams p) { f256::fwd_kernel_body(p, SMEM2); }
-__global__ void __launch_bounds__(EW_THREADS) k_f256_norm(f256::NormParams p) { f256::norm_kernel_body(p); }
-__global__ void __launch_bounds__(f256::THREADS, 1) k_f256_bwd(f256::BwdParams p) { f256::bwd_kernel_body(p, SMEM2); }
-
-// sum the per-CTA accumulator planes of one spectral column (fixed order), apply (-1)^(u+v) (adjoint of the
-// roll at Optics.py:126) and the scale, inverse FFT along v -> ST layout [3][129][256] for rows_c2r.
-// grid 3*129 columns, block 256 (thread = v).
-struct AccReduceParams {
-    const float2* acc;     // [grid_bwd][129][256]
-    float2* st;            // [3][129][256]
-    const float2* tw;
-    int grid_bwd;          // CTAs of the backward kernel
-    int B;
-    float scale;
-};
-__global__ void __launch_bounds__(256) k_f256_acc_reduce(AccReduceParams p) {
-    using P = Plan<256>;
-    __shared__ float2 line[256];
-    __shared__ float2 E[P::E_SIZE];
-    const int cu = blockIdx.x, c = cu / f256::NC, u = cu % f256::NC, v = threadIdx.x;
-    int nparts = (p.grid_bwd - c + 2) / 3;
-    if (nparts > p.B) nparts = p.B;
-    const float2* src = p.acc + (static_cast<size_t>(c) * f256::NC + u) * 256 + v;
-    const size_t step = static_cast<size_t>(3) * f256::SPEC_PLANE;
-    float2 s = make_float2(0.f, 0.f);
-    int i = 0;
-    for (; i + 8 <= nparts; i += 8) {
-        float2 t[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = __ldcg(src + (i + j) * step);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s.x += t[j].x; s.y += t[j].y; }
+// ------------------------------------------------------------------------------------------
+// Plane-resident N = 256 sensor kernels (plane.cuh): device execution policy and __global__ wrappers
+// ------------------------------------------------------------------------------------------
+struct PlaneCtx {
+    int rank, tid;
+    plane::Thread& t;
+    float2* smem;
+    unsigned* err;          // device error word (mapped host memory): set when a wait gives up
+    __device__ __forceinline__ float2 shfl_v(int idx, int src, bool half) {
+        const unsigned mask = half ? (0xffffu << (threadIdx.x & 16)) : 0xffffffffu;
+        const int s = (threadIdx.x & 16) | src;
+        return make_float2(__shfl_sync(mask, t.v[idx].x, s), __shfl_sync(mask, t.v[idx].y, s));
     }
-    for (; i < nparts; ++i) { const float2 t = __ldcg(src + i * step); s.x += t.x; s.y += t.y; }
-    const float sc = ((u + v) & 1) ? -p.scale : p.scale;
-    line[v] = make_float2(s.x * sc, s.y * sc);
-    __syncthreads();
-    if (v < 16) {
-        float2 q[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) q[k] = line[v + 16 * k];
-        P::stepC(q, v, E, p.tw);
+    __device__ __forceinline__ float2 shfl_u(int idx, int src, bool half) {
+        const unsigned mask = half ? (0xffffu << (threadIdx.x & 16)) : 0xffffffffu;
+        const int s = (threadIdx.x & 16) | src;
+        return make_float2(__shfl_sync(mask, t.u[idx].x, s), __shfl_sync(mask, t.u[idx].y, s));
     }
-    __syncthreads();
-    if (v < 16) {
-        float2 q[16];
-        P::stepD(q, v, E);
-        float2* dst = p.st + static_cast<size_t>(cu) * 256;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) dst[16 * k + v] = q[k];
+    // the per-image maximum is taken across the 3 x 8 CTAs that hold the image's planes: max first, then the arrival
+    __device__ __forceinline__ void publish_max(unsigned* s, unsigned key) {
+        atomicMax(s, key);
+        __threadfence();
+        atomicAdd(s + 1, 1u);
     }
-}
-
-// arg-max term of the amax backward (Optics.py:128), spatial form:
-//   gpsf[c][p] -= sum_b coef_b * sum_{ties t of b in channel c} x_b[c][(p*_t - p + N/2) mod N],
-//   coef_b = sum(g_b*y_b) / (n_b m_b) = (sdot[3b]+sdot[3b+1]+sdot[3b+2]) / (2 n_b m_b^2).
-// grid (256, 3), block 256 (thread = x).  Fixed b order: deterministic.
-struct TieSpatialParams {
-    float* gpsf; const float* x; const float* sdot; const float* img_max; const int* tie_count; const int* tie_pos;
-    float* coef; int B;
-};
-__global__ void __launch_bounds__(256) k_f256_tie(TieSpatialParams p) {
-    constexpr int N = 256, NN = N * N;
-    const int py = blockIdx.x, c = blockIdx.y, px = threadIdx.x;
-    float acc = 0.f;
-    for (int b = 0; b < p.B; ++b) {
-        const int cnt = p.tie_count[b];
-        const int nt = cnt < MAX_TIES ? cnt : MAX_TIES;
-        const float m = p.img_max[b];
-        const float sd = (p.sdot[3 * b] + p.sdot[3 * b + 1]) + p.sdot[3 * b + 2];
-        const float cf = sd / (2.0f * static_cast<float>(cnt > 0 ? cnt : 1) * m * m);
-        if (py == 0 && c == 0 && px == 0) p.coef[b] = cf;
-        for (int t = 0; t < nt; ++t) {
-            const int pos = p.tie_pos[b * MAX_TIES + t];
-            if (pos / NN != c) continue;
-            const int sy = ((pos % NN) / N - py + N / 2 + N) & (N - 1);
-            const int sx = (pos % N - px + N / 2 + N) & (N - 1);
-            acc += cf * __ldg(p.x + (static_cast<size_t>(b) * 3 + c) * NN + sy * N + sx);
+    // All 24 CTAs are resident (the grid is one wave of co-scheduled clusters, sized from the occupancy API) and reach
+    // this point within a fraction of a plane of each other.  A wait that outlives ~2 s means a broken launch: it is
+    // reported through the device error word (b200cam_device_error), never turned into a silent result.
+    __device__ __forceinline__ unsigned wait_max(unsigned* s, unsigned target) {
+        unsigned n;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(n) : "l"(s + 1) : "memory");
+            if (n >= target) break;
+            if (clock64() - t0 > 4000000000LL) {
+                if (err != nullptr) atomicExch(err, B200CAM_DEVERR_IMAGE_MAX_WAIT);
+                break;
+            }
         }
+        unsigned key;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(key) : "l"(s) : "memory");
+        return key;
     }
-    if (acc != 0.f) p.gpsf[c * NN + py * N + px] -= acc;
+};
+struct PlaneExec {
+    PlaneCtx ctx;
+    template <class F>
+    __device__ __forceinline__ void each(F&& f) { f(ctx); }
+    __device__ __forceinline__ void sync_warp() { __syncwarp(); }
+    __device__ __forceinline__ void sync_cta() { __syncthreads(); }
+    __device__ __forceinline__ void sync_cluster() {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    }
+};
+
+__global__ void __launch_bounds__(plane::THREADS, 4) k_prow(plane::RowParams p) {
+    plane::Thread t;
+    PlaneExec x{{0, static_cast<int>(threadIdx.x), t, SMEM2, nullptr}};
+    plane::prow_body(x, p, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
 }
+__global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREADS, 3) k_pconv(plane::ConvParams p, unsigned* err) {
+    plane::Thread t;
+    const int cluster = blockIdx.x / plane::C;
+    PlaneExec x{{static_cast<int>(blockIdx.x % plane::C), static_cast<int>(threadIdx.x), t, SMEM2, err}};
+    x.each([&](auto& c) { plane::load_twiddles(c, p.tw); });
+    for (int it = 0; cluster / 3 + p.G3 * it < p.B; ++it) {
+        plane::pconv_front(x, p, cluster, it);
+        plane::pconv_back(x, p, cluster, it);
+    }
+}
+__global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREADS, 2) k_pacc(plane::AccParams p) {
+    plane::Thread t;
+    const int cluster = blockIdx.x / plane::C;
+    PlaneExec x{{static_cast<int>(blockIdx.x % plane::C), static_cast<int>(threadIdx.x), t, SMEM2, nullptr}};
+    plane::pacc_init(x, p);
+    for (int it = 0; cluster / 3 + p.G3 * it < p.B; ++it) plane::pacc_plane(x, p, cluster, it);
+    plane::pacc_finish(x, p, cluster);
+}
+// coef[b] = sum(g_b * y_b) / (n_b m_b) = sum(g_b * conv_b) / (n_b m_b^2) from the 24 per-CTA Parseval partials of k_pacc
+// (which carry a factor 4) - the weight of the arg-max term of the amax backward (Optics.py:128)
+__global__ void __launch_bounds__(64) k_pcoef(const float* dotp, const float* img_max, const int* tie_count, float* coef, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float s = 0.f;
+    for (int i = 0; i < 3 * plane::C; ++i) s += dotp[b * 3 * plane::C + i];          // fixed order: deterministic
+    const int n = tie_count[b] > 0 ? tie_count[b] : 1;
+    const float m = img_max[b];
+    coef[b] = 0.25f * s / (static_cast<float>(n) * m * m);
+}
+
 // ------------------------------------------------------------------------------------------
 // PSF chain as ONE cooperative launch per direction: the same bodies, run as virtual blocks, with
 // grid-wide barriers where the multi-kernel version had kernel boundaries.
@@ -444,6 +452,8 @@ struct DeviceState {
     int conv_slots[11] = {0}, accum_slots[11] = {0};     // resident CTAs of the persistent column kernels
     cudaEvent_t chain_ev = nullptr;                      // orders a caller stream behind the first PSF-chain kernel
     int r2c_fit[11] = {0}, c2r_fit[11] = {0};            // resident CTAs per SM of the persistent row kernels
+    int prow_fit = 0, pconv_g3 = 0, pacc_g3 = 0;         // plane kernels (N = 256): resident CTAs per SM / co-resident cluster triples
+    unsigned* err_host = nullptr; unsigned* err_dev = nullptr;   // device error word (mapped pinned host memory)
 };
 static DeviceState g_state[MAX_DEV];
 static std::mutex g_mutex;
@@ -480,18 +490,6 @@ static unsigned* coop_barrier(int which) {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
     return g_state[dev].bar + 2 * which;
 }
-// N=256 has two implementations of the sensor path: the generic row/column/row kernels (kernels.cuh) and the fused
-// one-CTA-per-plane TMEM kernels (f256.cuh).  The fused kernels execute 2.3x fewer instructions and move half the
-// bytes, but one 512-thread CTA per SM issues at ~30 % (ncu: profiles/r01_f256_*), and they work in whole rounds of
-// one plane per SM (B = 64 on 148 SMs: 1.3 rounds of work cost 2).  Measured (graph replay, fwd+bwd, us):
-//   B = 49: 243 fused;  B = 64: 361 fused / 268 generic;  B = 128: 508 fused / 428 generic.
-// So the generic pipeline is the default and the fused one is opt-in (B200CAM_FUSED=1) until its issue rate is fixed.
-static bool fused_selected(int B) {
-    (void)B;
-    static const bool on = [] { const char* e = getenv("B200CAM_FUSED"); return e && e[0] == '1'; }();
-    return on;
-}
-
 static const float2* twiddle(int N) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
@@ -557,6 +555,50 @@ static cudaError_t column_slots(int sms, int* conv, int* accum) {
     *conv = sms * nc;
     *accum = sms * na;
     return cudaSuccess;
+}
+
+// The plane kernels (N = 256) run as ONE wave of co-scheduled 8-CTA clusters: the three clusters that hold the planes of
+// an image exchange the image maximum through global memory while they are resident, so the grid must never exceed what
+// the device keeps resident at once (cudaOccupancyMaxActiveClusters), rounded down to whole triples.
+constexpr int PLANE_MAX_G3 = 24;        // sizes the crossing scratch and the partial planes of the backward
+static bool plane_selected() {
+    static const bool on = [] { const char* e = getenv("B200CAM_PLANE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <class K>
+static cudaError_t max_cluster_triples(K kernel, int* g3) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(plane::THREADS);
+    cfg.gridDim = dim3(plane::C);
+    cfg.dynamicSmemBytes = plane::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plane::C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+    if (e != cudaSuccess) return e;
+    static const int cap = [] { const char* v = getenv("B200CAM_PLANE_G3"); return v ? atoi(v) : PLANE_MAX_G3; }();
+    int t = n / 3;
+    if (t > PLANE_MAX_G3) t = PLANE_MAX_G3;
+    if (cap > 0 && t > cap) t = cap;
+    *g3 = t;
+    return cudaSuccess;
+}
+static cudaError_t plane_init(int dev) {
+    cudaError_t e;
+    if ((e = optin(k_prow, plane::SMEM_BYTES))) return e;
+    if ((e = optin(k_pconv, plane::SMEM_BYTES))) return e;
+    if ((e = optin(k_pacc, plane::SMEM_BYTES))) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_state[dev].prow_fit, k_prow, plane::THREADS, plane::SMEM_BYTES))) return e;
+    if ((e = max_cluster_triples(k_pconv, &g_state[dev].pconv_g3))) return e;
+    if ((e = max_cluster_triples(k_pacc, &g_state[dev].pacc_g3))) return e;
+    return cudaSuccess;
+}
+static DeviceState* cur_state() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    return &g_state[dev];
 }
 
 // grid of a persistent row kernel: `want` CTAs per SM, never more than fit at once (a persistent grid larger than one
@@ -629,28 +671,22 @@ struct PsfWs {
     }
 };
 
-constexpr int FUSED_MAX_GRID = 160;   // upper bound on the CTAs of the fused backward kernel (one accumulator plane each)
-
 struct SensorWs {
     float2* stx; float2* stg; float2* partial; float2* stp; float* dot_lanes; float* coef;
-    float* plane_max; float* sdot; float2* acc; float2* st2; int* arrive;
+    float4* pscratch; float2* st2; int* arrive;
     size_t bytes;
     SensorWs(void* p, int N, int B, bool backward) {
         Carver c(p);
-        if (N == 256) {
-            plane_max = c.take<float>(static_cast<size_t>(3) * B);
-            sdot = c.take<float>(static_cast<size_t>(3) * B);
-            acc = backward ? c.take<float2>(static_cast<size_t>(FUSED_MAX_GRID) * f256::SPEC_PLANE) : nullptr;
-        } else {
-            plane_max = sdot = nullptr; acc = nullptr;
-        }
+        // N = 256 plane kernels: crossing scratch of the resident clusters, [3 * G3][2][128 x 128] float4 (L2 resident)
+        pscratch = (N == 256) ? c.take<float4>(static_cast<size_t>(3) * (B < PLANE_MAX_G3 ? B : PLANE_MAX_G3) * 2 * plane::PLANE_F4) : nullptr;
         const size_t plane = static_cast<size_t>(N / 2 + 1) * N;
         stx = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
         st2 = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
         arrive = c.take<int>(B);
         if (backward) {
             stg = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
-            partial = c.take<float2>(static_cast<size_t>(B < MAX_CHUNKS ? B : MAX_CHUNKS) * 3 * plane);
+            const int max_chunks = (N == 256 && PLANE_MAX_G3 > MAX_CHUNKS) ? PLANE_MAX_G3 : MAX_CHUNKS;
+            partial = c.take<float2>(static_cast<size_t>(B < max_chunks ? B : max_chunks) * 3 * plane);
             stp = c.take<float2>(3 * plane);
             dot_lanes = c.take<float>(static_cast<size_t>(B) * 3 * (N / 2 + 1) * 32);   // [B][3*NC][R1 <= 32]
             coef = c.take<float>(B);
@@ -789,33 +825,6 @@ static int otf_impl(const float* src, float2* otf, const float2* tw, float scale
     return 0;
 }
 
-static int fused_grid(int planes) {
-    int grid = sm_count();
-    if (grid <= 0) return 0;
-    if (grid > FUSED_MAX_GRID) grid = FUSED_MAX_GRID;
-    if (grid > planes) grid = planes;
-    return grid;
-}
-
-// N = 256: one persistent kernel (spectrum on chip) + the normalise pass
-static int fused_fwd(const float* img, float* sensor, const float2* otf, float2* spectrum, const float2* tw,
-                     const SensorWs& ws, float* img_max, int* tie_count, int* tie_pos, int B, cudaStream_t s) {
-    const int planes = 3 * B;
-    const int grid = fused_grid(planes);
-    if (grid <= 0) return B200CAM_E_NOT_INIT;
-    k_f256_fwd<<<grid, f256::THREADS, f256::SMEM_BYTES, s>>>(
-        f256::FwdParams{img, sensor, otf, spectrum, tw, ws.plane_max, tie_count, planes});
-    LAUNCH_CHECK();
-    if (sensor != nullptr) {
-        const long long n4 = static_cast<long long>(planes) * 256 * 256 / 4;
-        const int ngrid = static_cast<int>(n4 / EW_THREADS < 148 * 8 ? (n4 + EW_THREADS - 1) / EW_THREADS : 148 * 8);
-        k_f256_norm<<<ngrid, EW_THREADS, 0, s>>>(
-            f256::NormParams{sensor, ws.plane_max, img_max, tie_count, tie_pos, n4, MAX_TIES});
-        LAUNCH_CHECK();
-    }
-    return 0;
-}
-
 // first half of the generic forward: row transforms of the images (independent of the PSF, so a caller may run it on a
 // second stream while b200cam_psf_fwd is still busy); also resets the per-image max / tie counters
 template <int N>
@@ -825,6 +834,22 @@ static int sensor_rows_impl(const float* img, float2* srow, float* img_max, int*
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     // B200CAM_ROWS_PER_SM resident CTAs per SM (default 3 of the 4 that fit): see k_rows_r2c_persist
     static const int per_sm = [] { const char* e = getenv("B200CAM_ROWS_PER_SM"); const int v = e ? atoi(e) : 3; return v > 0 ? v : 3; }();
+    if constexpr (N == 256) {
+        if (plane_selected()) {
+            // plane layout "A"; the words behind it (the buffer is sized for 129 columns, A uses 128) hold the per-image
+            // {max key, arrivals} pairs of k_pconv: reset here, early, beside the PSF chain
+            const DeviceState* st = cur_state();
+            if (st == nullptr) return B200CAM_E_NOT_INIT;
+            const int planes = 3 * B;
+            float4* A = reinterpret_cast<float4*>(srow);
+            if (img_max != nullptr) CK(cudaMemsetAsync(A + static_cast<size_t>(planes) * plane::PLANE_F4, 0, sizeof(unsigned) * 2 * B, s));
+            if (tie_count != nullptr) CK(cudaMemsetAsync(tie_count, 0, sizeof(int) * B, s));
+            const int grid = persistent_grid(st->prow_fit, per_sm, planes * 8);
+            k_prow<<<grid, plane::THREADS, plane::SMEM_BYTES, s>>>(plane::RowParams{img, A, tw, planes});
+            LAUNCH_CHECK();
+            return 0;
+        }
+    }
     const int total = (N / T::ROWS) * 3 * B;
     const int grid = persistent_grid(rows_fit(N, false), per_sm, total);
     k_rows_r2c_persist<N><<<grid, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES, s>>>(
@@ -845,6 +870,19 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
         if (rc) return rc;
     }
     const int planes = 3 * B;
+    if constexpr (N == 256) {
+        if (plane_selected()) {
+            const DeviceState* st = cur_state();
+            if (st == nullptr || st->pconv_g3 < 1) return B200CAM_E_NOT_INIT;
+            const int G3 = B < st->pconv_g3 ? B : st->pconv_g3;
+            float4* A = reinterpret_cast<float4*>(const_cast<float2*>(srow));
+            unsigned* sync = reinterpret_cast<unsigned*>(A + static_cast<size_t>(planes) * plane::PLANE_F4);
+            k_pconv<<<3 * G3 * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
+                plane::ConvParams{A, otf, ws.pscratch, sensor, tw, sync, img_max, tie_count, tie_pos, B, G3, 1, 1}, st->err_dev);
+            LAUNCH_CHECK();
+            return 0;
+        }
+    }
     const dim3 rgrid(N / T::ROWS, planes);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int nchunks = conv_chunks(N, B);
@@ -888,6 +926,18 @@ static int conv_fwd_impl(const float* img, const float* kern, float* out, float2
     rc = otf_impl<N>(kern, otf, tw, 1.0f / (static_cast<float>(N) * N), s);
     if (rc) return rc;
     const int planes = 3 * B;
+    if constexpr (N == 256) {
+        if (plane_selected()) {
+            const DeviceState* st = cur_state();
+            if (st == nullptr || st->pconv_g3 < 1) return B200CAM_E_NOT_INIT;
+            const int G3 = B < st->pconv_g3 ? B : st->pconv_g3;
+            k_pconv<<<3 * G3 * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
+                plane::ConvParams{reinterpret_cast<float4*>(srow), otf, ws.pscratch, out, tw, nullptr, nullptr, nullptr, nullptr, B, G3,
+                                  1, 0}, st->err_dev);
+            LAUNCH_CHECK();
+            return 0;
+        }
+    }
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int nchunks = conv_chunks(N, B);
     k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
@@ -909,6 +959,46 @@ static int conv_bwd_impl(const float* g, const float* img, const float2* otf, co
     SensorWs ws(ws_ptr, N, B, true);
     const int planes = 3 * B, tiles = N / T::ROWS;
     const dim3 rgrid(tiles, planes);
+    if constexpr (N == 256) {
+        if (plane_selected()) {
+            const DeviceState* st = cur_state();
+            if (st == nullptr || st->pacc_g3 < 1 || st->pconv_g3 < 1) return B200CAM_E_NOT_INIT;
+            const float4* Xh = reinterpret_cast<const float4*>(spectrum);
+            if (Xh == nullptr) {
+                int rc = sensor_rows_impl<N>(img, ws.stx, nullptr, nullptr, B, s);
+                if (rc) return rc;
+                const int G3c = B < st->pconv_g3 ? B : st->pconv_g3;
+                k_pconv<<<3 * G3c * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
+                    plane::ConvParams{reinterpret_cast<float4*>(ws.stx), otf, ws.pscratch, nullptr, tw, nullptr, nullptr, nullptr,
+                                      nullptr, B, G3c, 1, 0}, st->err_dev);
+                LAUNCH_CHECK();
+                Xh = reinterpret_cast<const float4*>(ws.stx);
+            }
+            const int G3 = B < st->pacc_g3 ? B : st->pacc_g3;
+            k_pacc<<<3 * G3 * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
+                plane::AccParams{g, Xh, otf, ws.pscratch, tw, nullptr, ws.partial, ws.dot_lanes, B, G3});
+            LAUNCH_CHECK();
+            k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
+                ColsReduceInvParams{ws.partial, ws.stp, tw, G3, 0.25f / (static_cast<float>(N) * N), nullptr, nullptr, nullptr, nullptr, 0});
+            LAUNCH_CHECK();
+            k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+                RowsC2RParams{ws.stp, grad_kern, tw, nullptr, 1.0f, nullptr, nullptr, 0});
+            LAUNCH_CHECK();
+            if (grad_img != nullptr) {
+                k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
+                LAUNCH_CHECK();
+                const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
+                const int cchunks = conv_chunks(N, B);
+                k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+                    ColsConvParams{ws.stg, ws.stg, otf, tw, nullptr, B, cchunks, 1, 1.0f});
+                LAUNCH_CHECK();
+                k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+                    RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f, nullptr, nullptr, 0});
+                LAUNCH_CHECK();
+            }
+            return 0;
+        }
+    }
     const float2* srow = spectrum;
     if (srow == nullptr) {
         int rc = sensor_rows_impl<N>(img, ws.stx, nullptr, nullptr, B, s);
@@ -945,66 +1035,10 @@ template <int N>
 static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
                            int* tie_pos, float2* otf, float2* spectrum, void* ws_ptr, int B, cudaStream_t s) {
     SensorWs ws(ws_ptr, N, B, false);
-    if ((N == 256) && fused_selected(B)) {
-        const float2* tw = twiddle(N);
-        if (tw == nullptr) return B200CAM_E_NOT_INIT;
-        // the fused kernels take the OTF pre-halved (their real-row split yields 2*rfft, f256.cuh)
-        int rc = otf_impl<N>(psf, otf, tw, 0.5f / (static_cast<float>(N) * N), s);
-        if (rc) return rc;
-        return fused_fwd(img, sensor, otf, spectrum, tw, ws, img_max, tie_count, tie_pos, B, s);
-    }
     float2* srow = spectrum != nullptr ? spectrum : ws.stx;      // row spectra: kept for the backward when asked
     int rc = sensor_rows_impl<N>(img, srow, img_max, tie_count, B, s);
     if (rc) return rc;
     return sensor_finish_impl<N>(psf, sensor, img_max, tie_count, tie_pos, otf, srow, ws, B, 0, s);
-}
-
-// N = 256 backward: persistent accumulate kernel, partial reduction + inverse transform, arg-max term
-static int fused_bwd(const float* g, const float* img, const float* img_max, const int* tie_count, const int* tie_pos,
-                     const float* psf, const float2* otf, const float2* spectrum, float* grad_psf, float* grad_img,
-                     const float2* tw, const SensorWs& ws, int B, cudaStream_t s) {
-    constexpr int N = 256;
-    using T = Tile<N>;
-    const int planes = 3 * B;
-    const int grid = fused_grid(planes);
-    if (grid <= 0) return B200CAM_E_NOT_INIT;
-    const float2* X = spectrum;
-    if (X == nullptr) {          // the forward did not keep the image spectra: rebuild them (no output, no max)
-        k_f256_fwd<<<grid, f256::THREADS, f256::SMEM_BYTES, s>>>(
-            f256::FwdParams{img, nullptr, otf, ws.stx, tw, nullptr, nullptr, planes});
-        LAUNCH_CHECK();
-        X = ws.stx;
-    }
-    k_f256_bwd<<<grid, f256::THREADS, f256::SMEM_BYTES, s>>>(
-        f256::BwdParams{g, X, otf, tw, img_max, ws.acc, ws.sdot, B});
-    LAUNCH_CHECK();
-    k_f256_acc_reduce<<<3 * f256::NC, 256, 0, s>>>(
-        AccReduceParams{ws.acc, ws.stp, tw, grid, B, 0.25f / (static_cast<float>(N) * N)});
-    LAUNCH_CHECK();
-    k_rows_c2r<N><<<dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-        RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
-    LAUNCH_CHECK();
-    k_f256_tie<<<dim3(N, 3), 256, 0, s>>>(TieSpatialParams{grad_psf, img, ws.sdot, img_max, tie_count, tie_pos, ws.coef, B});
-    LAUNCH_CHECK();
-    if (grad_img != nullptr) {   // optional output (no reference caller asks for it): generic kernels
-        const dim3 rgrid(N / T::ROWS, planes);
-        k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-            RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
-        LAUNCH_CHECK();
-        const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
-        const int cchunks = conv_chunks(N, B);
-        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
-            ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunks, 1, 2.0f});
-        LAUNCH_CHECK();
-        k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
-            RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
-        LAUNCH_CHECK();
-        const long long tot = static_cast<long long>(planes) * N * N;
-        const int tgrid = static_cast<int>(tot / EW_THREADS < 148 * 8 ? (tot + EW_THREADS - 1) / EW_THREADS : 148 * 8);
-        k_tie_term_img<<<tgrid, EW_THREADS, 0, s>>>(TieTermImgParams{grad_img, psf, tie_count, tie_pos, ws.coef, B, N});
-        LAUNCH_CHECK();
-    }
-    return 0;
 }
 
 template <int N>
@@ -1016,10 +1050,57 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     SensorWs ws(ws_ptr, N, B, true);
-    if (N == 256 && fused_selected(B))
-        return fused_bwd(g, img, img_max, tie_count, tie_pos, psf, otf, spectrum, grad_psf, grad_img, tw, ws, B, s);
     const int planes = 3 * B, tiles = N / T::ROWS;
     const dim3 rgrid(tiles, planes);
+    if constexpr (N == 256) {
+        if (plane_selected()) {
+            const DeviceState* st = cur_state();
+            if (st == nullptr || st->pacc_g3 < 1 || st->pconv_g3 < 1) return B200CAM_E_NOT_INIT;
+            const float4* Xh = reinterpret_cast<const float4*>(spectrum);
+            if (Xh == nullptr) {                 // the forward did not keep X^: rebuild it (rows, then the column half of k_pconv)
+                int rc = sensor_rows_impl<N>(img, ws.stx, nullptr, nullptr, B, s);
+                if (rc) return rc;
+                const int G3c = B < st->pconv_g3 ? B : st->pconv_g3;
+                k_pconv<<<3 * G3c * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
+                    plane::ConvParams{reinterpret_cast<float4*>(ws.stx), otf, ws.pscratch, nullptr, tw, nullptr, nullptr, nullptr,
+                                      nullptr, B, G3c, 1, 0}, st->err_dev);
+                LAUNCH_CHECK();
+                Xh = reinterpret_cast<const float4*>(ws.stx);
+            }
+            const int G3 = B < st->pacc_g3 ? B : st->pacc_g3;
+            k_pacc<<<3 * G3 * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
+                plane::AccParams{g, Xh, otf, ws.pscratch, tw, img_max, ws.partial, ws.dot_lanes, B, G3});
+            LAUNCH_CHECK();
+            k_pcoef<<<(B + 63) / 64, 64, 0, s>>>(ws.dot_lanes, img_max, tie_count, ws.coef, B);
+            LAUNCH_CHECK();
+            k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
+                ColsReduceInvParams{ws.partial, ws.stp, tw, G3, 0.25f / (static_cast<float>(N) * N), nullptr, nullptr, nullptr, nullptr, 0});
+            LAUNCH_CHECK();
+            k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+                RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
+            LAUNCH_CHECK();
+            const int per_ch = N * N / 2 / EW_THREADS < 592 ? N * N / 2 / EW_THREADS : 592;
+            k_tie_term<<<dim3(per_ch, 3), EW_THREADS, 0, s>>>(TieTermParams{grad_psf, img, tie_count, tie_pos, ws.coef, B, N});
+            LAUNCH_CHECK();
+            if (grad_img != nullptr) {           // optional output (no reference caller asks for it): generic kernels on g
+                k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
+                LAUNCH_CHECK();
+                const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
+                const int cchunks = conv_chunks(N, B);
+                k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+                    ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunks, 1, 1.0f});
+                LAUNCH_CHECK();
+                k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+                    RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
+                LAUNCH_CHECK();
+                const long long tot = static_cast<long long>(planes) * N * N;
+                const int grid = static_cast<int>(tot / EW_THREADS < 148 * 8 ? (tot + EW_THREADS - 1) / EW_THREADS : 148 * 8);
+                k_tie_term_img<<<grid, EW_THREADS, 0, s>>>(TieTermImgParams{grad_img, psf, tie_count, tie_pos, ws.coef, B, N});
+                LAUNCH_CHECK();
+            }
+            return 0;
+        }
+    }
     const float2* srow = spectrum;
     if (srow == nullptr) {                       // forward did not keep the row spectra: recompute them
         k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
@@ -1107,11 +1188,21 @@ const char* b200cam_error_string(int code) {
         case B200CAM_E_WORKSPACE: return "b200cam: workspace too small";
         case B200CAM_E_NOT_INIT: return "b200cam: b200cam_init(N) was not called on this device";
         case B200CAM_E_ALIGN: return "b200cam: pointer not 16-byte aligned";
+        case B200CAM_E_DEVICE: return "b200cam: a kernel gave up waiting (image-max exchange, grid barrier or peer all-reduce); results of that call are invalid";
         default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "b200cam: unknown error";
     }
 }
 
 unsigned long long b200cam_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200cam_device_error(int clear) {
+    const DeviceState* st = cur_state();
+    if (st == nullptr || st->err_host == nullptr) return 0;
+    volatile unsigned* p = st->err_host;
+    const int v = static_cast<int>(*p);
+    if (clear && v != 0) *p = 0u;
+    return v;
+}
 
 int b200cam_supported(int N) { return N == 64 || N == 128 || N == 256 || N == 512 || N == 1024; }
 
@@ -1124,6 +1215,15 @@ int b200cam_init(int N) {
     const int l = log2i(N);
     if (g_state[dev].tw[l] != nullptr) return 0;
     if (g_state[dev].chain_ev == nullptr) CK(cudaEventCreateWithFlags(&g_state[dev].chain_ev, cudaEventDisableTiming));
+    if (g_state[dev].err_host == nullptr) {
+        unsigned* h = nullptr;
+        unsigned* d = nullptr;
+        CK(cudaHostAlloc(&h, 64, cudaHostAllocMapped));
+        *h = 0u;
+        CK(cudaHostGetDevicePointer(&d, h, 0));
+        g_state[dev].err_host = h;
+        g_state[dev].err_dev = d;
+    }
     if (g_state[dev].bar == nullptr) {
         unsigned* bar = nullptr;
         CK(cudaMalloc(&bar, 4 * sizeof(unsigned)));
@@ -1143,12 +1243,7 @@ int b200cam_init(int N) {
         case 512: e = init_kernels<512>(); break;
         case 1024: e = init_kernels<1024>(); break;
     }
-    if (e == cudaSuccess && N == 256) e = optin(k_f256_fwd, f256::SMEM_BYTES);
-    if (e == cudaSuccess && N == 256) e = optin(k_f256_bwd, f256::SMEM_BYTES);
-    // 132 KB of the 256 KB L1/shared array is enough for one CTA per SM: leave the rest to L1 (the OTF / spectrum
-    // columns are prefetched into it)
-    if (e == cudaSuccess && N == 256) e = cudaFuncSetAttribute(k_f256_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
-    if (e == cudaSuccess && N == 256) e = cudaFuncSetAttribute(k_f256_bwd, cudaFuncAttributePreferredSharedMemoryCarveout, 58);
+    if (e == cudaSuccess && N == 256) e = plane_init(dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_state[dev].sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) {
         const int sms = g_state[dev].sms;
@@ -1391,7 +1486,7 @@ int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float*
 }
 
 int b200cam_sensor_split_supported(int N, int B) {
-    return b200cam_supported(N) && B >= 1 && !(N == 256 && fused_selected(B));
+    return b200cam_supported(N) && B >= 1;
 }
 
 int b200cam_sensor_rows(const float* img, float* spectrum, float* img_max, int* tie_count, int B, int N, void* stream) {

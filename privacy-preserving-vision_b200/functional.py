@@ -123,6 +123,7 @@ class PsfSynth(torch.autograd.Function):
         """`stream`: enqueue the kernels there (after everything already on the current stream) and return WITHOUT
         joining - the caller must `current_stream().wait_stream(stream)` before using the outputs."""
         N = plan.N
+        _lib.raise_on_device_error(plan.index)          # a wait that timed out in an earlier step is reported here
         hc = _as_f32(h.detach(), plan.device).reshape(N, N)
         psf = torch.empty(1, 3, N, N, dtype=torch.float32, device=plan.device)
         field = torch.empty(3, N, N, 2, dtype=torch.float32, device=plan.device)

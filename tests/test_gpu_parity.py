@@ -244,7 +244,8 @@ def test_empty_batch():
 
 
 # ---------------------------------------------------------------------------------------------------------
-# fused N=256 sensor kernels (f256.cuh): opt-in with B200CAM_FUSED=1 (read once per process -> subprocess)
+# N=256 has two sensor paths: the plane kernels (plane.cuh, default) and the generic row/column/row kernels that the
+# other sizes use (B200CAM_PLANE=0, read once per process -> subprocess)
 # ---------------------------------------------------------------------------------------------------------
 _FORCED_FUSED_SCRIPT = r"""
 import sys, torch
@@ -276,14 +277,14 @@ print("REL", rel(y.detach(), out["sensor"].detach()), rel(h.grad, ho.grad), rel(
 
 
 @pytest.mark.parametrize("B", [3, 52])
-def test_fused_kernels_forced(B):
-    """B200CAM_FUSED=1 in a fresh process: fused TMEM kernels (B = 52: more planes than SMs, i.e. two rounds and
-    per-CTA accumulators over several images), sensor, dL/dh and the optional dL/dimg against the oracle."""
+def test_generic_kernels_forced_at_256(B):
+    """B200CAM_PLANE=0 in a fresh process: the generic kernels at N = 256 - sensor, dL/dh and the optional dL/dimg against
+    the oracle (the default path at this size is covered by every other N = 256 test in this file)."""
     import os
     import subprocess
     import sys
     from conftest import REPO
-    env = dict(os.environ, B200CAM_FUSED="1")
+    env = dict(os.environ, B200CAM_PLANE="0")
     res = subprocess.run([sys.executable, "-c", _FORCED_FUSED_SCRIPT.format(repo=str(REPO)), str(B)], env=env,
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
