@@ -215,40 +215,89 @@ struct PlaneCtx {
         const int s = (threadIdx.x & 16) | src;
         return make_float2(__shfl_sync(mask, t.u[idx].x, s), __shfl_sync(mask, t.u[idx].y, s));
     }
-    // the per-image maximum is taken across the 3 x 8 CTAs that hold the image's planes: max first, then the arrival
-    __device__ __forceinline__ void publish_max(unsigned* s, unsigned key) {
-        atomicMax(s, key);
-        __threadfence();
-        atomicAdd(s + 1, 1u);
+    __device__ __forceinline__ unsigned lane0_key() { return __shfl_sync(0xffffffffu, t.key, 0); }
+    __device__ __forceinline__ unsigned warp_max_key() { return __reduce_max_sync(0xffffffffu, t.key); }
+    __device__ __forceinline__ float warp_sum_dot() {
+        float s = t.dot;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);     // fixed tree: deterministic
+        return s;
     }
-    // All 24 CTAs are resident (the grid is one wave of co-scheduled clusters, sized from the occupancy API) and reach
-    // this point within a fraction of a plane of each other.  A wait that outlives ~2 s means a broken launch: it is
-    // reported through the device error word (b200cam_device_error), never turned into a silent result.
+    __device__ __forceinline__ void bulk_init(unsigned long long* bar) { BulkOps::init(bar); }
+    __device__ __forceinline__ void bulk_fence_init() { BulkOps::fence_init(); }
+    __device__ __forceinline__ void bulk_expect(unsigned long long* bar, unsigned bytes) { BulkOps::expect(bar, bytes); }
+    __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) { BulkOps::copy(dst, src, bytes, bar); }
+    __device__ __forceinline__ void bulk_wait(unsigned long long* bar, unsigned parity) { BulkOps::wait(bar, parity); }
+    // The per-image maximum is taken across the 3 x 8 CTAs that hold the image's planes: max first, then the arrival.
+    // No acquire fences anywhere on this path: an acquire at gpu / cluster scope makes ptxas emit CCTL.IVALL (the whole
+    // L1 of the SM is invalidated - measured: 30 % of this kernel's stall samples sat on it).  Release on the writer
+    // (membar + atomic) and L2-coherent accesses on the reader (relaxed.gpu load, then an atomic read of the max) order
+    // the two words without touching L1.
+    __device__ __forceinline__ void publish_max(unsigned* s, unsigned key) {
+        asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;\n" ::"l"(s), "r"(key) : "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(s + 1) : "memory");
+    }
+    // All 24 CTAs are resident (the grid is one wave of co-scheduled clusters, sized from the occupancy API) and published
+    // a whole pipeline step ago.  A wait that outlives ~2 s means a broken launch: it is reported through the device
+    // error word (b200cam_device_error), never turned into a silent result.
     __device__ __forceinline__ unsigned wait_max(unsigned* s, unsigned target) {
         unsigned n;
-        const long long t0 = clock64();
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(n) : "l"(s + 1) : "memory");
+        long long t0 = 0;
+        for (int spin = 0;; ++spin) {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(n) : "l"(s + 1) : "memory");
             if (n >= target) break;
-            if (clock64() - t0 > 4000000000LL) {
+            if (spin == 64) t0 = clock64();
+            if (spin > 64 && clock64() - t0 > 4000000000LL) {
                 if (err != nullptr) atomicExch(err, B200CAM_DEVERR_IMAGE_MAX_WAIT);
                 break;
             }
         }
         unsigned key;
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(key) : "l"(s) : "memory");
+        asm volatile("atom.relaxed.gpu.global.max.u32 %0, [%1], 0;\n" : "=r"(key) : "l"(s) : "memory");
         return key;
     }
 };
+// The barrier of a cluster is NOT barrier.cluster: its wait carries acquire semantics, for which ptxas emits CCTL.IVALL
+// (invalidate the SM's whole L1) - with bulk copies in flight that instruction alone held 30 % of k_pconv's stall samples.
+// The crossing data is read with L1-bypassing loads, so no invalidation is needed; what is needed is a release on the
+// writers and an arrival count the readers can poll:  bar.sync ; thread 0: red.release.gpu (membar + add) on the cluster's
+// word in global memory ... thread 0: poll with relaxed loads ; bar.sync.  The word is never reset: every CTA reads it
+// before an initial (hardware) cluster barrier, i.e. before any arrival of this launch, and counts from there - so the
+// workspace needs no initialisation and CUDA-graph replays just keep counting.
 struct PlaneExec {
     PlaneCtx ctx;
+    unsigned* ctr = nullptr;
+    unsigned base = 0, waits = 0;
     template <class F>
     __device__ __forceinline__ void each(F&& f) { f(ctx); }
     __device__ __forceinline__ void sync_warp() { __syncwarp(); }
     __device__ __forceinline__ void sync_cta() { __syncthreads(); }
-    __device__ __forceinline__ void sync_cluster() {
+    __device__ __forceinline__ void cluster_begin(unsigned* word) {
+        ctr = word;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(base) : "l"(ctr) : "memory");
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    }
+    __device__ __forceinline__ void cluster_arrive() {
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(ctr) : "memory");
+    }
+    __device__ __forceinline__ void cluster_wait() {
+        ++waits;
+        if (threadIdx.x == 0) {
+            unsigned n;
+            long long t0 = 0;
+            for (int spin = 0;; ++spin) {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(n) : "l"(ctr) : "memory");
+                if (n - base >= waits * plane::C) break;
+                if (spin == 64) t0 = clock64();
+                if (spin > 64 && clock64() - t0 > 4000000000LL) {
+                    if (ctx.err != nullptr) atomicExch(ctx.err, B200CAM_DEVERR_GRID_BARRIER);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
     }
 };
 
@@ -257,23 +306,22 @@ __global__ void __launch_bounds__(plane::THREADS, 4) k_prow(plane::RowParams p) 
     PlaneExec x{{0, static_cast<int>(threadIdx.x), t, SMEM2, nullptr}};
     plane::prow_body(x, p, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
 }
-__global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREADS, 3) k_pconv(plane::ConvParams p, unsigned* err) {
+__global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREADS, 2) k_pconv(plane::ConvParams p, unsigned* ctr, unsigned* err) {
     plane::Thread t;
     const int cluster = blockIdx.x / plane::C;
     PlaneExec x{{static_cast<int>(blockIdx.x % plane::C), static_cast<int>(threadIdx.x), t, SMEM2, err}};
-    x.each([&](auto& c) { plane::load_twiddles(c, p.tw); });
-    for (int it = 0; cluster / 3 + p.G3 * it < p.B; ++it) {
-        plane::pconv_front(x, p, cluster, it);
-        plane::pconv_back(x, p, cluster, it);
-    }
+    const int T = plane::planes_of_cluster(cluster, p.B, p.G3);
+    if (T == 0) return;
+    x.cluster_begin(ctr + 32 * cluster);
+    plane::pconv_init(x, p, cluster);
+    for (int it = 0; it <= T + 1; ++it) plane::pconv_step(x, p, cluster, it);
 }
-__global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREADS, 2) k_pacc(plane::AccParams p) {
+__global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREADS, 2) k_pacc(plane::AccParams p, unsigned* ctr, unsigned* err) {
     plane::Thread t;
     const int cluster = blockIdx.x / plane::C;
-    PlaneExec x{{static_cast<int>(blockIdx.x % plane::C), static_cast<int>(threadIdx.x), t, SMEM2, nullptr}};
-    plane::pacc_init(x, p);
-    for (int it = 0; cluster / 3 + p.G3 * it < p.B; ++it) plane::pacc_plane(x, p, cluster, it);
-    plane::pacc_finish(x, p, cluster);
+    PlaneExec x{{static_cast<int>(blockIdx.x % plane::C), static_cast<int>(threadIdx.x), t, SMEM2, err}};
+    x.cluster_begin(ctr + 32 * cluster);
+    plane::pacc_body(x, p, cluster);
 }
 // coef[b] = sum(g_b * y_b) / (n_b m_b) = sum(g_b * conv_b) / (n_b m_b^2) from the 24 per-CTA Parseval partials of k_pacc
 // (which carry a factor 4) - the weight of the arg-max term of the amax backward (Optics.py:128)
@@ -281,7 +329,7 @@ __global__ void __launch_bounds__(64) k_pcoef(const float* dotp, const float* im
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float s = 0.f;
-    for (int i = 0; i < 3 * plane::C; ++i) s += dotp[b * 3 * plane::C + i];          // fixed order: deterministic
+    for (int i = 0; i < 3 * plane::DOT_PER_PLANE; ++i) s += dotp[b * 3 * plane::DOT_PER_PLANE + i];     // fixed order: deterministic
     const int n = tie_count[b] > 0 ? tie_count[b] : 1;
     const float m = img_max[b];
     coef[b] = 0.25f * s / (static_cast<float>(n) * m * m);
@@ -561,16 +609,21 @@ static cudaError_t column_slots(int sms, int* conv, int* accum) {
 // an image exchange the image maximum through global memory while they are resident, so the grid must never exceed what
 // the device keeps resident at once (cudaOccupancyMaxActiveClusters), rounded down to whole triples.
 constexpr int PLANE_MAX_G3 = 24;        // sizes the crossing scratch and the partial planes of the backward
+// Measured (round 2, B = 64, one B200, CUDA-graph replay; profiles/r02_plane_kernels.md): k_prow 30 us, k_pconv 116 us,
+// k_pacc 70 us against 20 + (22 + 23 + 16) + (18 + 23) us for the generic kernels doing the same work - the cluster
+// kernels execute fewer bytes but every plane costs them ~6 dependent synchronisations (stage barrier, cluster arrive /
+// wait, image-max exchange) and the CTAs of a cluster and the clusters of an image all run at the pace of the slowest of
+// their 24 CTAs.  They stay in the tree as an opt-in (B200CAM_PLANE=1), tested, not as the default path.
 static bool plane_selected() {
-    static const bool on = [] { const char* e = getenv("B200CAM_PLANE"); return !(e && e[0] == '0'); }();
+    static const bool on = [] { const char* e = getenv("B200CAM_PLANE"); return e && e[0] == '1'; }();
     return on;
 }
 template <class K>
-static cudaError_t max_cluster_triples(K kernel, int* g3) {
+static cudaError_t max_cluster_triples(K kernel, int smem_bytes, int* g3) {
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(plane::THREADS);
     cfg.gridDim = dim3(plane::C);
-    cfg.dynamicSmemBytes = plane::SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = plane::C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -588,11 +641,11 @@ static cudaError_t max_cluster_triples(K kernel, int* g3) {
 static cudaError_t plane_init(int dev) {
     cudaError_t e;
     if ((e = optin(k_prow, plane::SMEM_BYTES))) return e;
-    if ((e = optin(k_pconv, plane::SMEM_BYTES))) return e;
-    if ((e = optin(k_pacc, plane::SMEM_BYTES))) return e;
+    if ((e = optin(k_pconv, plane::CONV_SMEM_BYTES))) return e;
+    if ((e = optin(k_pacc, plane::ACC_SMEM_BYTES))) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_state[dev].prow_fit, k_prow, plane::THREADS, plane::SMEM_BYTES))) return e;
-    if ((e = max_cluster_triples(k_pconv, &g_state[dev].pconv_g3))) return e;
-    if ((e = max_cluster_triples(k_pacc, &g_state[dev].pacc_g3))) return e;
+    if ((e = max_cluster_triples(k_pconv, plane::CONV_SMEM_BYTES, &g_state[dev].pconv_g3))) return e;
+    if ((e = max_cluster_triples(k_pacc, plane::ACC_SMEM_BYTES, &g_state[dev].pacc_g3))) return e;
     return cudaSuccess;
 }
 static DeviceState* cur_state() {
@@ -673,12 +726,13 @@ struct PsfWs {
 
 struct SensorWs {
     float2* stx; float2* stg; float2* partial; float2* stp; float* dot_lanes; float* coef;
-    float4* pscratch; float2* st2; int* arrive;
+    float4* pscratch; unsigned* pctr; float2* st2; int* arrive;
     size_t bytes;
     SensorWs(void* p, int N, int B, bool backward) {
         Carver c(p);
         // N = 256 plane kernels: crossing scratch of the resident clusters, [3 * G3][2][128 x 128] float4 (L2 resident)
-        pscratch = (N == 256) ? c.take<float4>(static_cast<size_t>(3) * (B < PLANE_MAX_G3 ? B : PLANE_MAX_G3) * 2 * plane::PLANE_F4) : nullptr;
+        pscratch = (N == 256) ? c.take<float4>(static_cast<size_t>(3) * (B < PLANE_MAX_G3 ? B : PLANE_MAX_G3) * plane::NBUF * plane::PLANE_F4) : nullptr;
+        pctr = (N == 256) ? c.take<unsigned>(static_cast<size_t>(3) * PLANE_MAX_G3 * 32) : nullptr;   // one arrival word per cluster, 128 B apart
         const size_t plane = static_cast<size_t>(N / 2 + 1) * N;
         stx = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
         st2 = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
@@ -877,8 +931,8 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
             const int G3 = B < st->pconv_g3 ? B : st->pconv_g3;
             float4* A = reinterpret_cast<float4*>(const_cast<float2*>(srow));
             unsigned* sync = reinterpret_cast<unsigned*>(A + static_cast<size_t>(planes) * plane::PLANE_F4);
-            k_pconv<<<3 * G3 * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
-                plane::ConvParams{A, otf, ws.pscratch, sensor, tw, sync, img_max, tie_count, tie_pos, B, G3, 1, 1}, st->err_dev);
+            k_pconv<<<3 * G3 * plane::C, plane::THREADS, plane::CONV_SMEM_BYTES, s>>>(
+                plane::ConvParams{A, otf, ws.pscratch, sensor, tw, sync, img_max, tie_count, tie_pos, B, G3, 1, 1}, ws.pctr, st->err_dev);
             LAUNCH_CHECK();
             return 0;
         }
@@ -931,9 +985,9 @@ static int conv_fwd_impl(const float* img, const float* kern, float* out, float2
             const DeviceState* st = cur_state();
             if (st == nullptr || st->pconv_g3 < 1) return B200CAM_E_NOT_INIT;
             const int G3 = B < st->pconv_g3 ? B : st->pconv_g3;
-            k_pconv<<<3 * G3 * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
+            k_pconv<<<3 * G3 * plane::C, plane::THREADS, plane::CONV_SMEM_BYTES, s>>>(
                 plane::ConvParams{reinterpret_cast<float4*>(srow), otf, ws.pscratch, out, tw, nullptr, nullptr, nullptr, nullptr, B, G3,
-                                  1, 0}, st->err_dev);
+                                  1, 0}, ws.pctr, st->err_dev);
             LAUNCH_CHECK();
             return 0;
         }
@@ -968,15 +1022,15 @@ static int conv_bwd_impl(const float* g, const float* img, const float2* otf, co
                 int rc = sensor_rows_impl<N>(img, ws.stx, nullptr, nullptr, B, s);
                 if (rc) return rc;
                 const int G3c = B < st->pconv_g3 ? B : st->pconv_g3;
-                k_pconv<<<3 * G3c * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
+                k_pconv<<<3 * G3c * plane::C, plane::THREADS, plane::CONV_SMEM_BYTES, s>>>(
                     plane::ConvParams{reinterpret_cast<float4*>(ws.stx), otf, ws.pscratch, nullptr, tw, nullptr, nullptr, nullptr,
-                                      nullptr, B, G3c, 1, 0}, st->err_dev);
+                                      nullptr, B, G3c, 1, 0}, ws.pctr, st->err_dev);
                 LAUNCH_CHECK();
                 Xh = reinterpret_cast<const float4*>(ws.stx);
             }
             const int G3 = B < st->pacc_g3 ? B : st->pacc_g3;
-            k_pacc<<<3 * G3 * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
-                plane::AccParams{g, Xh, otf, ws.pscratch, tw, nullptr, ws.partial, ws.dot_lanes, B, G3});
+            k_pacc<<<3 * G3 * plane::C, plane::THREADS, plane::ACC_SMEM_BYTES, s>>>(
+                plane::AccParams{g, Xh, otf, ws.pscratch, tw, nullptr, ws.partial, ws.dot_lanes, B, G3}, ws.pctr, st->err_dev);
             LAUNCH_CHECK();
             k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
                 ColsReduceInvParams{ws.partial, ws.stp, tw, G3, 0.25f / (static_cast<float>(N) * N), nullptr, nullptr, nullptr, nullptr, 0});
@@ -1061,15 +1115,15 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
                 int rc = sensor_rows_impl<N>(img, ws.stx, nullptr, nullptr, B, s);
                 if (rc) return rc;
                 const int G3c = B < st->pconv_g3 ? B : st->pconv_g3;
-                k_pconv<<<3 * G3c * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
+                k_pconv<<<3 * G3c * plane::C, plane::THREADS, plane::CONV_SMEM_BYTES, s>>>(
                     plane::ConvParams{reinterpret_cast<float4*>(ws.stx), otf, ws.pscratch, nullptr, tw, nullptr, nullptr, nullptr,
-                                      nullptr, B, G3c, 1, 0}, st->err_dev);
+                                      nullptr, B, G3c, 1, 0}, ws.pctr, st->err_dev);
                 LAUNCH_CHECK();
                 Xh = reinterpret_cast<const float4*>(ws.stx);
             }
             const int G3 = B < st->pacc_g3 ? B : st->pacc_g3;
-            k_pacc<<<3 * G3 * plane::C, plane::THREADS, plane::SMEM_BYTES, s>>>(
-                plane::AccParams{g, Xh, otf, ws.pscratch, tw, img_max, ws.partial, ws.dot_lanes, B, G3});
+            k_pacc<<<3 * G3 * plane::C, plane::THREADS, plane::ACC_SMEM_BYTES, s>>>(
+                plane::AccParams{g, Xh, otf, ws.pscratch, tw, img_max, ws.partial, ws.dot_lanes, B, G3}, ws.pctr, st->err_dev);
             LAUNCH_CHECK();
             k_pcoef<<<(B + 63) / 64, 64, 0, s>>>(ws.dot_lanes, img_max, tie_count, ws.coef, B);
             LAUNCH_CHECK();

@@ -120,7 +120,7 @@ def test_accumulate_kernel(B, G3):
     otf = _otf(psf)
     assert lib.emu_pconv(B, G3, _p(A), _p(otf), _p(y), _p(m), _p(tc), _p(tp), 1, 1) == 0
     partial = torch.zeros(G3, 3, 129, N, 2)
-    dotp = torch.zeros(3 * B, 8)
+    dotp = torch.zeros(3 * B, 64)
     assert lib.emu_pacc(B, G3, _p(w.contiguous()), _p(A), _p(otf), _p(m), _p(partial), _p(dotp)) == 0
     X = torch.fft.rfft2(img.double())                                               # [B][3][v][u]
     G = torch.fft.rfft2(w.double())
@@ -130,4 +130,4 @@ def test_accumulate_kernel(B, G3):
     K = torch.fft.rfft2(torch.roll(psf.double(), (-N // 2, -N // 2), (-2, -1)))
     conv = torch.fft.irfft2(X * K, s=(N, N))
     sdot = (w.double() * conv).sum(dim=(1, 2, 3))
-    assert rel_l2(dotp.double().reshape(B, 24).sum(1) / 4, sdot) < 1e-5
+    assert rel_l2(dotp.double().reshape(B, 192).sum(1) / 4, sdot) < 1e-5

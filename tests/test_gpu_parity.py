@@ -244,8 +244,8 @@ def test_empty_batch():
 
 
 # ---------------------------------------------------------------------------------------------------------
-# N=256 has two sensor paths: the plane kernels (plane.cuh, default) and the generic row/column/row kernels that the
-# other sizes use (B200CAM_PLANE=0, read once per process -> subprocess)
+# N=256 has two sensor paths: the generic row/column/row kernels (default, all sizes) and the cluster "plane" kernels of
+# plane.cuh (opt-in, B200CAM_PLANE=1, read once per process -> subprocess)
 # ---------------------------------------------------------------------------------------------------------
 _FORCED_FUSED_SCRIPT = r"""
 import sys, torch
@@ -277,14 +277,14 @@ print("REL", rel(y.detach(), out["sensor"].detach()), rel(h.grad, ho.grad), rel(
 
 
 @pytest.mark.parametrize("B", [3, 52])
-def test_generic_kernels_forced_at_256(B):
-    """B200CAM_PLANE=0 in a fresh process: the generic kernels at N = 256 - sensor, dL/dh and the optional dL/dimg against
-    the oracle (the default path at this size is covered by every other N = 256 test in this file)."""
+def test_plane_kernels_forced_at_256(B):
+    """B200CAM_PLANE=1 in a fresh process: the cluster plane kernels (B = 52: several planes per cluster, i.e. the whole
+    software pipeline incl. its drain steps) - sensor, dL/dh and the optional dL/dimg against the oracle."""
     import os
     import subprocess
     import sys
     from conftest import REPO
-    env = dict(os.environ, B200CAM_PLANE="0")
+    env = dict(os.environ, B200CAM_PLANE="1")
     res = subprocess.run([sys.executable, "-c", _FORCED_FUSED_SCRIPT.format(repo=str(REPO)), str(B)], env=env,
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
