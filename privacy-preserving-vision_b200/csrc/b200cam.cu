@@ -33,8 +33,9 @@ __global__ void __launch_bounds__(RowsStreamSmem<N>::THREADS) k_rows_r2c_persist
     rows_r2c_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
 }
 template <int N>
-__global__ void __launch_bounds__(RowsC2RStreamSmem<N>::THREADS) k_rows_c2r_persist(RowsC2RParams p, int tiles_total) {
+__global__ void __launch_bounds__(RowsC2RStreamSmem<N>::THREADS, N <= 256 ? 4 : 1) k_rows_c2r_persist(RowsC2RParams p, int tiles_total, unsigned* err) {
     DeviceExec ex;
+    ex.err = err;
     rows_c2r_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
 }
 template <int N>
@@ -940,17 +941,27 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     const dim3 rgrid(N / T::ROWS, planes);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int nchunks = conv_chunks(N, B);
+    static const int per_sm = [] { const char* e = getenv("B200CAM_C2R_PER_SM"); const int v = e ? atoi(e) : 4; return v; }();
+    // one-pass normalise (RowsC2RParams::arrive): the persistent inverse-row kernel writes conv / max directly
+    static const int one_pass = [] { const char* e = getenv("B200CAM_ONE_PASS"); return e ? atoi(e) : 1; }();
+    constexpr bool FUSABLE = (Plan<N>::R1 <= 16) && (Plan<N>::LANES == Plan<N>::R2);
+    const bool fused = FUSABLE && one_pass && per_sm > 0;
     k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
-        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f});
+        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f, fused ? ws.arrive : nullptr, fused ? B : 0});
     LAUNCH_CHECK();
     {
-        static const int per_sm = [] { const char* e = getenv("B200CAM_C2R_PER_SM"); const int v = e ? atoi(e) : 4; return v; }();
         if (per_sm > 0) {
             const int total = (N / T::ROWS) * planes;
             const int grid = persistent_grid(rows_fit(N, true), per_sm, total);
             static const int discard = [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }();
+            const DeviceState* st = cur_state();
             k_rows_c2r_persist<N><<<grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s>>>(
-                RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0, discard}, total);
+                RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, tie_count, tie_pos, 0, discard, fused ? ws.arrive : nullptr,
+                              fused ? 3 * (N / T::ROWS) : 0}, total, st != nullptr ? st->err_dev : nullptr);
+            if (fused) {
+                LAUNCH_CHECK();
+                return 0;
+            }
         } else {
             k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
                 RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0});

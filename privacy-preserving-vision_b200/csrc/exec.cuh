@@ -43,8 +43,76 @@ struct BulkOps {
         } while (!ok);
     }
 };
+
+// ---- tensor memory as a thread-private stash -------------------------------------------------------------------
+// TMEM (256 KB per SM) is addressed [lane][column]; a warp reaches the 32 lanes of its own quadrant, so "32 columns of
+// my lane" is 128 bytes of storage private to one thread that costs neither registers nor shared memory.  The fused
+// inverse-row + normalise kernel parks a tile's outputs there until the image maximum is known.
+struct Tmem {
+    static __device__ __forceinline__ void alloc(unsigned* smem_slot, unsigned ncols) {          // one warp, converged
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         static_cast<unsigned>(__cvta_generic_to_shared(smem_slot))), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    static __device__ __forceinline__ void dealloc(unsigned base, unsigned ncols) {               // the same warp
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(base), "r"(ncols) : "memory");
+    }
+    static __device__ __forceinline__ void st32(unsigned taddr, const float2 (&v)[16]) {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+            "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+            "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y),
+            "f"(v[4].x), "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y),
+            "f"(v[8].x), "f"(v[8].y), "f"(v[9].x), "f"(v[9].y), "f"(v[10].x), "f"(v[10].y), "f"(v[11].x), "f"(v[11].y),
+            "f"(v[12].x), "f"(v[12].y), "f"(v[13].x), "f"(v[13].y), "f"(v[14].x), "f"(v[14].y), "f"(v[15].x), "f"(v[15].y)
+            : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    }
+    static __device__ __forceinline__ void ld32(unsigned taddr, float2 (&v)[16]) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+            : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+              "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y),
+              "=f"(v[8].x), "=f"(v[8].y), "=f"(v[9].x), "=f"(v[9].y), "=f"(v[10].x), "=f"(v[10].y), "=f"(v[11].x),
+              "=f"(v[11].y), "=f"(v[12].x), "=f"(v[12].y), "=f"(v[13].x), "=f"(v[13].y), "=f"(v[14].x), "=f"(v[14].y),
+              "=f"(v[15].x), "=f"(v[15].y)
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    }
+};
+// cross-CTA hand-off without acquire fences (an acquire at gpu scope makes ptxas emit CCTL.IVALL - the SM's whole L1 is
+// invalidated): release on the writer, L2-coherent relaxed accesses on the reader
+struct HandOff {
+    static __device__ __forceinline__ void arrive(int* counter) {          // earlier writes of this thread, then +1
+        asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(counter) : "memory");
+    }
+    // lane 0 of the warp polls, every lane gets the answer; false = gave up after ~2 s
+    static __device__ __forceinline__ bool wait_count(const int* counter, int target) {
+        int ok = 1;
+        if ((threadIdx.x & 31) == 0) {
+            int n;
+            long long t0 = 0;
+            for (int spin = 0;; ++spin) {
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(n) : "l"(counter) : "memory");
+                if (n >= target) break;
+                if (spin == 64) t0 = clock64();
+                if (spin > 64 && clock64() - t0 > 4000000000LL) { ok = 0; break; }
+            }
+        }
+        return __shfl_sync(0xffffffffu, ok, 0) != 0;
+    }
+    static __device__ __forceinline__ float load_float(const float* p) {
+        float v;
+        asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
+        return v;
+    }
+};
 struct DeviceExec {
     static constexpr bool IS_HOST = false;
+    unsigned tmem = 0;       // base address of this CTA's TMEM allocation (kernels that stash), else unused
+    unsigned* err = nullptr; // device error word
     __device__ __forceinline__ int bx() const { return blockIdx.x; }
     __device__ __forceinline__ int by() const { return blockIdx.y; }
     __device__ __forceinline__ int nthreads() const { return blockDim.x; }
@@ -69,6 +137,26 @@ struct DeviceExec {
     __device__ __forceinline__ void bulk_expect(unsigned long long* bar, unsigned bytes) { BulkOps::expect(bar, bytes); }
     __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) { BulkOps::copy(dst, src, bytes, bar); }
     __device__ __forceinline__ void bulk_wait(unsigned long long* bar, unsigned parity) { BulkOps::wait(bar, parity); }
+    // thread-private stash of up to 16 complex values (see Tmem)
+    template <int R>
+    __device__ __forceinline__ void stash_put(const float2 (&v)[R]) {
+        static_assert(R <= 16, "stash holds 16 complex values per thread");
+        float2 w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = i < R ? v[i] : make_float2(0.f, 0.f);
+        Tmem::st32(tmem + (((threadIdx.x >> 5) & 3u) << 21), w);
+    }
+    template <int R>
+    __device__ __forceinline__ void stash_get(float2 (&v)[R]) {
+        float2 w[16];
+        Tmem::ld32(tmem + (((threadIdx.x >> 5) & 3u) << 21), w);
+#pragma unroll
+        for (int i = 0; i < R; ++i) v[i] = w[i];
+    }
+    __device__ __forceinline__ void arrive(int* counter) { HandOff::arrive(counter); }
+    __device__ __forceinline__ bool wait_count(const int* counter, int target) { return HandOff::wait_count(counter, target); }
+    __device__ __forceinline__ float load_coherent(const float* p) { return HandOff::load_float(p); }
+    __device__ __forceinline__ void report(unsigned code) { if (err != nullptr) atomicExch(err, code); }
 };
 // A "virtual block" of a cooperative kernel: the CTA plays block (vbx, vby) of a body written for
 // `nthr` threads; surplus threads only take part in the barriers.
@@ -98,6 +186,12 @@ struct VirtualExec {
     __device__ __forceinline__ void bulk_expect(unsigned long long* bar, unsigned bytes) { BulkOps::expect(bar, bytes); }
     __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) { BulkOps::copy(dst, src, bytes, bar); }
     __device__ __forceinline__ void bulk_wait(unsigned long long* bar, unsigned parity) { BulkOps::wait(bar, parity); }
+    template <int R> __device__ __forceinline__ void stash_put(const float2 (&)[R]) {}
+    template <int R> __device__ __forceinline__ void stash_get(float2 (&)[R]) {}
+    __device__ __forceinline__ void arrive(int* counter) { HandOff::arrive(counter); }
+    __device__ __forceinline__ bool wait_count(const int* counter, int target) { return HandOff::wait_count(counter, target); }
+    __device__ __forceinline__ float load_coherent(const float* p) { return HandOff::load_float(p); }
+    __device__ __forceinline__ void report(unsigned) {}
 };
 #endif
 
@@ -126,6 +220,13 @@ struct HostExec {
     void bulk_expect(unsigned long long*, unsigned) {}
     void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long*) { std::memcpy(dst, src, bytes); }
     void bulk_wait(unsigned long long*, unsigned) {}
+    // the fused inverse-row + normalise mode exchanges maxima between concurrently running CTAs: device only
+    template <int R> void stash_put(const float2 (&)[R]) {}
+    template <int R> void stash_get(float2 (&)[R]) {}
+    void arrive(int* counter) { *counter += 1; }
+    bool wait_count(const int*, int) { return true; }
+    float load_coherent(const float* p) { return *p; }
+    void report(unsigned) {}
 };
 
 }  // namespace b200cam

@@ -243,7 +243,9 @@ struct ColsConvParams {
     int B;
     int nchunks;             // = gridDim.y: CTA (., y) owns images [B*y/nchunks, B*(y+1)/nchunks) (balanced split)
     int conj_otf;
-    float otf_scale;         // extra factor on the OTF (the fused N=256 path stores it pre-halved)
+    float otf_scale;         // extra factor on the OTF
+    int* zero_ints;          // nullable: n_zero ints zeroed by CTA (0,0) for the kernel that follows (arrival counters)
+    int n_zero;
 };
 
 template <int N>
@@ -297,6 +299,8 @@ B200_HD void cols_conv_body(Exec& ex, const ColsConvParams& p, float2* smem, Con
     ex.warp_phase([&](int tid) {
         const int jc = tid / P::LANES, b = tid % P::LANES;
         const int cu = cu0 + jc;
+        if (p.zero_ints != nullptr && ex.bx() == 0 && ex.by() == 0)
+            for (int i = tid; i < p.n_zero; i += S::THREADS) p.zero_ints[i] = 0;
         if (cu < TOTAL && b < P::R1) {
             ConvState<N>& s = st[ex.slot(tid)];
             const float2* k = p.otf + static_cast<size_t>(cu) * N;
@@ -450,6 +454,12 @@ struct RowsC2RParams {
     int* tie_pos;        // [planes/3][MAX_TIES] flat index into (3,N,N)
     int norm;
     int discard_input;   // stream kernel: `st` is dead after this pass - drop its lines from L2 instead of writing them back
+    // stream kernel, arrivals > 0: ONE pass - y = conv / max is written directly.  A tile's outputs wait in the thread's
+    // registers while its CTA max is published ({atomic max, arrival count} per image); the CTA finishes the
+    // tile one iteration later, when the `arrivals` tiles of that image - all processed in the same wave of the
+    // persistent grid - have long arrived.  No un-normalised image, no normalise pass (Optics.py:128).
+    int* arrive;         // [planes/3], zero on entry
+    int arrivals;        // tiles per image = 3 * N / ROWS
 };
 
 template <int N, class Exec>
@@ -595,6 +605,41 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
                          Q::SEG * 8, bars + buf);
     };
 
+    // one-pass normalise (see RowsC2RParams::arrive): every lane holds a full transform output (LANES == R2) of <= 16 values
+    constexpr bool FUSABLE = (P::R1 <= 16) && (P::LANES == P::R2);
+    const bool fused = FUSABLE && p.arrivals > 0 && p.arrive != nullptr && p.img_max != nullptr && p.out != nullptr;
+    // the previous tile's outputs wait here (registers, or thread-private local memory where the compiler spills them: tensor
+    // memory would be the natural stash, but a kernel that contains tcgen05.alloc is limited to ONE CTA per SM by the
+    // launch machinery - measured: grid 592 -> 148)
+    struct OutState { float2 v[P::R1]; };
+    OutState keep[Exec::IS_HOST ? S::THREADS : 1], cur[Exec::IS_HOST ? S::THREADS : 1];
+    // write the stashed tile `tt` as conv / max of its image; the positions that attain the max are recorded for the backward
+    auto finish = [&](int tid, int tt) {
+        const int fplane = tt / TILES, fy0 = (tt % TILES) * T::ROWS, img = fplane / 3;
+        if (!ex.wait_count(p.arrive + img, p.arrivals)) ex.report(1u);
+        const float m = ex.load_coherent(p.img_max + img);
+        const float inv = 1.0f / m;
+        const int j = tid / P::LANES, a = tid % P::LANES;
+        const float2 (&v)[P::R1] = keep[ex.slot(tid)].v;
+        const size_t row = (static_cast<size_t>(fplane) * N + fy0 + 2 * j) * N;
+        unsigned eq = 0u;
+#pragma unroll
+        for (int i = 0; i < P::R1; ++i) {
+            eq |= (v[i].x == m ? 1u : 0u) << (2 * i);
+            eq |= (v[i].y == m ? 1u : 0u) << (2 * i + 1);
+            p.out[row + P::R2 * i + a] = v[i].x == m ? 1.0f : v[i].x * inv;       // the arg-max itself: exactly 1 (torch: x / x)
+            p.out[row + N + P::R2 * i + a] = v[i].y == m ? 1.0f : v[i].y * inv;
+        }
+        while (eq != 0u) {                                                         // rare
+            int bit = 0;
+            while (((eq >> bit) & 1u) == 0u) ++bit;
+            eq &= eq - 1u;
+            const int slot = atomic_add_int(p.tie_count + img, 1);
+            if (slot < C2R_MAX_TIES)
+                p.tie_pos[img * C2R_MAX_TIES + slot] = (fplane % 3) * N * N + (fy0 + 2 * j + (bit & 1)) * N + P::R2 * (bit >> 1) + a;
+        }
+    };
+
     ex.phase([&](int tid) {
         if (tid == 0) {
             ex.bulk_init(bars + 0);
@@ -665,10 +710,11 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
 #pragma unroll
                 for (int i = 0; i < P::R1; ++i) {
                     const float e = v[i].x * p.scale, o = v[i].y * p.scale;
-                    if (p.out != nullptr) {
+                    if (p.out != nullptr && !fused) {
                         p.out[row + P::R2 * i + a] = e;
                         p.out[row + N + P::R2 * i + a] = o;
                     }
+                    if constexpr (FUSABLE) cur[ex.slot(tid)].v[i] = make_float2(e, o);
                     mx = fmaxf(mx, fmaxf(e, o));
                 }
             }
@@ -680,9 +726,20 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
                     float mx = red[0];
                     for (int k = 1; k < S::THREADS; ++k) mx = fmaxf(mx, red[k]);
                     atomic_max_float(p.img_max + plane / 3, mx);
+                    if (fused) ex.arrive(p.arrive + plane / 3);        // release: the max above is visible before the count
+                }
+                if constexpr (FUSABLE) {
+                    if (fused) {
+                        if (it > 0) finish(tid, t - nctas);            // the previous tile's image is complete by now
+#pragma unroll
+                        for (int i = 0; i < P::R1; ++i) keep[ex.slot(tid)].v[i] = cur[ex.slot(tid)].v[i];
+                    }
                 }
             });
         }
+    }
+    if constexpr (FUSABLE) {
+        if (fused && it > 0) ex.phase([&](int tid) { finish(tid, first + (it - 1) * nctas); });
     }
 }
 
