@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <utility>
 
 #include "../../include/b200cam.h"
 #include "kernels.cuh"
@@ -17,10 +18,18 @@ namespace b200cam {
 // __global__ wrappers: one CUDA thread per Exec "tid", dynamic shared memory as float2[]
 // ------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char smem_raw[];
+// programmatic dependent launch: let the next kernel of the stream be scheduled now, then wait until the previous one has
+// completed and its writes are visible (no-ops for a kernel launched without the attribute)
+__constant__ int c_pdl_trigger = 0;      // 1: signal the dependents at kernel entry (B200CAM_PDL_TRIGGER=1); 0: at completion
+__device__ __forceinline__ void pdl_gate() {
+    if (c_pdl_trigger) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
 #define SMEM2 reinterpret_cast<float2*>(smem_raw)
 
 template <int N>
 __global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_r2c(RowsR2CParams p) {
+    pdl_gate();
     DeviceExec ex;
     rows_r2c_body<N>(ex, p, SMEM2);
 }
@@ -29,47 +38,56 @@ __global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_r2c(RowsR2CPar
 // small high-priority kernels need free registers / shared memory on every SM the moment they are launched
 template <int N>
 __global__ void __launch_bounds__(RowsStreamSmem<N>::THREADS) k_rows_r2c_persist(RowsR2CParams p, int tiles_total) {
+    pdl_gate();
     DeviceExec ex;
     rows_r2c_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
 }
 template <int N>
 __global__ void __launch_bounds__(RowsC2RStreamSmem<N>::THREADS, N <= 256 ? 4 : 1) k_rows_c2r_persist(RowsC2RParams p, int tiles_total, unsigned* err) {
+    pdl_gate();
     DeviceExec ex;
     ex.err = err;
     rows_c2r_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
 }
 template <int N>
 __global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 4 : (N == 512 ? 2 : 1)) k_cols_conv(ColsConvParams p) {
+    pdl_gate();
     DeviceExec ex;
     ConvState<N> st;
     cols_conv_body<N>(ex, p, SMEM2, &st);
 }
 template <int N>
 __global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_cols_fwd(ColsFwdParams p) {
+    pdl_gate();
     DeviceExec ex;
     cols_fwd_body<N>(ex, p, SMEM2);
 }
 template <int N>
 __global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_rows_c2r(RowsC2RParams p) {
+    pdl_gate();
     DeviceExec ex;
     rows_c2r_body<N>(ex, p, SMEM2);
 }
 __global__ void __launch_bounds__(EW_THREADS) k_normalise(NormaliseParams p) {
+    pdl_gate();
     DeviceExec ex;
     normalise_body(ex, p, gridDim.x);
 }
 template <int N>
 __global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 3 : 1) k_cols_accum(ColsAccumParams p) {
+    pdl_gate();
     DeviceExec ex;
     AccumState<N> st;
     cols_accum_body<N>(ex, p, SMEM2, &st);
 }
 template <int N>
 __global__ void __launch_bounds__(ReduceInvSmem<N>::THREADS) k_cols_reduce_inv(ColsReduceInvParams p) {
+    pdl_gate();
     DeviceExec ex;
     cols_reduce_inv_body<N>(ex, p, SMEM2);
 }
 __global__ void __launch_bounds__(EW_THREADS) k_tie_term(TieTermParams p) {
+    pdl_gate();
     __shared__ float s_coef[TIE_PASS * MAX_TIES];
     __shared__ int s_meta[3 * TIE_PASS * MAX_TIES];
     __shared__ int s_cnt[TIE_PASS + 1];
@@ -77,26 +95,31 @@ __global__ void __launch_bounds__(EW_THREADS) k_tie_term(TieTermParams p) {
     tie_term_body(ex, p, gridDim.x, s_coef, s_meta, s_cnt);
 }
 __global__ void __launch_bounds__(EW_THREADS) k_tie_term_img(TieTermImgParams p) {
+    pdl_gate();
     DeviceExec ex;
     tie_term_img_body(ex, p, gridDim.x);
 }
 template <int N, class Load>
 __global__ void __launch_bounds__(CRowsSmem<N>::THREADS) k_crows_fwd(CRowsFwdParams p, Load load) {
+    pdl_gate();
     DeviceExec ex;
     crows_fwd_body<N>(ex, p, load, SMEM2);
 }
 template <int N>
 __global__ void __launch_bounds__(CColsSmem<N>::THREADS) k_ccols_mix(CColsMixParams p) {
+    pdl_gate();
     DeviceExec ex;
     ccols_mix_body<N>(ex, p, SMEM2);
 }
 template <int N, class Epi>
 __global__ void __launch_bounds__(CRowsSmem<N>::THREADS) k_crows_inv(CRowsInvParams p, Epi epi) {
+    pdl_gate();
     DeviceExec ex;
     crows_inv_body<N>(ex, p, epi, SMEM2);
 }
 template <int N>
 __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad(CRowsInvParams p, PupilLoad pupil, float* gh) {
+    pdl_gate();
     DeviceExec ex;
     crows_inv_hgrad_body<N>(ex, p, pupil, gh, SMEM2);
 }
@@ -124,6 +147,7 @@ struct CommDev {
 template <int N>
 __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad_allreduce(CRowsInvParams p, PupilLoad pupil,
                                                                                      float* gh, CommDev c) {
+    pdl_gate();
     DeviceExec ex;
     crows_inv_hgrad_body<N>(ex, p, pupil, gh, SMEM2);            // local dL/dh rows of this tile -> gh (ends with a barrier)
     __shared__ unsigned s_epoch;
@@ -189,11 +213,13 @@ __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad_allre
 }
 
 __global__ void __launch_bounds__(EW_THREADS) k_psf_finalise(PsfFinaliseParams p) {
+    pdl_gate();
     __shared__ float red[3 * EW_THREADS + 2];
     DeviceExec ex;
     psf_finalise_body(ex, p, gridDim.x, red);
 }
 __global__ void __launch_bounds__(EW_THREADS) k_psf_grad_prepare(PsfGradPrepParams p) {
+    pdl_gate();
     __shared__ float red[EW_THREADS];
     DeviceExec ex;
     psf_grad_prepare_body(ex, p, gridDim.x, red);
@@ -303,11 +329,13 @@ struct PlaneExec {
 };
 
 __global__ void __launch_bounds__(plane::THREADS, 4) k_prow(plane::RowParams p) {
+    pdl_gate();
     plane::Thread t;
     PlaneExec x{{0, static_cast<int>(threadIdx.x), t, SMEM2, nullptr}};
     plane::prow_body(x, p, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x));
 }
 __global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREADS, 2) k_pconv(plane::ConvParams p, unsigned* ctr, unsigned* err) {
+    pdl_gate();
     plane::Thread t;
     const int cluster = blockIdx.x / plane::C;
     PlaneExec x{{static_cast<int>(blockIdx.x % plane::C), static_cast<int>(threadIdx.x), t, SMEM2, err}};
@@ -318,6 +346,7 @@ __global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREAD
     for (int it = 0; it <= T + 1; ++it) plane::pconv_step(x, p, cluster, it);
 }
 __global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREADS, 2) k_pacc(plane::AccParams p, unsigned* ctr, unsigned* err) {
+    pdl_gate();
     plane::Thread t;
     const int cluster = blockIdx.x / plane::C;
     PlaneExec x{{static_cast<int>(blockIdx.x % plane::C), static_cast<int>(threadIdx.x), t, SMEM2, err}};
@@ -327,6 +356,7 @@ __global__ void __cluster_dims__(plane::C, 1, 1) __launch_bounds__(plane::THREAD
 // coef[b] = sum(g_b * y_b) / (n_b m_b) = sum(g_b * conv_b) / (n_b m_b^2) from the 24 per-CTA Parseval partials of k_pacc
 // (which carry a factor 4) - the weight of the arg-max term of the amax backward (Optics.py:128)
 __global__ void __launch_bounds__(64) k_pcoef(const float* dotp, const float* img_max, const int* tie_count, float* coef, int B) {
+    pdl_gate();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float s = 0.f;
@@ -384,6 +414,7 @@ struct PsfFwdArgs {
 
 template <int N>
 __global__ void __launch_bounds__(COOP_THREADS) k_psf_fwd_coop(PsfFwdArgs a) {
+    pdl_gate();
     GridBarrier grid{a.barrier};
     __shared__ float red[3 * EW_THREADS + 2];
     using T = Tile<N>;
@@ -420,6 +451,7 @@ struct PsfBwdArgs {
 
 template <int N>
 __global__ void __launch_bounds__(COOP_THREADS) k_psf_bwd_coop(PsfBwdArgs a) {
+    pdl_gate();
     GridBarrier grid{a.barrier};
     __shared__ float red[3 * EW_THREADS + 2];
     using T = Tile<N>;
@@ -456,21 +488,25 @@ static_assert(HGradSmem<1024>::THREADS <= COOP_THREADS && HGradSmem<512>::THREAD
               "cooperative block too small for a body");
 
 __global__ void __launch_bounds__(EW_THREADS) k_zernike_fwd(ZernikeFwdParams p) {
+    pdl_gate();
     __shared__ int flag;
     DeviceExec ex;
     zernike_fwd_body(ex, p, &flag);
 }
 __global__ void __launch_bounds__(EW_THREADS) k_zernike_bwd(ZernikeBwdParams p) {
+    pdl_gate();
     __shared__ float red[EW_THREADS];
     DeviceExec ex;
     zernike_bwd_body(ex, p, red);
 }
 
 __global__ void __launch_bounds__(EW_THREADS) k_crop_abs_resize_fwd(CropAbsResizeParams p) {
+    pdl_gate();
     DeviceExec ex;
     crop_abs_resize_fwd_body(ex, p, gridDim.x);
 }
 __global__ void __launch_bounds__(EW_THREADS) k_crop_abs_resize_bwd(CropAbsResizeBwdParams p) {
+    pdl_gate();
     DeviceExec ex;
     crop_abs_resize_bwd_body(ex, p, gridDim.x);
 }
@@ -765,6 +801,49 @@ static std::atomic<unsigned long long> g_launches{0};
     } while (0)
 
 // ------------------------------------------------------------------------------------------
+// Every kernel of the library is launched through launch_k.  Programmatic dependent launch is wired in
+// - every kernel starts with pdl_gate(), the small kernels of the PSF chain / backward tail are launched with the
+// attribute - but it is OFF by default (B200CAM_PDL=1 enables; B200CAM_PDL_TRIGGER=1 also signals dependents at kernel
+// entry).  Measured, B = 64, graph replay (profiles/r02_pdl.md): 173 us per step without, 179 us with completion-time
+// trigger, 183-197 us with entry-time trigger: the early-resident CTAs of the next kernels take registers / shared
+// memory / issue slots from the kernel that is still running (the chain's head gets 6 us shorter, the image row pass
+// beside it 9 us longer, tie_term and the last kernel 6-7 us longer each).
+// ------------------------------------------------------------------------------------------
+static bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("B200CAM_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+// `Pdl`: the launch may overlap the tail of its predecessor.  Only the small kernels of the PSF chain and of the backward tail
+// ask for it: a big batch kernel whose CTAs start early just sits on registers / shared memory that the concurrently
+// running PSF chain (side stream) needs - measured 197 us per step with every launch programmatic, 174 us with none.
+struct Pdl {};
+template <class... KArgs, class... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args);
+template <class... KArgs, class... Args>
+static void launch_k(Pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);      // errors: cudaGetLastError in LAUNCH_CHECK
+}
+template <class... KArgs, class... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+// ------------------------------------------------------------------------------------------
 // launch sequences
 // ------------------------------------------------------------------------------------------
 // first part of the PSF synthesis: pupil -> propagated field U, |U|^2 (workspace) and S = sum |U|^2 (stats[0])
@@ -777,7 +856,7 @@ static int psf_field_impl(const float* h, const float2* A, const float2* Ht, con
     PsfWs ws(ws_ptr, N);
     PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
     const dim3 rgrid(N / T::CROWS, 3);
-    k_crows_fwd<N, PupilLoad><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(CRowsFwdParams{ws.st, tw}, load);
+    launch_k(k_crows_fwd<N, PupilLoad>, rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s, CRowsFwdParams{ws.st, tw}, load);
     LAUNCH_CHECK();
     if (has_dependent) {
         // The caller's big batch kernel (image row pass) is held back until this first small kernel is done: both it and
@@ -788,10 +867,10 @@ static int psf_field_impl(const float* h, const float2* A, const float2* Ht, con
         CK(cudaEventRecord(ev, s));
         CK(cudaStreamWaitEvent(dependent, ev, 0));
     }
-    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(
+    launch_k(Pdl{}, k_ccols_mix<N>, (N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s, 
         CColsMixParams{ws.st, Ht, tw, 0, 1.0f / (3.0f * N * N)});
     LAUNCH_CHECK();
-    k_crows_inv<N, IntensityEpilogue><<<rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(
+    launch_k(Pdl{}, k_crows_inv<N, IntensityEpilogue>, rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s, 
         CRowsInvParams{ws.st, tw}, IntensityEpilogue{field, ws.I, ws.part_rows, ws.arrive, N});
     LAUNCH_CHECK();
     return 0;
@@ -801,7 +880,7 @@ static int psf_field_impl(const float* h, const float2* A, const float2* Ht, con
 template <int N>
 static int psf_finish_impl(const float* rho, float* psf, float* stats, void* ws_ptr, cudaStream_t s) {
     PsfWs ws(ws_ptr, N);
-    k_psf_finalise<<<ew_grid(N), EW_THREADS, 0, s>>>(PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, 3 * (N / Tile<N>::CROWS), N});
+    launch_k(Pdl{}, k_psf_finalise, ew_grid(N), EW_THREADS, 0, s, PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, 3 * (N / Tile<N>::CROWS), N});
     LAUNCH_CHECK();
     return 0;
 }
@@ -851,17 +930,17 @@ static int psf_bwd_impl(const float* gpsf, const float* g_rad, const float* g_ce
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
-    k_psf_grad_prepare<<<ew_grid(N), EW_THREADS, 0, s>>>(PsfGradPrepParams{gpsf, g_rad, g_cen, psf, rho, stats, ws.gtot, ws.part_ew, N});
+    launch_k(Pdl{}, k_psf_grad_prepare, ew_grid(N), EW_THREADS, 0, s, PsfGradPrepParams{gpsf, g_rad, g_cen, psf, rho, stats, ws.gtot, ws.part_ew, N});
     LAUNCH_CHECK();
-    k_crows_fwd<N, GradFieldLoad><<<dim3(N / T::CROWS, 3), CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s>>>(
+    launch_k(Pdl{}, k_crows_fwd<N, GradFieldLoad>, dim3(N / T::CROWS, 3), CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s, 
         rf, GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, ew_grid(N), N});
     LAUNCH_CHECK();
-    k_ccols_mix<N><<<(N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s>>>(mix);
+    launch_k(Pdl{}, k_ccols_mix<N>, (N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s, mix);
     LAUNCH_CHECK();
     if (comm != nullptr)
-        k_crows_inv_hgrad_allreduce<N><<<N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s>>>(ri, pupil, grad_h, *comm);
+        launch_k(Pdl{}, k_crows_inv_hgrad_allreduce<N>, N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s, ri, pupil, grad_h, *comm);
     else
-        k_crows_inv_hgrad<N><<<N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s>>>(ri, pupil, grad_h);
+        launch_k(Pdl{}, k_crows_inv_hgrad<N>, N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s, ri, pupil, grad_h);
     LAUNCH_CHECK();
     return 0;
 }
@@ -870,11 +949,11 @@ template <int N>
 static int otf_impl(const float* src, float2* otf, const float2* tw, float scale, cudaStream_t s,
                     const float* sum_partials = nullptr, int npartials = 0) {
     using T = Tile<N>;
-    k_rows_r2c<N><<<dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+    launch_k(Pdl{}, k_rows_r2c<N>, dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
         RowsR2CParams{src, otf, tw, nullptr, nullptr});
     LAUNCH_CHECK();
     const int total = 3 * T::NC;
-    k_cols_fwd<N><<<(total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+    launch_k(Pdl{}, k_cols_fwd<N>, (total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s, 
         ColsFwdParams{otf, tw, total, 1, scale, sum_partials, npartials});
     LAUNCH_CHECK();
     return 0;
@@ -900,14 +979,14 @@ static int sensor_rows_impl(const float* img, float2* srow, float* img_max, int*
             if (img_max != nullptr) CK(cudaMemsetAsync(A + static_cast<size_t>(planes) * plane::PLANE_F4, 0, sizeof(unsigned) * 2 * B, s));
             if (tie_count != nullptr) CK(cudaMemsetAsync(tie_count, 0, sizeof(int) * B, s));
             const int grid = persistent_grid(st->prow_fit, per_sm, planes * 8);
-            k_prow<<<grid, plane::THREADS, plane::SMEM_BYTES, s>>>(plane::RowParams{img, A, tw, planes});
+            launch_k(k_prow, grid, plane::THREADS, plane::SMEM_BYTES, s, plane::RowParams{img, A, tw, planes});
             LAUNCH_CHECK();
             return 0;
         }
     }
     const int total = (N / T::ROWS) * 3 * B;
     const int grid = persistent_grid(rows_fit(N, false), per_sm, total);
-    k_rows_r2c_persist<N><<<grid, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES, s>>>(
+    launch_k(k_rows_r2c_persist<N>, grid, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES, s, 
         RowsR2CParams{img, srow, tw, img_max, tie_count}, total);
     LAUNCH_CHECK();
     return 0;
@@ -946,7 +1025,7 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     static const int one_pass = [] { const char* e = getenv("B200CAM_ONE_PASS"); return e ? atoi(e) : 1; }();
     constexpr bool FUSABLE = (Plan<N>::R1 <= 16) && (Plan<N>::LANES == Plan<N>::R2);
     const bool fused = FUSABLE && one_pass && per_sm > 0;
-    k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+    launch_k(k_cols_conv<N>, dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s, 
         ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f, fused ? ws.arrive : nullptr, fused ? B : 0});
     LAUNCH_CHECK();
     {
@@ -955,7 +1034,7 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
             const int grid = persistent_grid(rows_fit(N, true), per_sm, total);
             static const int discard = [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }();
             const DeviceState* st = cur_state();
-            k_rows_c2r_persist<N><<<grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s>>>(
+            launch_k(k_rows_c2r_persist<N>, grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s, 
                 RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, tie_count, tie_pos, 0, discard, fused ? ws.arrive : nullptr,
                               fused ? 3 * (N / T::ROWS) : 0}, total, st != nullptr ? st->err_dev : nullptr);
             if (fused) {
@@ -963,14 +1042,14 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
                 return 0;
             }
         } else {
-            k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+            launch_k(k_rows_c2r<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
                 RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0});
         }
     }
     LAUNCH_CHECK();
     const long long n4 = static_cast<long long>(planes) * N * N / 4;
     const int grid = static_cast<int>(n4 / EW_THREADS < 148 * 8 ? (n4 + EW_THREADS - 1) / EW_THREADS : 148 * 8);
-    k_normalise<<<grid, EW_THREADS, 0, s>>>(NormaliseParams{sensor, img_max, tie_count, tie_pos, n4, 3 * N * N / 4});
+    launch_k(k_normalise, grid, EW_THREADS, 0, s, NormaliseParams{sensor, img_max, tie_count, tie_pos, n4, 3 * N * N / 4});
     LAUNCH_CHECK();
     return 0;
 }
@@ -1005,10 +1084,10 @@ static int conv_fwd_impl(const float* img, const float* kern, float* out, float2
     }
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int nchunks = conv_chunks(N, B);
-    k_cols_conv<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+    launch_k(k_cols_conv<N>, dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s, 
         ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f});
     LAUNCH_CHECK();
-    k_rows_c2r<N><<<dim3(N / T::ROWS, planes), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+    launch_k(k_rows_c2r<N>, dim3(N / T::ROWS, planes), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
         RowsC2RParams{ws.st2, out, tw, nullptr, 1.0f, nullptr, nullptr, 0});
     LAUNCH_CHECK();
     return 0;
@@ -1043,21 +1122,21 @@ static int conv_bwd_impl(const float* g, const float* img, const float2* otf, co
             k_pacc<<<3 * G3 * plane::C, plane::THREADS, plane::ACC_SMEM_BYTES, s>>>(
                 plane::AccParams{g, Xh, otf, ws.pscratch, tw, nullptr, ws.partial, ws.dot_lanes, B, G3}, ws.pctr, st->err_dev);
             LAUNCH_CHECK();
-            k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
+            launch_k(Pdl{}, k_cols_reduce_inv<N>, 3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s, 
                 ColsReduceInvParams{ws.partial, ws.stp, tw, G3, 0.25f / (static_cast<float>(N) * N), nullptr, nullptr, nullptr, nullptr, 0});
             LAUNCH_CHECK();
-            k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+            launch_k(Pdl{}, k_rows_c2r<N>, dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
                 RowsC2RParams{ws.stp, grad_kern, tw, nullptr, 1.0f, nullptr, nullptr, 0});
             LAUNCH_CHECK();
             if (grad_img != nullptr) {
-                k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
+                launch_k(k_rows_r2c<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
                 LAUNCH_CHECK();
                 const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
                 const int cchunks = conv_chunks(N, B);
-                k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+                launch_k(k_cols_conv<N>, dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s, 
                     ColsConvParams{ws.stg, ws.stg, otf, tw, nullptr, B, cchunks, 1, 1.0f});
                 LAUNCH_CHECK();
-                k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+                launch_k(k_rows_c2r<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
                     RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f, nullptr, nullptr, 0});
                 LAUNCH_CHECK();
             }
@@ -1074,22 +1153,22 @@ static int conv_bwd_impl(const float* g, const float* img, const float2* otf, co
     if (rc) return rc;
     const int nchunks = accum_chunks(N, B);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
-    k_cols_accum<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+    launch_k(k_cols_accum<N>, dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s, 
         ColsAccumParams{srow, ws.stg, ws.partial, tw, nullptr, nullptr, nullptr, B, nchunks});
     LAUNCH_CHECK();
-    k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
+    launch_k(Pdl{}, k_cols_reduce_inv<N>, 3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s, 
         ColsReduceInvParams{ws.partial, ws.stp, tw, nchunks, 1.0f / (static_cast<float>(N) * N),
                             nullptr, nullptr, nullptr, nullptr, 0});
     LAUNCH_CHECK();
-    k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+    launch_k(Pdl{}, k_rows_c2r<N>, dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
         RowsC2RParams{ws.stp, grad_kern, tw, nullptr, 1.0f, nullptr, nullptr, 0});
     LAUNCH_CHECK();
     if (grad_img != nullptr) {
         const int cchunks = conv_chunks(N, B);
-        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+        launch_k(k_cols_conv<N>, dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s, 
             ColsConvParams{ws.stg, ws.stg, otf, tw, nullptr, B, cchunks, 1, 1.0f});
         LAUNCH_CHECK();
-        k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        launch_k(k_rows_c2r<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
             RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f, nullptr, nullptr, 0});
         LAUNCH_CHECK();
     }
@@ -1136,31 +1215,31 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
             k_pacc<<<3 * G3 * plane::C, plane::THREADS, plane::ACC_SMEM_BYTES, s>>>(
                 plane::AccParams{g, Xh, otf, ws.pscratch, tw, img_max, ws.partial, ws.dot_lanes, B, G3}, ws.pctr, st->err_dev);
             LAUNCH_CHECK();
-            k_pcoef<<<(B + 63) / 64, 64, 0, s>>>(ws.dot_lanes, img_max, tie_count, ws.coef, B);
+            launch_k(Pdl{}, k_pcoef, (B + 63) / 64, 64, 0, s, ws.dot_lanes, img_max, tie_count, ws.coef, B);
             LAUNCH_CHECK();
-            k_cols_reduce_inv<N><<<3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
+            launch_k(Pdl{}, k_cols_reduce_inv<N>, 3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s, 
                 ColsReduceInvParams{ws.partial, ws.stp, tw, G3, 0.25f / (static_cast<float>(N) * N), nullptr, nullptr, nullptr, nullptr, 0});
             LAUNCH_CHECK();
-            k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+            launch_k(Pdl{}, k_rows_c2r<N>, dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
                 RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
             LAUNCH_CHECK();
             const int per_ch = N * N / 2 / EW_THREADS < 592 ? N * N / 2 / EW_THREADS : 592;
-            k_tie_term<<<dim3(per_ch, 3), EW_THREADS, 0, s>>>(TieTermParams{grad_psf, img, tie_count, tie_pos, ws.coef, B, N});
+            launch_k(Pdl{}, k_tie_term, dim3(per_ch, 3), EW_THREADS, 0, s, TieTermParams{grad_psf, img, tie_count, tie_pos, ws.coef, B, N});
             LAUNCH_CHECK();
             if (grad_img != nullptr) {           // optional output (no reference caller asks for it): generic kernels on g
-                k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
+                launch_k(k_rows_r2c<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
                 LAUNCH_CHECK();
                 const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
                 const int cchunks = conv_chunks(N, B);
-                k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+                launch_k(k_cols_conv<N>, dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s, 
                     ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunks, 1, 1.0f});
                 LAUNCH_CHECK();
-                k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+                launch_k(k_rows_c2r<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
                     RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
                 LAUNCH_CHECK();
                 const long long tot = static_cast<long long>(planes) * N * N;
                 const int grid = static_cast<int>(tot / EW_THREADS < 148 * 8 ? (tot + EW_THREADS - 1) / EW_THREADS : 148 * 8);
-                k_tie_term_img<<<grid, EW_THREADS, 0, s>>>(TieTermImgParams{grad_img, psf, tie_count, tie_pos, ws.coef, B, N});
+                launch_k(k_tie_term_img, grid, EW_THREADS, 0, s, TieTermImgParams{grad_img, psf, tie_count, tie_pos, ws.coef, B, N});
                 LAUNCH_CHECK();
             }
             return 0;
@@ -1168,7 +1247,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     }
     const float2* srow = spectrum;
     if (srow == nullptr) {                       // forward did not keep the row spectra: recompute them
-        k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        launch_k(k_rows_r2c<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
             RowsR2CParams{img, ws.stx, tw, nullptr, nullptr});
         LAUNCH_CHECK();
         srow = ws.stx;
@@ -1181,42 +1260,42 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
         if (per_sm > 0) {
             const int total = tiles * planes;
             const int grid = persistent_grid(rows_fit(N, false), per_sm, total);
-            k_rows_r2c_persist<N><<<grid, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES, s>>>(
+            launch_k(k_rows_r2c_persist<N>, grid, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES, s, 
                 RowsR2CParams{g, ws.stg, tw, nullptr, nullptr}, total);
         } else {
-            k_rows_r2c<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
+            launch_k(k_rows_r2c<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, RowsR2CParams{g, ws.stg, tw, nullptr, nullptr});
         }
     }
     LAUNCH_CHECK();
     const int nchunks = accum_chunks(N, B);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
-    k_cols_accum<N><<<dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s>>>(
+    launch_k(k_cols_accum<N>, dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s, 
         ColsAccumParams{srow, ws.stg, ws.partial, tw, img_max, otf, ws.dot_lanes, B, nchunks,
                         grad_img == nullptr ? [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }() : 0});
     LAUNCH_CHECK();
-    k_cols_reduce_inv<N><<<3 * T::NC + B, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s>>>(
+    launch_k(Pdl{}, k_cols_reduce_inv<N>, 3 * T::NC + B, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s, 
         ColsReduceInvParams{ws.partial, ws.stp, tw, nchunks, 1.0f / (static_cast<float>(N) * N),
                             ws.dot_lanes, img_max, tie_count, ws.coef, B});
     LAUNCH_CHECK();
-    k_rows_c2r<N><<<dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+    launch_k(Pdl{}, k_rows_c2r<N>, dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
         RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
     LAUNCH_CHECK();
     {   // arg-max term of the amax backward (spatial form), ties of channel c handled by the CTAs of row c
         const int per_ch = N * N / 2 / EW_THREADS < 592 ? N * N / 2 / EW_THREADS : 592;   // two adjacent pixels per thread
-        k_tie_term<<<dim3(per_ch, 3), EW_THREADS, 0, s>>>(TieTermParams{grad_psf, img, tie_count, tie_pos, ws.coef, B, N});
+        launch_k(Pdl{}, k_tie_term, dim3(per_ch, 3), EW_THREADS, 0, s, TieTermParams{grad_psf, img, tie_count, tie_pos, ws.coef, B, N});
         LAUNCH_CHECK();
     }
     if (grad_img != nullptr) {
         const int cchunks = conv_chunks(N, B);
-        k_cols_conv<N><<<dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s>>>(
+        launch_k(k_cols_conv<N>, dim3(colgroups, cchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s, 
             ColsConvParams{ws.stg, ws.stg, otf, tw, img_max, B, cchunks, 1, 1.0f});
         LAUNCH_CHECK();
-        k_rows_c2r<N><<<rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s>>>(
+        launch_k(k_rows_c2r<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
             RowsC2RParams{ws.stg, grad_img, tw, nullptr, 1.0f});
         LAUNCH_CHECK();
         const long long tot = static_cast<long long>(planes) * N * N;
         const int grid = static_cast<int>(tot / EW_THREADS < 148 * 8 ? (tot + EW_THREADS - 1) / EW_THREADS : 148 * 8);
-        k_tie_term_img<<<grid, EW_THREADS, 0, s>>>(TieTermImgParams{grad_img, psf, tie_count, tie_pos, ws.coef, B, N});
+        launch_k(k_tie_term_img, grid, EW_THREADS, 0, s, TieTermImgParams{grad_img, psf, tie_count, tie_pos, ws.coef, B, N});
         LAUNCH_CHECK();
     }
     return 0;
@@ -1280,6 +1359,11 @@ int b200cam_init(int N) {
     const int l = log2i(N);
     if (g_state[dev].tw[l] != nullptr) return 0;
     if (g_state[dev].chain_ev == nullptr) CK(cudaEventCreateWithFlags(&g_state[dev].chain_ev, cudaEventDisableTiming));
+    {
+        const char* e = getenv("B200CAM_PDL_TRIGGER");
+        const int trig = e ? atoi(e) : 0;
+        CK(cudaMemcpyToSymbol(c_pdl_trigger, &trig, sizeof(int)));
+    }
     if (g_state[dev].err_host == nullptr) {
         unsigned* h = nullptr;
         unsigned* d = nullptr;
@@ -1389,7 +1473,7 @@ int b200cam_crop_abs_resize_fwd(const float* conv, float* out, int planes, int n
     if (planes < 1 || n < 2 || P < 2 || off < 0 || off + P - 1 > n) return B200CAM_E_BAD_SIZE;
     if (!conv || !out) return B200CAM_E_NULL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    k_crop_abs_resize_fwd<<<ew_blocks(static_cast<long long>(planes) * P * P), EW_THREADS, 0, s>>>(
+    launch_k(k_crop_abs_resize_fwd, ew_blocks(static_cast<long long>(planes) * P * P), EW_THREADS, 0, s, 
         CropAbsResizeParams{conv, out, planes, n, P, off});
     LAUNCH_CHECK();
     return 0;
@@ -1400,7 +1484,7 @@ int b200cam_crop_abs_resize_bwd(const float* grad_out, const float* conv, float*
     if (planes < 1 || n < 2 || P < 2 || off < 0 || off + P - 1 > n) return B200CAM_E_BAD_SIZE;
     if (!grad_out || !conv || !grad_conv) return B200CAM_E_NULL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    k_crop_abs_resize_bwd<<<ew_blocks(static_cast<long long>(planes) * n * n), EW_THREADS, 0, s>>>(
+    launch_k(k_crop_abs_resize_bwd, ew_blocks(static_cast<long long>(planes) * n * n), EW_THREADS, 0, s, 
         CropAbsResizeBwdParams{grad_out, conv, grad_conv, planes, n, P, off});
     LAUNCH_CHECK();
     return 0;
@@ -1435,7 +1519,7 @@ int b200cam_zernike_fwd(const float* coef, const float* Z, float* h, void* works
     Carver c(workspace);
     int* arrive = c.take<int>(xblocks);                       // zero on entry (caller zero-fills the workspace once), left zero
     float4* partial = c.take<float4>(static_cast<size_t>(ks) * NN4);
-    k_zernike_fwd<<<dim3(xblocks, ks), EW_THREADS, 0, s>>>(
+    launch_k(k_zernike_fwd, dim3(xblocks, ks), EW_THREADS, 0, s, 
         ZernikeFwdParams{coef, reinterpret_cast<const float4*>(Z), partial, reinterpret_cast<float4*>(h), arrive, T, NN4, ks});
     LAUNCH_CHECK();
     return 0;
@@ -1446,7 +1530,7 @@ int b200cam_zernike_bwd(const float* grad_h, const float* Z, float* grad_coef, i
     if (!grad_h || !Z || !grad_coef) return B200CAM_E_NULL;
     if (!aligned16(Z) || !aligned16(grad_h)) return B200CAM_E_ALIGN;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    k_zernike_bwd<<<T, EW_THREADS, 0, s>>>(ZernikeBwdParams{reinterpret_cast<const float4*>(grad_h),
+    launch_k(k_zernike_bwd, T, EW_THREADS, 0, s, ZernikeBwdParams{reinterpret_cast<const float4*>(grad_h),
                                                             reinterpret_cast<const float4*>(Z), grad_coef,
                                                             static_cast<int>(NN / 4)});
     LAUNCH_CHECK();
