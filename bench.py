@@ -51,33 +51,62 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="timed loop only (for ncu): no breakdown / e2e / cpu legs")
-    return ap.parse_args()
+    ap.add_argument("--config", default="2", choices=["1", "2", "3cam", "5"],
+                    help="BASELINE.json config: 1 = forward only, batch 8 (CPU-reference shape); 2 = fwd+bwd batch 64 (headline, "
+                         "default); 3cam = the Image_Caption camera of config 3 (896/256/T=350, batch 128) without the caption "
+                         "nets; 5 = hi-res sweep (use --size 512|1024; the batch defaults to what fits the bench comfortably)")
+    args = ap.parse_args()
+    if args.config == "1":
+        args.batch = 8 if args.batch == 64 else args.batch
+    if args.config == "5":
+        if args.size == 256:
+            args.size = 512
+        if args.batch == 64:
+            args.batch = 32 if args.size == 512 else 8
+    if args.config == "3cam" and args.batch == 64:
+        args.batch = 128
+    return args
 
 
 # --------------------------------------------------------------------------------------------
 # CPU arm: oracle port on the host cores
 # --------------------------------------------------------------------------------------------
-def cpu_port_rate(N: int, B: int, budget_s: float, steps: int | None = None, warmup: int = 1):
-    """images/s of the oracle (fwd+bwd into h) with all host threads; bounded by budget_s."""
+def cpu_port_rate(N: int, B: int, budget_s: float, steps: int | None = None, warmup: int = 1, forward_only: bool = False,
+                  device: str = "cpu"):
+    """images/s of the oracle (fwd+bwd into h, or forward only) with all host threads; bounded by budget_s.
+    device="cuda": the same restatement on stock torch / cuFFT kernels of the GPU (the on-GPU comparison bar)."""
     from oracle import camera_oracle as co
     import b200cam.synthetic as synth
     torch.set_num_threads(os.cpu_count() or 1)
     C = co.build_constants(N)
     img, w = synth.images(B, N), synth.upstream_grad(B, N)
-    h = synth.height_map(N).requires_grad_(True)
+    h = synth.height_map(N)
+    if device != "cpu":
+        import dataclasses
+        C = dataclasses.replace(C, **{f.name: getattr(C, f.name).to(device) for f in dataclasses.fields(C)
+                                      if torch.is_tensor(getattr(C, f.name))})
+        img, w, h = img.to(device), w.to(device), h.to(device)
+    h.requires_grad_(not forward_only)
+    sync = torch.cuda.synchronize if device != "cpu" else (lambda: None)
 
     def step():
+        if forward_only:
+            with torch.no_grad():
+                co.camera_forward(img, h, C)
+            return
         h.grad = None
         out = co.camera_forward(img, h, C)
         ((out["sensor"] * w).sum() + out["loss_rad"] + out["centering_loss"]).backward()
 
     for _ in range(max(1, warmup)):
         step()
+    sync()
     times = []
     t_end = time.perf_counter() + budget_s
     while (steps is None and time.perf_counter() < t_end and len(times) < 50) or (steps is not None and len(times) < steps):
         t0 = time.perf_counter()
         step()
+        sync()
         times.append(time.perf_counter() - t0)
         if steps is not None and time.perf_counter() > t_end + 120:
             break
@@ -88,7 +117,9 @@ def cpu_port_rate(N: int, B: int, budget_s: float, steps: int | None = None, war
 
 def workload_config(args, world: int, launch: str) -> dict:
     N, B, R = args.size, args.batch, max(1, args.input_sets)
-    return {"workload": f"Face-DeId Camera fwd+bwd into height map, batch {B}/GPU of {N}x{N} RGB, random height map",
+    what = "forward only" if args.config == "1" else "fwd+bwd into height map"
+    return {"workload": f"Face-DeId Camera {what}, batch {B}/GPU of {N}x{N} RGB, random height map",
+            "baseline_config": args.config,
             "global_batch": B * world, "size": N, "parallelism": f"dp{world}" if world > 1 else "single",
             "l2": (f"{R} distinct resident input sets rotated: {R * 2 * B * 3 * N * N * 4 / 1e6:.0f} MB of inputs "
                    + ("(larger than the 126 MB L2)" if R * 2 * B * 3 * N * N * 4 > 126e6 else "(SMALLER than L2 - not a valid bench size)")),
@@ -101,10 +132,11 @@ def run_reference(args) -> None:
         return
     N, B = args.size, args.batch
     steps = min(args.steps, 20)
-    rate, med, n, cores = cpu_port_rate(N, B, budget_s=120.0, steps=steps, warmup=min(args.warmup, 2))
+    warm = max(1, min(args.warmup, 10))            # the warm-up the caller asked for (a CPU step is ~70 ms: cheap)
+    rate, med, n, cores = cpu_port_rate(N, B, budget_s=120.0, steps=steps, warmup=warm, forward_only=args.config == "1")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": min(args.warmup, 2), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, max(1, args.gpus), f"torch {torch.__version__} CPU, {cores} threads, rank 0 only"),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
@@ -217,10 +249,17 @@ def run_b200(args) -> None:
     ws = [synth.upstream_grad(B, N, seed=2000 + 17 * rank + r).to(dev) for r in range(R)]
 
     one = torch.ones((), device=dev)
+    fwd_only = args.config == "1"
+    last_y = [None]
 
     def step(i: int):
         """forward + backward into h; upstream gradients: w for the sensor image, 1 for the two regularisers
-        (i.e. L = sum(sensor*w) + loss_rad + centering_loss without materialising the product)."""
+        (i.e. L = sum(sensor*w) + loss_rad + centering_loss without materialising the product).
+        Config 1: the forward alone (no autograd graph)."""
+        if fwd_only:
+            with torch.no_grad():
+                last_y[0] = cam(imgs[i % R])
+            return
         h.grad = None
         y = cam(imgs[i % R])
         torch.autograd.backward([y, cam.loss_rad, cam.centering_loss], [ws[i % R], one, one])
@@ -385,13 +424,39 @@ def run_b200(args) -> None:
         time_call("psf_fwd", lambda i: F.PsfSynth.apply(hd, plan))
         psf = F.PsfSynth.apply(hd, plan)[0]
         time_call("sensor_fwd", lambda i: F.SensorConv.apply(imgs[i % R], psf, plan))
-    p_req = psf.clone().requires_grad_(True)
-    ys = [F.sensor_conv(imgs[r], p_req, plan) for r in range(R)]
-    time_call("sensor_bwd", lambda i: torch.autograd.grad(ys[i % R], p_req, ws[i % R], retain_graph=True))
-    hr = h.detach().clone().requires_grad_(True)
-    pp, _l1, _l2 = F.psf_synth(hr, plan)
-    gp = torch.rand_like(pp)
-    time_call("psf_bwd", lambda i: torch.autograd.grad(pp, hr, gp, retain_graph=True))
+    if not fwd_only:
+        p_req = psf.clone().requires_grad_(True)
+        ys = [F.sensor_conv(imgs[r], p_req, plan) for r in range(R)]
+        time_call("sensor_bwd", lambda i: torch.autograd.grad(ys[i % R], p_req, ws[i % R], retain_graph=True))
+        hr = h.detach().clone().requires_grad_(True)
+        pp, _l1, _l2 = F.psf_synth(hr, plan)
+        gp = torch.rand_like(pp)
+        time_call("psf_bwd", lambda i: torch.autograd.grad(pp, hr, gp, retain_graph=True))
+        del ys, p_req, pp
+
+    # ---- data parallel: is the fused peer-memory all-reduce right?  (outside every timed region)  dL/dh of one step through
+    #      b200cam_psf_bwd_allreduce (the path timed above) against the same step with dist.all_reduce, and bitwise equality
+    #      of the result across ranks.
+    allreduce_check = None
+    if world > 1 and not fwd_only:
+        def grad_once(camera):
+            h.grad = None
+            y = camera(imgs[0])
+            torch.autograd.backward([y, camera.loss_rad, camera.centering_loss], [ws[0], one, one])
+            torch.cuda.synchronize()
+            return h.grad.detach().clone()
+        g_peer = grad_once(cam)
+        fused_path = cam._plan(dev).peer_comm is not None
+        cam_ref = Camera(device=dev, N=N, zernike_terms=12)
+        cam_ref.get_Heith_Map = lambda: h
+        cam_ref.data_parallel(average=True, peer_memory=False)
+        g_nccl = grad_once(cam_ref)
+        gathered = [torch.empty_like(g_peer) for _ in range(world)]
+        dist.all_gather(gathered, g_peer)
+        allreduce_check = {"rel": float((g_peer - g_nccl).norm() / g_nccl.norm()),
+                           "ranks_bitwise_equal": bool(all(torch.equal(t, gathered[0]) for t in gathered)),
+                           "fused_peer_path": bool(fused_path), "finite": bool(torch.isfinite(g_peer).all())}
+        cam.check_device_errors()
 
     # ---- end to end through the module API with host image buffers ------------------------------------
     copy_stream = torch.cuda.Stream()
@@ -414,6 +479,12 @@ def run_b200(args) -> None:
             if i >= 1:                                    # compute batch i-1
                 s = (i - 1) % 2
                 cur.wait_event(ready[s])
+                if fwd_only:                              # config 1: the sensor images themselves are the result
+                    with torch.no_grad():
+                        y = cam(dev_bufs[s])
+                    freed[s].record(cur)
+                    y_host.copy_(y, non_blocking=True)
+                    continue
                 h.grad = None
                 y = cam(dev_bufs[s])
                 torch.autograd.backward([y, cam.loss_rad, cam.centering_loss], [ws[(i - 1) % R], one, one])
@@ -421,6 +492,7 @@ def run_b200(args) -> None:
                 gh_host.copy_(h.grad, non_blocking=True)
                 loss_host.copy_((cam.loss_rad + cam.centering_loss).detach().reshape(1), non_blocking=True)
 
+    y_host = torch.empty(B, 3, N, N).pin_memory() if fwd_only else None
     for s in range(2):
         freed[s].record(torch.cuda.current_stream())
     e2e_loop(3)
@@ -452,6 +524,12 @@ def run_b200(args) -> None:
             if i >= 1:
                 s = (i - 1) % 2
                 cur.wait_event(ready[s])
+                if fwd_only:
+                    with torch.no_grad():
+                        y = cam(dev_u8[s])
+                    freed[s].record(cur)
+                    y_host.copy_(y, non_blocking=True)
+                    continue
                 h.grad = None
                 y = cam(dev_u8[s])
                 torch.autograd.backward([y, cam.loss_rad, cam.centering_loss], [ws[(i - 1) % R], one, one])
@@ -490,49 +568,179 @@ def run_b200(args) -> None:
         return
 
     peak, peak_src = hbm_peak()
-    bytes_per_image = 48 * N * N
+    bytes_per_image = (24 if fwd_only else 48) * N * N
     achieved = B * bytes_per_image / (ms_per_step * 1e-3) / 1e9          # per GPU
-    traffic = None
+    # DRAM traffic of one step: NOT measured by this run (it needs ncu) - the committed ncu capture of the same command
+    # is quoted as `traffic_static` with its source; `traffic` stays null unless a live counter is available
+    traffic_static = None
     tpath = REPO / "profiles" / "traffic.json"
-    if tpath.exists():
+    if tpath.exists() and not fwd_only:
         try:
-            traffic = json.loads(tpath.read_text()).get(f"N{N}_B{B}")
+            tj = json.loads(tpath.read_text())
+            if f"N{N}_B{B}" in tj:
+                traffic_static = {"bytes_per_step": tj[f"N{N}_B{B}"], "source": tj.get("source", "profiles/traffic.json")}
         except Exception:
-            traffic = None
+            traffic_static = None
     cpu = None
+    torch_cuda = None
     if world == 1:
-        rate, med, n, cores = cpu_port_rate(N, B, args.cpu_seconds)
+        what = "forward" if fwd_only else "fwd+bwd"
+        rate, med, n, cores = cpu_port_rate(N, B, args.cpu_seconds, forward_only=fwd_only)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} fwd+bwd steps of batch {B} at N={N} (median), oracle/camera_oracle.py on torch CPU"}
+               "sample": f"{n} {what} steps of batch {B} at N={N} (median), oracle/camera_oracle.py on torch CPU"}
+        # the on-GPU bar: the same restatement of the reference module on stock torch + cuFFT, this GPU
+        try:
+            trate, tmed, tn, _ = cpu_port_rate(N, B, 3.0, warmup=3, forward_only=fwd_only, device=str(dev))
+            torch_cuda = {"value": trate, "unit": UNIT, "ms_per_step": tmed * 1e3, "steps": tn,
+                          "kind": "oracle restatement of the reference Camera on stock torch/cuFFT kernels, eager, same GPU",
+                          "speedup_of_this_repo": value / trate}
+        except Exception as exc:
+            torch_cuda = {"error": str(exc)[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world, "cuda-graph replay" if graphs is not None else "eager"),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * N * N * 4, "d2h_bytes_per_step": N * N * 4 + 4,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * N * N * 4,
+                "d2h_bytes_per_step": B * 3 * N * N * 4 if fwd_only else N * N * 4 + 4,
                 "steps": e2e_steps, "note": "nn.Module API, pinned host images, double-buffered H2D, loss + dL/dh read back"},
-        "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * N * N, "d2h_bytes_per_step": N * N * 4 + 4,
+        "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * N * N,
+                   "d2h_bytes_per_step": B * 3 * N * N * 4 if fwd_only else N * N * 4 + 4,
                    "steps": e2e_steps, "note": "same loop, uint8 host images (decoder output), /255 on the GPU: extra information, "
                                                "the fp32 `e2e` above is the contract's number"},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "scope": "whole step: every kernel of fwd+bwd (algorithmic bytes 48*N^2 per image, SURVEY 8d)",
+                     "traffic": None, "traffic_static": traffic_static, "peak_source": peak_src,
+                     "scope": ("whole step: every kernel of the forward (algorithmic bytes 24*N^2 per image)" if fwd_only else
+                               "whole step: every kernel of fwd+bwd (algorithmic bytes 48*N^2 per image, SURVEY 8d)"),
                      "breakdown_us": {k: round(v, 2) for k, v in breakdown.items()},
                      "kernels_cupti": kernel_table},
         "clocks": clocks,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if torch_cuda is not None:
+        line["torch_cuda_baseline"] = torch_cuda
+    if allreduce_check is not None:
+        line["allreduce_check"] = allreduce_check
     print(json.dumps(line), flush=True)
     finish()
+
+
+# --------------------------------------------------------------------------------------------
+# config "3cam": the Image_Caption camera of BASELINE config 3 (OpticsZernike, shipped geometry of
+# Image_Caption/train.py:64-66: wave 896, patch 256, T = 350, batch 128) - forward + backward into the trainable Zernike
+# coefficient, WITHOUT the caption nets (ResNet-101 / LSTM are cuDNN / cuBLAS work outside the hot path).
+# --------------------------------------------------------------------------------------------
+def run_caption_camera(args) -> None:
+    from b200cam.lens import OpticsZernike
+    from b200cam import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, P = args.batch, 256
+    lib = _lib.load_library()
+    cam = OpticsZernike(input_shape=[None, P, P, 3], device=dev, zernike_terms=350, patch_size=P, height_tolerance=2e-8,
+                        sensor_distance=0.025, wave_resolution=[896, 896], sample_interval=3e-06, upsample=False).to(dev)
+    R = max(1, args.input_sets)
+    g = torch.Generator().manual_seed(5)
+    imgs_host = [torch.rand(B, 3, P, P, generator=g).pin_memory() for _ in range(R)]
+    imgs = [t.to(dev) for t in imgs_host]
+    ws = [torch.rand(B, 3, P, P, generator=g).to(dev) for _ in range(R)]
+
+    def step(i):
+        cam.zero_grad(set_to_none=True)
+        sensor, psf, coeffs, loss = cam(imgs[i % R])
+        torch.autograd.backward([sensor], [ws[i % R]])
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    c0 = lib.b200cam_launch_count()
+    step(0)
+    torch.cuda.synchronize()
+    launches = int(lib.b200cam_launch_count() - c0)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    t_spin = time.perf_counter()
+    i = 0
+    while time.perf_counter() - t_spin < 1.2:
+        step(i); i += 1
+    for i in range(max(3, args.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+    steps = min(args.steps, 200)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    clocks = sampler.stop()
+    # end to end: pinned host images in, sensor checksum + coefficient gradient out
+    out_host = torch.empty(2).pin_memory()
+    dbuf = torch.empty_like(imgs[0])
+    e2e_steps = max(5, min(steps, 30))
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(e2e_steps):
+        dbuf.copy_(imgs_host[i % R], non_blocking=True)
+        cam.zero_grad(set_to_none=True)
+        sensor, psf, coeffs, loss = cam(dbuf)
+        torch.autograd.backward([sensor], [ws[i % R]])
+        out_host.copy_(torch.stack([sensor.detach().sum(), cam.zernike_coeffs_train.grad.reshape(-1)[0]]), non_blocking=True)
+    t1.record()
+    torch.cuda.synchronize()
+    e2e = B * e2e_steps / (t0.elapsed_time(t1) * 1e-3)
+    peak, peak_src = hbm_peak()
+    achieved = B * 48 * P * P / (ms * 1e-3) / 1e9
+    # CPU baseline: the oracle restatement of the reference module, bounded sample (one step of batch 4 is ~1.5 s)
+    from oracle import lens_oracle as lo
+    import b200cam.zernike as zern
+    import numpy as np
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = lo.LensConfig()
+    vol = cam.zernike_volume.detach().cpu() if hasattr(cam, "zernike_volume") else torch.tensor(
+        zern.zernike_volume(896, 350, 1e-6).astype(np.float32))
+    coeffs = torch.zeros(350, 1, 1); coeffs[3] = -22.0
+    bs = 4
+    img_c, w_c = imgs_host[0][:bs].clone(), ws[0][:bs].cpu()
+    times = []
+    for k in range(3):
+        cz = coeffs.clone().requires_grad_(True)
+        tt = time.perf_counter()
+        out = lo.lens_forward(img_c, cz, vol, cfg)
+        (out["sensor"] * w_c).sum().backward()
+        times.append(time.perf_counter() - tt)
+    cpu_rate = bs / sorted(times)[1]
+    line = {"metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"Image_Caption camera (OpticsZernike 896/256/T=350) fwd+bwd into the trainable coefficient, batch {B} "
+                                   "of 256x256 RGB; caption nets not included", "baseline_config": "3cam", "global_batch": B,
+                       "l2": f"{R} input sets rotated: {R * 2 * B * 3 * P * P * 4 / 1e6:.0f} MB", "launch": "eager"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 3 * P * P * 4, "d2h_bytes_per_step": 8, "steps": e2e_steps},
+            "gpu_launches": launches * steps, "launches_per_step": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src,
+                         "scope": "whole step incl. the PSF synthesis (torch ops) - the path is FP32-compute bound, SURVEY 8a"},
+            "clocks": clocks,
+            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"3 fwd+bwd steps of batch {bs} (median), oracle/lens_oracle.py on torch CPU"}}
+    print(json.dumps(line), flush=True)
 
 
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "3cam":
+        run_caption_camera(args)
     else:
         run_b200(args)
 

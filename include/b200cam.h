@@ -55,6 +55,8 @@ unsigned long long b200cam_launch_count(void);
 int b200cam_init(int N);
 
 size_t b200cam_otf_bytes(int N);                                   /* 3*(N/2+1)*N complex */
+/* The PSF workspace must be ZERO-FILLED once before its first use (it holds the grid-barrier words of the cooperative PSF
+ * kernels, which the library leaves at zero); use one workspace per stream - calls that share one must not overlap. */
 size_t b200cam_psf_workspace_bytes(int N);
 size_t b200cam_sensor_workspace_bytes(int N, int B, int want_img_grad);
 /* size of the optional saved forward spectrum (row-transformed rfft of every image plane) */
@@ -125,7 +127,9 @@ int b200cam_psf_bwd(const float* grad_psf, const float* grad_rad, const float* g
  *   peer_bufs  HOST array [world] of device pointers: rank r's symmetric buffer of b200cam_comm_bytes(N, world) bytes as
  *              mapped in THIS process (e.g. torch.distributed._symmetric_memory buffer_ptrs); zero-filled once before
  *              the first call, then owned by the library (per-tile epochs and the double-buffered slots live in it).
- * All ranks must call it the same number of times (it is a collective). */
+ * All ranks must call it the same number of times (it is a collective).  A rank whose peers do not arrive within
+ * B200CAM_COMM_TIMEOUT_S seconds (environment, default 30) does NOT return a partial sum: its dL/dh is filled with NaN and
+ * the device error word is set to B200CAM_DEVERR_ALLREDUCE_WAIT (b200cam_device_error). */
 size_t b200cam_comm_bytes(int N, int world);
 int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_rad, const float* grad_cen, const float* h, const float* A,
                               const float* Ht, const float* rho, const float* kappa, const float* psf, const float* field,

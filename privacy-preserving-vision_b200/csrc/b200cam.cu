@@ -142,11 +142,12 @@ struct CommDev {
     unsigned char* buf[COMM_MAX_WORLD];     // every rank's buffer, as mapped in this process
     int rank, world;
     float scale;
+    long long timeout_clk;                  // give-up deadline of the receive loop in SM clocks (B200CAM_COMM_TIMEOUT_S, default 30 s)
 };
 
 template <int N>
 __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad_allreduce(CRowsInvParams p, PupilLoad pupil,
-                                                                                     float* gh, CommDev c) {
+                                                                                     float* gh, CommDev c, unsigned* err) {
     pdl_gate();
     DeviceExec ex;
     crows_inv_hgrad_body<N>(ex, p, pupil, gh, SMEM2);            // local dL/dh rows of this tile -> gh (ends with a barrier)
@@ -177,7 +178,11 @@ __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad_allre
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
-    const long long t0 = clock64();                             // never hang the device if a peer died (~1 s)
+    // A peer that never arrives (died, or the ranks called the collective a different number of times) must not hang the
+    // device for ever, and must not yield a result either: after `c.timeout_clk` cycles the tile gives up, raises the
+    // device error word (b200cam_device_error -> RuntimeError in the wrapper) and fills its rows of dL/dh with NaN.
+    const long long t0 = clock64();
+    bool gave_up = false;
     for (int r0 = 0; r0 < c.world; r0 += 4) {
         uint2 w[K][4];
         bool ok;
@@ -199,16 +204,21 @@ __global__ void __launch_bounds__(HGradSmem<N>::THREADS) k_crows_inv_hgrad_allre
             for (int k = 0; k < K; ++k)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) ok = ok && (w[k][q].y == epoch);
-        } while (!ok && clock64() - t0 < 2000000000LL);
+            if (!ok && clock64() - t0 > c.timeout_clk) {
+                gave_up = true;
+                break;
+            }
+        } while (!ok);
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[k] += __uint_as_float(w[k][q].x);      // rank order; absent ranks add +0
     }
+    if (gave_up && err != nullptr) atomicExch(err, B200CAM_DEVERR_ALLREDUCE_WAIT);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int i = tid + k * THREADS;
-        if (i < COUNT) gh[base + i] = acc[k] * c.scale;
+        if (i < COUNT) gh[base + i] = gave_up ? __int_as_float(0x7fc00000) : acc[k] * c.scale;
     }
 }
 
@@ -375,6 +385,7 @@ __global__ void __launch_bounds__(64) k_pcoef(const float* dotp, const float* im
 // ~1.2 us on 192 CTAs (one L2 atomic + one polled line), against ~5 us for cooperative_groups' grid.sync().
 struct GridBarrier {
     unsigned* ctr;      // [2]: arrivals, departures; both zero between launches
+    unsigned* err = nullptr;
     unsigned k = 0;
     __device__ __forceinline__ void sync() {
         __syncthreads();
@@ -383,8 +394,13 @@ struct GridBarrier {
             __threadfence();
             atomicAdd(ctr, 1u);
             const unsigned target = k * gridDim.x;
-            const long long t0 = clock64();          // never hang the device: give up after ~1 s (results are then garbage)
-            while (*reinterpret_cast<volatile unsigned*>(ctr) < target && clock64() - t0 < 2000000000LL) {}
+            const long long t0 = clock64();          // never hang the device: give up after ~2 s and say so (device error word)
+            while (*reinterpret_cast<volatile unsigned*>(ctr) < target) {
+                if (clock64() - t0 > 4000000000LL) {
+                    if (err != nullptr) atomicExch(err, B200CAM_DEVERR_GRID_BARRIER);
+                    break;
+                }
+            }
             __threadfence();
         }
         __syncthreads();
@@ -410,12 +426,13 @@ struct PsfFwdArgs {
     CRowsInvParams rows_inv; IntensityEpilogue inten;
     PsfFinaliseParams fin;
     unsigned* barrier;
+    unsigned* err;
 };
 
 template <int N>
 __global__ void __launch_bounds__(COOP_THREADS) k_psf_fwd_coop(PsfFwdArgs a) {
     pdl_gate();
-    GridBarrier grid{a.barrier};
+    GridBarrier grid{a.barrier, a.err};
     __shared__ float red[3 * EW_THREADS + 2];
     using T = Tile<N>;
     const int G = gridDim.x;
@@ -447,12 +464,13 @@ struct PsfBwdArgs {
     CColsMixParams mix;
     CRowsInvParams rows_inv; PupilLoad pupil; float* gh;
     unsigned* barrier;
+    unsigned* err;
 };
 
 template <int N>
 __global__ void __launch_bounds__(COOP_THREADS) k_psf_bwd_coop(PsfBwdArgs a) {
     pdl_gate();
-    GridBarrier grid{a.barrier};
+    GridBarrier grid{a.barrier, a.err};
     __shared__ float red[3 * EW_THREADS + 2];
     using T = Tile<N>;
     const int G = gridDim.x;
@@ -569,11 +587,6 @@ static int coop_grid(int N, cudaStream_t s) {
         if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return 0;
     }
     return g_state[dev].coop_grid[log2i(N)];
-}
-static unsigned* coop_barrier(int which) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
-    return g_state[dev].bar + 2 * which;
 }
 static const float2* twiddle(int N) {
     int dev = 0;
@@ -746,7 +759,7 @@ static int accum_chunks(int N, int B) {
 }
 
 struct PsfWs {
-    float2* st; float* I; float* gtot; float* part_rows; float* part_ew; int* arrive;
+    float2* st; float* I; float* gtot; float* part_rows; float* part_ew; int* arrive; unsigned* bar;
     size_t bytes;
     PsfWs(void* p, int N) {
         Carver c(p);
@@ -757,6 +770,7 @@ struct PsfWs {
         part_rows = c.take<float>(3 * N);
         part_ew = c.take<float>(3 * 1024);          // element-wise partials: grid <= 1024 CTAs
         arrive = c.take<int>(1);
+        bar = c.take<unsigned>(4);                   // grid-barrier words of the cooperative kernels: forward [0,1], backward [2,3]
         bytes = c.off;
     }
 };
@@ -896,7 +910,7 @@ static int psf_fwd_impl(const float* h, const float2* A, const float2* Ht, const
         PupilLoad load{A, h, {kappa[0], kappa[1], kappa[2]}, N};
         PsfFwdArgs args{CRowsFwdParams{ws.st, tw}, load, CColsMixParams{ws.st, Ht, tw, 0, 1.0f / (3.0f * N * N)},
                         CRowsInvParams{ws.st, tw}, IntensityEpilogue{field, ws.I, ws.part_rows, ws.arrive, N},
-                        PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, 3 * (N / Tile<N>::CROWS), N}, coop_barrier(0)};
+                        PsfFinaliseParams{ws.I, rho, stats, psf, ws.part_ew, ws.part_rows, ws.arrive, 3 * (N / Tile<N>::CROWS), N}, ws.bar, cur_state() != nullptr ? cur_state()->err_dev : nullptr};
         void* kargs[] = {&args};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_psf_fwd_coop<N>), dim3(G), dim3(COOP_THREADS), kargs,
                                        coop_smem_bytes<N>(), s));
@@ -923,7 +937,7 @@ static int psf_bwd_impl(const float* gpsf, const float* g_rad, const float* g_ce
     if (const int G = (comm != nullptr ? 0 : coop_grid(N, s))) {
         PsfBwdArgs args{PsfGradPrepParams{gpsf, g_rad, g_cen, psf, rho, stats, ws.gtot, ws.part_ew, N}, rf,
                         GradFieldLoad{field, ws.gtot, stats, ws.part_ew, nullptr, G, N}, mix, ri, pupil, grad_h,
-                        coop_barrier(1)};
+                        ws.bar + 2, cur_state() != nullptr ? cur_state()->err_dev : nullptr};
         void* kargs[] = {&args};
         CK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_psf_bwd_coop<N>), dim3(G), dim3(COOP_THREADS), kargs,
                                        coop_smem_bytes<N>(), s));
@@ -938,7 +952,8 @@ static int psf_bwd_impl(const float* gpsf, const float* g_rad, const float* g_ce
     launch_k(Pdl{}, k_ccols_mix<N>, (N + CColsSmem<N>::CC - 1) / CColsSmem<N>::CC, CColsSmem<N>::THREADS, CColsSmem<N>::BYTES, s, mix);
     LAUNCH_CHECK();
     if (comm != nullptr)
-        launch_k(Pdl{}, k_crows_inv_hgrad_allreduce<N>, N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s, ri, pupil, grad_h, *comm);
+        launch_k(Pdl{}, k_crows_inv_hgrad_allreduce<N>, N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s, ri, pupil, grad_h, *comm,
+                 cur_state() != nullptr ? cur_state()->err_dev : nullptr);
     else
         launch_k(Pdl{}, k_crows_inv_hgrad<N>, N / T::CROWS, HGradSmem<N>::THREADS, HGradSmem<N>::BYTES, s, ri, pupil, grad_h);
     LAUNCH_CHECK();
@@ -1608,6 +1623,8 @@ int b200cam_psf_bwd_allreduce(const float* grad_psf, const float* grad_rad, cons
     }
     for (int r = world; r < COMM_MAX_WORLD; ++r) comm.buf[r] = nullptr;
     comm.rank = rank; comm.world = world; comm.scale = scale;
+    static const double timeout_s = [] { const char* e = getenv("B200CAM_COMM_TIMEOUT_S"); const double v = e ? atof(e) : 30.0; return v > 0 ? v : 30.0; }();
+    comm.timeout_clk = static_cast<long long>(timeout_s * 2.0e9);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DISPATCH_N(N, (psf_bwd_impl<NN_>(grad_psf, grad_rad, grad_cen, h, reinterpret_cast<const float2*>(A),
                                      reinterpret_cast<const float2*>(Ht), rho, kappa, psf,

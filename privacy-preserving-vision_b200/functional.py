@@ -41,7 +41,8 @@ class DevicePlan:
             self.rho = t.rho.to(torch.float32).contiguous().to(device)
             self.kappa = (ctypes.c_float * 3)(*t.kappa)
             self.kappa_list = list(t.kappa)
-            self._psf_ws = torch.empty(self.lib.b200cam_psf_workspace_bytes(N), dtype=torch.uint8, device=device)
+            # zero-filled ONCE: the grid-barrier words of the cooperative PSF kernels live in it (the library leaves them zero)
+            self._psf_ws = torch.zeros(self.lib.b200cam_psf_workspace_bytes(N), dtype=torch.uint8, device=device)
         self._sensor_ws: dict[int, torch.Tensor] = {}
         self._zernike_ws: dict[tuple[int, int], torch.Tensor] = {}
         self.otf_floats = self.lib.b200cam_otf_bytes(N) // 4

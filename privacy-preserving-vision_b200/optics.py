@@ -110,6 +110,17 @@ class Camera(nn.Module):
             plan.peer_comm = self._peer_comm if plan.device == getattr(self._peer_comm, "buf", torch.empty(0)).device else None
         return self
 
+    def check_device_errors(self, synchronize: bool = True) -> None:
+        """Raise if a kernel of this camera gave up waiting for other CTAs / ranks (a peer all-reduce whose peers never
+        arrived, an image-max exchange or grid barrier that timed out).  Such a step's outputs are invalid (dL/dh is NaN
+        after an all-reduce time-out).  Called automatically at the start of every PSF synthesis; call it yourself
+        after the last step of a run."""
+        from . import _lib
+        for dev in self._plans:
+            if synchronize:
+                torch.cuda.synchronize(dev)
+            _lib.raise_on_device_error(dev.index if dev.index is not None else torch.cuda.current_device())
+
     # ------------------------------------------------------------------ reference API
     def get_Heith_Map(self):
         zernike_coeffs_concat = torch.cat((self.Zer_no_train, self.Zer_train), 0)
