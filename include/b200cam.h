@@ -168,6 +168,22 @@ int b200cam_sensor_finish(const float* psf, float* sensor, float* img_max, int* 
                           const float* spectrum, int otf_ready, void* workspace, size_t workspace_bytes, int B, int N,
                           void* stream);
 
+/* Opt-in sensor read-out epilogue (north_star step 5 "sensor noise plus quantisation"; SURVEY trap T6).  The reference has
+ * no live sensor noise and no quantiser (its gaussian_noise call is commented out: Image_Caption/Camera/Lens.py:295-301,
+ * Utils.py:300-302; Face-DeId has none), so flags = 0 reproduces it.  With flags:
+ *     y = conv / max;   NOISE: y += noise_scale * noise[b][c][y][x];   QUANT: y = round(clamp(y, 0, 1) * L) / L,  L = 2^quant_bits - 1
+ * `noise` is a caller-supplied standard-normal tensor shaped like the images (draw it with the framework's seeded generator;
+ * a fused Philox could not reproduce torch's stream).  b200cam_sensor_bwd treats the epilogue as the identity (straight
+ * through).  Same arguments / reference lines as the calls without _ex. */
+#define B200CAM_SENSOR_NOISE 1
+#define B200CAM_SENSOR_QUANT 2
+int b200cam_sensor_fwd_ex(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos,
+                          float* otf, float* spectrum, void* workspace, size_t workspace_bytes, int B, int N, void* stream,
+                          int flags, const float* noise, float noise_scale, int quant_bits);
+int b200cam_sensor_finish_ex(const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos, float* otf,
+                             const float* spectrum, int otf_ready, void* workspace, size_t workspace_bytes, int B, int N,
+                             void* stream, int flags, const float* noise, float noise_scale, int quant_bits);
+
 /* Sensor image, backward (autograd through Optics.py:126-128 in closed form, incl. the amax term).
  *   grad_sensor [B][3][N][N]   dL/dsensor
  *   sensor, img_max, tie_count, tie_pos, otf, spectrum (or NULL): outputs of b200cam_sensor_fwd on the same img/psf

@@ -56,6 +56,12 @@ _SIGNATURES = {
     "b200cam_spectrum_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "b200cam_sensor_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _f,
                                           _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "b200cam_sensor_fwd_ex": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _f,
+                                             _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_int, _f, ctypes.c_float, ctypes.c_int]),
+    "b200cam_sensor_finish_ex": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, ctypes.c_int,
+                                                _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                ctypes.c_int, _f, ctypes.c_float, ctypes.c_int]),
     "b200cam_sensor_split_supported": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "b200cam_sensor_rows": (ctypes.c_int, [_f, _f, _f, _f, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "b200cam_psf_otf": (ctypes.c_int, [_f, _f, ctypes.c_int, ctypes.c_void_p]),

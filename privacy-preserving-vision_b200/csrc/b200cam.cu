@@ -1010,7 +1010,8 @@ static int sensor_rows_impl(const float* img, float2* srow, float* img_max, int*
 // second half: OTF of the PSF, column convolution, inverse rows + per-image max, normalise
 template <int N>
 static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos, float2* otf,
-                              const float2* srow, const SensorWs& ws, int B, int otf_ready, cudaStream_t s) {
+                              const float2* srow, const SensorWs& ws, int B, int otf_ready, cudaStream_t s,
+                              SensorEpilogue epi = SensorEpilogue{nullptr, 0.f, 0.f}) {
     using T = Tile<N>;
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
@@ -1020,7 +1021,7 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     }
     const int planes = 3 * B;
     if constexpr (N == 256) {
-        if (plane_selected()) {
+        if (plane_selected() && epi.noise == nullptr && epi.levels <= 0.f) {      // (the opt-in plane kernels have no read-out epilogue)
             const DeviceState* st = cur_state();
             if (st == nullptr || st->pconv_g3 < 1) return B200CAM_E_NOT_INIT;
             const int G3 = B < st->pconv_g3 ? B : st->pconv_g3;
@@ -1051,7 +1052,7 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
             const DeviceState* st = cur_state();
             launch_k(k_rows_c2r_persist<N>, grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s, 
                 RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, tie_count, tie_pos, 0, discard, fused ? ws.arrive : nullptr,
-                              fused ? 3 * (N / T::ROWS) : 0}, total, st != nullptr ? st->err_dev : nullptr);
+                              fused ? 3 * (N / T::ROWS) : 0, epi}, total, st != nullptr ? st->err_dev : nullptr);
             if (fused) {
                 LAUNCH_CHECK();
                 return 0;
@@ -1064,7 +1065,7 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     LAUNCH_CHECK();
     const long long n4 = static_cast<long long>(planes) * N * N / 4;
     const int grid = static_cast<int>(n4 / EW_THREADS < 148 * 8 ? (n4 + EW_THREADS - 1) / EW_THREADS : 148 * 8);
-    launch_k(k_normalise, grid, EW_THREADS, 0, s, NormaliseParams{sensor, img_max, tie_count, tie_pos, n4, 3 * N * N / 4});
+    launch_k(k_normalise, grid, EW_THREADS, 0, s, NormaliseParams{sensor, img_max, tie_count, tie_pos, n4, 3 * N * N / 4, epi});
     LAUNCH_CHECK();
     return 0;
 }
@@ -1192,12 +1193,13 @@ static int conv_bwd_impl(const float* g, const float* img, const float2* otf, co
 
 template <int N>
 static int sensor_fwd_impl(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
-                           int* tie_pos, float2* otf, float2* spectrum, void* ws_ptr, int B, cudaStream_t s) {
+                           int* tie_pos, float2* otf, float2* spectrum, void* ws_ptr, int B, cudaStream_t s,
+                           SensorEpilogue epi = SensorEpilogue{nullptr, 0.f, 0.f}) {
     SensorWs ws(ws_ptr, N, B, false);
     float2* srow = spectrum != nullptr ? spectrum : ws.stx;      // row spectra: kept for the backward when asked
     int rc = sensor_rows_impl<N>(img, srow, img_max, tie_count, B, s);
     if (rc) return rc;
-    return sensor_finish_impl<N>(psf, sensor, img_max, tie_count, tie_pos, otf, srow, ws, B, 0, s);
+    return sensor_finish_impl<N>(psf, sensor, img_max, tie_count, tie_pos, otf, srow, ws, B, 0, s, epi);
 }
 
 template <int N>
@@ -1636,9 +1638,33 @@ size_t b200cam_spectrum_bytes(int N, int B) {
     return static_cast<size_t>(3) * B * (N / 2 + 1) * N * sizeof(float2);
 }
 
+static int make_epilogue(int flags, const float* noise, float noise_scale, int quant_bits, SensorEpilogue* epi) {
+    *epi = SensorEpilogue{nullptr, 0.f, 0.f};
+    if (flags & ~(B200CAM_SENSOR_NOISE | B200CAM_SENSOR_QUANT)) return B200CAM_E_BAD_SIZE;
+    if (flags & B200CAM_SENSOR_NOISE) {
+        if (noise == nullptr) return B200CAM_E_NULL;
+        epi->noise = noise;
+        epi->noise_scale = noise_scale;
+    }
+    if (flags & B200CAM_SENSOR_QUANT) {
+        if (quant_bits < 1 || quant_bits > 16) return B200CAM_E_BAD_SIZE;
+        epi->levels = static_cast<float>((1 << quant_bits) - 1);
+    }
+    return 0;
+}
+
 int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
                        int* tie_pos, float* otf, float* spectrum, void* workspace, size_t workspace_bytes, int B,
                        int N, void* stream) {
+    return b200cam_sensor_fwd_ex(img, psf, sensor, img_max, tie_count, tie_pos, otf, spectrum, workspace, workspace_bytes, B, N,
+                                 stream, 0, nullptr, 0.f, 0);
+}
+
+int b200cam_sensor_fwd_ex(const float* img, const float* psf, float* sensor, float* img_max, int* tie_count,
+                          int* tie_pos, float* otf, float* spectrum, void* workspace, size_t workspace_bytes, int B,
+                          int N, void* stream, int flags, const float* noise, float noise_scale, int quant_bits) {
+    SensorEpilogue epi;
+    if (const int rc = make_epilogue(flags, noise, noise_scale, quant_bits, &epi)) return rc;
     if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
     if (!img || !psf || !sensor || !img_max || !tie_count || !tie_pos || !otf || !workspace) return B200CAM_E_NULL;
     if (workspace_bytes < b200cam_sensor_workspace_bytes(N, B, 0)) return B200CAM_E_WORKSPACE;
@@ -1648,7 +1674,7 @@ int b200cam_sensor_fwd(const float* img, const float* psf, float* sensor, float*
     if (spectrum != nullptr && !aligned16(spectrum)) return B200CAM_E_ALIGN;
     DISPATCH_N(N, (sensor_fwd_impl<NN_>(img, psf, sensor, img_max, tie_count, tie_pos,
                                         reinterpret_cast<float2*>(otf), reinterpret_cast<float2*>(spectrum), workspace,
-                                        B, s)));
+                                        B, s, epi)));
 }
 
 int b200cam_sensor_split_supported(int N, int B) {
@@ -1677,6 +1703,15 @@ int b200cam_psf_otf(const float* psf, float* otf, int N, void* stream) {
 int b200cam_sensor_finish(const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos, float* otf,
                           const float* spectrum, int otf_ready, void* workspace, size_t workspace_bytes, int B, int N,
                           void* stream) {
+    return b200cam_sensor_finish_ex(psf, sensor, img_max, tie_count, tie_pos, otf, spectrum, otf_ready, workspace, workspace_bytes,
+                                    B, N, stream, 0, nullptr, 0.f, 0);
+}
+
+int b200cam_sensor_finish_ex(const float* psf, float* sensor, float* img_max, int* tie_count, int* tie_pos, float* otf,
+                             const float* spectrum, int otf_ready, void* workspace, size_t workspace_bytes, int B, int N,
+                             void* stream, int flags, const float* noise, float noise_scale, int quant_bits) {
+    SensorEpilogue epi;
+    if (const int rc = make_epilogue(flags, noise, noise_scale, quant_bits, &epi)) return rc;
     if (!b200cam_supported(N) || B < 1) return B200CAM_E_BAD_SIZE;
     if (!psf || !sensor || !img_max || !tie_count || !tie_pos || !otf || !spectrum || !workspace) return B200CAM_E_NULL;
     if (workspace_bytes < b200cam_sensor_workspace_bytes(N, B, 0)) return B200CAM_E_WORKSPACE;
@@ -1686,7 +1721,7 @@ int b200cam_sensor_finish(const float* psf, float* sensor, float* img_max, int* 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DISPATCH_N(N, (sensor_finish_impl<NN_>(psf, sensor, img_max, tie_count, tie_pos, reinterpret_cast<float2*>(otf),
                                            reinterpret_cast<const float2*>(spectrum), SensorWs(workspace, NN_, B, false),
-                                           B, otf_ready, s)));
+                                           B, otf_ready, s, epi)));
 }
 
 int b200cam_conv_fwd(const float* img, const float* kernel, float* out, float* otf, float* spectrum, void* workspace,

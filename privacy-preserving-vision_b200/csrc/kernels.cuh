@@ -441,6 +441,26 @@ B200_HD void cols_fwd_body(Exec& ex, const ColsFwdParams& p, float2* smem) {
 // ---------------------------------------------------------------------------------------------
 constexpr int C2R_MAX_TIES = 8;     // = MAX_TIES (declared with the normalise kernel below)
 
+// Opt-in sensor read-out epilogue (north_star step 5; SURVEY trap T6: the reference has NO live sensor noise and no
+// quantisation - its gaussian_noise call is commented out, Image_Caption/Camera/Lens.py:295-301, Utils.py:300-302 - so
+// both are OFF unless asked for):   y <- conv / max ;  y += noise_scale * noise[idx] ;  y <- round(clamp(y,0,1) * L) / L
+// `noise` is a caller-supplied N(0,1) tensor shaped like the image batch (drawn with torch's generator, so a run is
+// reproducible against the oracle); L = 2^bits - 1.  The backward is straight through (dL/dconv as if the epilogue
+// were the identity), the usual treatment of a quantiser.
+struct SensorEpilogue {
+    const float* noise;      // nullable
+    float noise_scale;
+    float levels;            // <= 0: no quantisation
+};
+B200_HD float apply_epilogue(const SensorEpilogue& e, float y, size_t idx) {
+    if (e.noise != nullptr) y += e.noise_scale * ld_ro(e.noise + idx);
+    if (e.levels > 0.f) {
+        y = fminf(fmaxf(y, 0.f), 1.f);
+        y = rintf(y * e.levels) / e.levels;
+    }
+    return y;
+}
+
 struct RowsC2RParams {
     const float2* st;    // [planes][NC][N]
     float* out;          // [planes][N][N]; nullptr: nothing is stored (max-only pass)
@@ -460,6 +480,7 @@ struct RowsC2RParams {
     // persistent grid - have long arrived.  No un-normalised image, no normalise pass (Optics.py:128).
     int* arrive;         // [planes/3], zero on entry
     int arrivals;        // tiles per image = 3 * N / ROWS
+    SensorEpilogue epi;  // applied by the one-pass mode where it writes y
 };
 
 template <int N, class Exec>
@@ -627,8 +648,9 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
         for (int i = 0; i < P::R1; ++i) {
             eq |= (v[i].x == m ? 1u : 0u) << (2 * i);
             eq |= (v[i].y == m ? 1u : 0u) << (2 * i + 1);
-            p.out[row + P::R2 * i + a] = v[i].x == m ? 1.0f : v[i].x * inv;       // the arg-max itself: exactly 1 (torch: x / x)
-            p.out[row + N + P::R2 * i + a] = v[i].y == m ? 1.0f : v[i].y * inv;
+            const size_t i0 = row + P::R2 * i + a, i1 = i0 + N;
+            p.out[i0] = apply_epilogue(p.epi, v[i].x == m ? 1.0f : v[i].x * inv, i0);    // the arg-max itself: exactly 1 (torch: x / x)
+            p.out[i1] = apply_epilogue(p.epi, v[i].y == m ? 1.0f : v[i].y * inv, i1);
         }
         while (eq != 0u) {                                                         // rare
             int bit = 0;
@@ -758,6 +780,7 @@ struct NormaliseParams {
     int* tie_pos;           // [B][MAX_TIES] flat index into (3,N,N)
     long long n4;           // number of float4 elements
     int per_image4;         // 3*N*N/4
+    SensorEpilogue epi;
 };
 
 // Four independent float4 per thread and iteration (the kernel is a pure stream: keep loads in flight).
@@ -796,6 +819,7 @@ B200_HD void normalise_body(Exec& ex, const NormaliseParams& p, int grid_x) {
                     } else {
                         e[q] *= inv;
                     }
+                    e[q] = apply_epilogue(p.epi, e[q], static_cast<size_t>(i) * 4 + q);
                 }
                 y4[i] = make_float4(e[0], e[1], e[2], e[3]);
             }

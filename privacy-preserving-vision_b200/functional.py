@@ -260,8 +260,20 @@ def sensor_rows(img: torch.Tensor, plan: DevicePlan):
 
 class SensorConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan, rows: RowSpectra | None = None):
+    def forward(ctx, img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan, rows: RowSpectra | None = None, epilogue=None):
+        """`epilogue`: None (the reference's read-out: nothing) or (noise, noise_scale, quant_bits) - the opt-in sensor
+        noise + quantisation of include/b200cam.h (B200CAM_SENSOR_NOISE / _QUANT); straight-through in backward."""
         N = plan.N
+        flags, noise_t, noise_scale, quant_bits = 0, None, 0.0, 0
+        if epilogue is not None:
+            noise_t, noise_scale, quant_bits = epilogue
+            if noise_t is not None:
+                noise_t = _as_f32(noise_t.detach(), plan.device)
+                if noise_t.shape != img.shape:
+                    raise ValueError(f"sensor noise must have the shape of the images {tuple(img.shape)}, got {tuple(noise_t.shape)}")
+                flags |= 1
+            if quant_bits:
+                flags |= 2
         _check_img(img, N)
         x = rows.x if rows is not None else _as_f32(img.detach(), plan.device)
         p = _as_f32(psf.detach(), plan.device).reshape(3, N, N)
@@ -283,17 +295,19 @@ class SensorConv(torch.autograd.Function):
                 otf = cached[1]
             plan.otf_cache = None
             with torch.cuda.device(plan.index):
-                _lib.check(plan.lib.b200cam_sensor_finish(
+                _lib.check(plan.lib.b200cam_sensor_finish_ex(
                     _lib.ptr(p), _lib.ptr(sensor), _lib.ptr(img_max), _lib.ptr(tie_count), _lib.ptr(tie_pos),
-                    _lib.ptr(otf), _lib.ptr(spectrum), otf_ready, _lib.ptr(ws), ws.numel(), B, N, _stream()))
+                    _lib.ptr(otf), _lib.ptr(spectrum), otf_ready, _lib.ptr(ws), ws.numel(), B, N, _stream(),
+                    flags, _lib.ptr(noise_t), float(noise_scale), int(quant_bits)))
             if not any(ctx.needs_input_grad[:2]):
                 spectrum = None
         elif B > 0:
             ws = plan.sensor_workspace(B)
             with torch.cuda.device(plan.index):
-                _lib.check(plan.lib.b200cam_sensor_fwd(
+                _lib.check(plan.lib.b200cam_sensor_fwd_ex(
                     _lib.ptr(x), _lib.ptr(p), _lib.ptr(sensor), _lib.ptr(img_max), _lib.ptr(tie_count),
-                    _lib.ptr(tie_pos), _lib.ptr(otf), _lib.ptr(spectrum), _lib.ptr(ws), ws.numel(), B, N, _stream()))
+                    _lib.ptr(tie_pos), _lib.ptr(otf), _lib.ptr(spectrum), _lib.ptr(ws), ws.numel(), B, N, _stream(),
+                    flags, _lib.ptr(noise_t), float(noise_scale), int(quant_bits)))
         ctx.plan = plan
         ctx.psf_shape = psf.shape
         ctx.spectrum = spectrum
@@ -319,12 +333,13 @@ class SensorConv(torch.autograd.Function):
                     _lib.ptr(tie_pos), _lib.ptr(p), _lib.ptr(otf), _lib.ptr(ctx.spectrum), _lib.ptr(grad_psf),
                     _lib.ptr(grad_img),
                     _lib.ptr(ws), ws.numel(), B, N, _stream()))
-        return grad_img, grad_psf.reshape(ctx.psf_shape), None, None
+        return grad_img, grad_psf.reshape(ctx.psf_shape), None, None, None
 
 
 def psf_synth(h: torch.Tensor, plan: DevicePlan, stream: torch.cuda.Stream | None = None):
     return PsfSynth.apply(h, plan, stream)
 
 
-def sensor_conv(img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan, rows: RowSpectra | None = None) -> torch.Tensor:
-    return SensorConv.apply(img, psf, plan, rows)
+def sensor_conv(img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan, rows: RowSpectra | None = None,
+                epilogue=None) -> torch.Tensor:
+    return SensorConv.apply(img, psf, plan, rows, epilogue)

@@ -61,6 +61,10 @@ class Camera(nn.Module):
         self.centering_loss = None
         self.psf_rad = None
 
+        # opt-in sensor read-out (north_star step 5; the reference has neither, SURVEY trap T6): additive Gaussian noise of this
+        # standard deviation on the normalised sensor image, then quantisation to this many bits; 0 / 0 = the reference
+        self.sensor_noise_sigma = 0.0
+        self.sensor_quant_bits = 0
         self.overlap_psf = True          # run the PSF-independent half of forward() beside the PSF synthesis
         self._plans: dict[torch.device, F.DevicePlan] = {}
         self._pending_centering = None
@@ -150,7 +154,18 @@ class Camera(nn.Module):
         self._pending_centering = centering
         return self.psfs
 
-    def forward(self, img):
+    def _epilogue(self, img, noise):
+        """(noise tensor, sigma, bits) for the kernels, or None when the read-out epilogue is off (the reference)."""
+        sigma, bits = float(self.sensor_noise_sigma), int(self.sensor_quant_bits)
+        if noise is None and sigma > 0.0:
+            noise = torch.randn(img.shape, dtype=torch.float32, device=img.device)     # torch's global generator: seed it to reproduce
+        if noise is None and bits == 0:
+            return None
+        return (noise, sigma if noise is not None else 0.0, bits)
+
+    def forward(self, img, noise=None):
+        """`noise`: optional standard-normal tensor shaped like `img` for the opt-in sensor noise (drawn here with
+        torch.randn when `sensor_noise_sigma > 0` and none is given)."""
         # uint8 images (what a decoder produces; the reference's loader turns them into fp32 in [0,1] with ToTensor on the
         # host, Face-DeId/core/data_loader.py:118-124) may be passed as they are: the division by 255 then happens on the
         # GPU and the host->device copy is a quarter of the fp32 one.
@@ -162,10 +177,11 @@ class Camera(nn.Module):
         h_dev = self.Zer_train.device
         overlap = (self.overlap_psf and torch.is_tensor(img) and img.is_cuda and img.dim() == 4 and img.shape[0] > 0
                    and h_dev.type == "cuda")
+        epi = self._epilogue(img, noise) if torch.is_tensor(img) else None
         if not overlap:
             psf = self.get_psf()
             self.centering_loss = self._pending_centering
-            return F.sensor_conv(img, psf, self._plan(psf.device))
+            return F.sensor_conv(img, psf, self._plan(psf.device), None, epi)
         plan = self._plan(img.device)
         side = plan.side_stream()
         psf = self.get_psf(_stream=side)                       # enqueued on `side`, not joined yet
@@ -177,7 +193,7 @@ class Camera(nn.Module):
             ev, plan.otf_event = plan.otf_event, None
             cur.wait_event(ev)
             self.centering_loss = self._pending_centering
-            y = F.sensor_conv(img, psf, self._plan(psf.device), rows)
+            y = F.sensor_conv(img, psf, self._plan(psf.device), rows, epi)
             aux = plan.aux_stream()
             aux.wait_event(ev)
             plan.finish_psf(aux)
@@ -187,4 +203,4 @@ class Camera(nn.Module):
         plan.finish_psf(side)
         cur.wait_stream(side)
         self.centering_loss = self._pending_centering
-        return F.sensor_conv(img, psf, self._plan(psf.device), rows)
+        return F.sensor_conv(img, psf, self._plan(psf.device), rows, epi)

@@ -361,3 +361,36 @@ def test_fused_peer_allreduce_matches_nccl_when_two_gpus_are_visible():
     m = re.search(r"PEER_ALLREDUCE world=2 rel_vs_nccl=([0-9.e+-]+) rel_graph=([0-9.e+-]+)", res.stdout + res.stderr)
     assert m, (res.stdout + res.stderr)[-2000:]
     assert float(m.group(1)) <= 1e-5 and float(m.group(2)) <= 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,B", [(256, 5), (512, 2)])
+def test_opt_in_sensor_noise_and_quantisation(N, B):
+    """north_star step 5 / SURVEY trap T6: the opt-in read-out epilogue (include/b200cam.h B200CAM_SENSOR_NOISE / _QUANT).
+    Off by default (the reference has neither: Image_Caption/Camera/Lens.py:295-301 is commented out); with it, the
+    sensor image equals round(clamp(conv/max + sigma*noise, 0, 1) * L) / L for the SAME torch.randn tensor, and the
+    gradient into the height map is the one of the plain read-out (straight through).  N = 256 runs the one-pass inverse-row
+    kernel, N = 512 the normalise kernel.  Tolerance: a value within float rounding of a quantisation boundary may fall on
+    either side, so at most 0.1 % of the pixels may differ, each by exactly one level."""
+    h_cpu, img, w = synth.height_map(N, 3), synth.images(B, N, 4), synth.upstream_grad(B, N, 5)
+    out, gh = oracle_step(img, w, h_cpu, N)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    noise = torch.randn(B, 3, N, N, generator=g, device="cuda")
+    sigma, bits = 0.01, 8
+    L = float(2 ** bits - 1)
+    cam, h = make_camera(N, h_cpu)
+    cam.sensor_noise_sigma, cam.sensor_quant_bits = sigma, bits
+    y = cam(img.cuda(), noise=noise)
+    ((y * w.cuda()).sum() + cam.loss_rad + cam.centering_loss).backward()
+    ref = torch.round(torch.clamp(out["sensor"] + sigma * noise.cpu(), 0.0, 1.0) * L) / L
+    diff = (y.detach().cpu() - ref).abs()
+    assert float(diff.max()) <= 1.0 / L + 1e-6
+    assert float((diff > 1e-6).float().mean()) <= 1e-3
+    assert torch.all((y.detach() * L - torch.round(y.detach() * L)).abs() < 1e-3)      # on the quantisation grid
+    assert rel_l2(h.grad, gh) <= TOL_GRAD                                               # straight-through backward
+    # noise only (no quantiser): exact up to fp32 rounding
+    cam2, _ = make_camera(N, h_cpu)
+    cam2.sensor_noise_sigma = sigma
+    with torch.no_grad():
+        y2 = cam2(img.cuda(), noise=noise)
+    assert rel_l2(y2, out["sensor"] + sigma * noise.cpu()) <= TOL_SENSOR
