@@ -209,6 +209,35 @@ int b200cam_conv_fwd(const float* img, const float* kernel, float* out, float* o
 int b200cam_conv_bwd(const float* grad_out, const float* img, const float* otf, const float* spectrum, float* grad_kernel,
                      float* grad_img, void* workspace, size_t workspace_bytes, int B, int N, void* stream);
 
+/* PSF synthesis of the Image_Caption camera (OpticsZernike.forward, Image_Caption/Camera/Lens.py:176-274), batch
+ * independent, and its adjoint into the height map.  R = wave resolution (R x R height map, R % 4 == 0), P = patch size.
+ *   phase plate        field = A * exp(i delta_l (h + noise))        Utils.py:192-205 (fp64 phase -> complex64), 396-410
+ *   Fresnel propagation zero-pad R -> n = R + 2 (R/4), FFT2, x H, IFFT2, crop     Utils.py:329-378.  n = 1344 = 2^6 3 7 for the
+ *                      shipped R = 896: mixed-radix transforms (2/3/4/5/7/8 and any prime <= 31), zero rows / columns pruned
+ *   intensity, area down-sampling to P x P (nearest x up, up x up mean)           Utils.py:208, 216-248
+ *   per-channel normalisation, disc masks and energy loss                         Lens.py:239, 269-274
+ * Inputs (device unless noted):
+ *   h [R][R] fp32; noise [R][R] fp32 or NULL - the U(-tol,tol) field of PhasePlate._build drawn by the caller with the
+ *   reference's own torch.rand call; A [3][R][R] complex64 = aperture * spherical wavefront (Lens.py:191-213, Utils.py:88-97);
+ *   delta HOST double[3] = 2 pi / lambda_l * (n_l - 1); Hx [3][n] complex128 = exp(-i pi lambda_l z f_k^2), f in FFT order
+ *   (the transfer function is separable: H(fx, fy) = Hx(fx) Hx(fy), multiplied in fp64); tw [n] complex64 = exp(-2 pi i k / n);
+ *   mask1 / mask2 [P][P][3] fp64 (flags & 1 / flags & 2), else NULL.
+ * Outputs: field, U [3][R][R] complex64 (saved for the backward); psf [P][P][3] fp32 (normalised, unmasked); chan_sum [3];
+ *   psf_out [P][P][3] fp64 = psf (* mask2 with flag 2); loss: device double = || psf * mask1 - psf ||_2 (flag 1).
+ * flags: 1 = energy loss (prueba "1"/"3"), 2 = mask the PSF (prueba "2"/"3"). */
+int b200cam_lens_psf_supported(int R, int P);
+int b200cam_lens_psf_padded(int R);                                  /* n */
+size_t b200cam_lens_psf_workspace_bytes(int R, int P);
+int b200cam_lens_psf_fwd(const float* h, const float* noise, const float* A, const double* delta, const double* Hx, const float* tw,
+                         float* field, float* U, float* psf, float* chan_sum, const double* mask1, const double* mask2, int flags,
+                         double* psf_out, double* loss, void* workspace, size_t workspace_bytes, int R, int P, void* stream);
+/* grad_psf_out [P][P][3] fp64 (dL/dpsf_out) or NULL, grad_loss device double or NULL; the rest as produced by the forward.
+ * grad_h [R][R] fp32 out. */
+int b200cam_lens_psf_bwd(const double* grad_psf_out, const double* grad_loss, const double* loss, const float* psf,
+                         const float* chan_sum, const float* field, const float* U, const double* delta, const double* Hx,
+                         const float* tw, const double* mask1, const double* mask2, int flags, float* grad_h, void* workspace,
+                         size_t workspace_bytes, int R, int P, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,15 @@ _SIGNATURES = {
                                         ctypes.c_void_p]),
     "b200cam_sensor_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f,
                                           _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "b200cam_lens_psf_supported": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "b200cam_lens_psf_padded": (ctypes.c_int, [ctypes.c_int]),
+    "b200cam_lens_psf_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "b200cam_lens_psf_fwd": (ctypes.c_int, [_f, _f, _f, ctypes.POINTER(ctypes.c_double), _f, _f, _f, _f, _f, _f, _f, _f,
+                                            ctypes.c_int, _f, _f, _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p]),
+    "b200cam_lens_psf_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, ctypes.POINTER(ctypes.c_double), _f, _f, _f, _f,
+                                            ctypes.c_int, _f, _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -83,18 +92,34 @@ def sources() -> list[Path]:
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu into csrc/libb200cam.so for sm_100a (cross-compiles without a GPU)."""
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))
-    if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
-        return LIB_PATH
+    headers = list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))
+    if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in sources() + headers):
+        return LIB_PATH                      # (the GPU box gets the built library, not the objects)
+    newest_header = max(h.stat().st_mtime for h in headers)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(s) for s in sources()]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+    objdir = CSRC / "build"
+    objdir.mkdir(exist_ok=True)
+    # one object per translation unit, compiled side by side; only stale ones are rebuilt (every TU includes the headers)
+    jobs, objs = [], []
+    for src in sources():
+        obj = objdir / (src.stem + ".o")
+        objs.append(obj)
+        if force or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, newest_header):
+            cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-shared"], "-c", "-o", str(obj), str(src)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for cmd, proc in jobs:
+        out, err = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{out}\n{err}")
+        if verbose:
+            print(err)
+    if jobs or not LIB_PATH.exists() or any(LIB_PATH.stat().st_mtime < o.stat().st_mtime for o in objs):
+        cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *[str(o) for o in objs]]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
     return LIB_PATH
 
 

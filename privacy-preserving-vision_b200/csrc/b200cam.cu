@@ -808,6 +808,7 @@ struct SensorWs {
         if (e_ != cudaSuccess) return static_cast<int>(e_); \
     } while (0)
 static std::atomic<unsigned long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }   // other translation units (lens_psf.cu)
 #define LAUNCH_CHECK()           \
     do {                         \
         CK(cudaGetLastError());  \

@@ -160,6 +160,53 @@ class GlobalMaxNormalise(torch.autograd.Function):
         return g / m - ties * (owner * s / (m * n)), None
 
 
+class LensPsf(torch.autograd.Function):
+    """height map (R,R) [+ tolerance noise] -> normalised PSF (1,P,P,3) and the energy loss, Lens.py:176-274, on the
+    b200cam kernels of ``csrc/lens_psf.cu`` (phase plate, pruned mixed-radix Fresnel propagation, intensity, area
+    down-sampling, per-channel normalisation, masks / loss) with the closed-form adjoint chain as backward.
+    ``flags``: 1 = energy loss against mask_1 (prueba "1"/"3"), 2 = multiply by mask_2 (prueba "2"/"3")."""
+
+    @staticmethod
+    def forward(ctx, h: torch.Tensor, noise, c: dict, flags: int, R: int, P: int, lib):
+        dev = h.device
+        hh = F._as_f32(h.detach(), dev).reshape(R, R)
+        nz = F._as_f32(noise.detach(), dev).reshape(R, R) if noise is not None else None
+        field = torch.empty(3, R, R, 2, dtype=torch.float32, device=dev)
+        U = torch.empty(3, R, R, 2, dtype=torch.float32, device=dev)
+        psf = torch.empty(1, P, P, 3, dtype=torch.float32, device=dev)
+        psf_out = torch.empty(1, P, P, 3, dtype=torch.float64, device=dev)
+        chan_sum = torch.empty(3, dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float64, device=dev)
+        ws = torch.empty(lib.b200cam_lens_psf_workspace_bytes(R, P), dtype=torch.uint8, device=dev)
+        m1, m2 = (c["mask1"] if flags & 1 else None), (c["mask2"] if flags & 2 else None)
+        with torch.cuda.device(dev):
+            _lib.check(lib.b200cam_lens_psf_fwd(_lib.ptr(hh), _lib.ptr(nz), _lib.ptr(c["A"]), c["delta_c"], _lib.ptr(c["Hx"]),
+                                                _lib.ptr(c["tw"]), _lib.ptr(field), _lib.ptr(U), _lib.ptr(psf), _lib.ptr(chan_sum),
+                                                _lib.ptr(m1), _lib.ptr(m2), flags, _lib.ptr(psf_out), _lib.ptr(loss),
+                                                _lib.ptr(ws), ws.numel(), R, P, F._stream()))
+        ctx.c, ctx.flags, ctx.geom, ctx.lib, ctx.hshape = c, flags, (R, P), lib, h.shape
+        ctx.save_for_backward(psf, chan_sum, field, U, loss)
+        # the reference's PSF is fp32 until an fp64 mask promotes it (Lens.py:239 vs :274)
+        return (psf_out if flags & 2 else psf), (loss if flags & 1 else None)
+
+    @staticmethod
+    def backward(ctx, g_psf, g_loss):
+        psf, chan_sum, field, U, loss = ctx.saved_tensors
+        c, flags, (R, P), lib = ctx.c, ctx.flags, ctx.geom, ctx.lib
+        dev = psf.device
+        gp = g_psf.detach().to(device=dev, dtype=torch.float64).contiguous() if g_psf is not None else None
+        gl = g_loss.detach().to(device=dev, dtype=torch.float64).reshape(()).contiguous() if g_loss is not None else None
+        grad_h = torch.empty(R, R, dtype=torch.float32, device=dev)
+        ws = torch.empty(lib.b200cam_lens_psf_workspace_bytes(R, P), dtype=torch.uint8, device=dev)
+        m1, m2 = (c["mask1"] if flags & 1 else None), (c["mask2"] if flags & 2 else None)
+        with torch.cuda.device(dev):
+            _lib.check(lib.b200cam_lens_psf_bwd(_lib.ptr(gp), _lib.ptr(gl), _lib.ptr(loss), _lib.ptr(psf), _lib.ptr(chan_sum),
+                                                _lib.ptr(field), _lib.ptr(U), c["delta_c"], _lib.ptr(c["Hx"]), _lib.ptr(c["tw"]),
+                                                _lib.ptr(m1), _lib.ptr(m2), flags, _lib.ptr(grad_h), _lib.ptr(ws), ws.numel(),
+                                                R, P, F._stream()))
+        return grad_h.reshape(ctx.hshape), None, None, None, None, None, None
+
+
 class OpticsZernike(nn.Module):
     def __init__(self,
                  input_shape,
@@ -273,6 +320,25 @@ class OpticsZernike(nn.Module):
                              * (self.refractive_idcs.reshape([1, 1, 1, -1]) - 1.))
         c = {"wavefront": wavefront.to(dev), "aperture": aperture.to(dev), "H": H.to(dev), "delta": delta.to(dev),
              "pad": (Mpad, Npad)}
+        lib = _lib.load_library() if dev.type == "cuda" else None
+        c["kernels"] = bool(lib is not None and N == M and lib.b200cam_lens_psf_supported(N, self.patch_size))
+        if c["kernels"]:
+            # tables of csrc/lens_psf.cu: A = aperture * wavefront, planar (3,R,R) complex64 (the aperture is 0/1: exact);
+            # the transfer function as two 1-D fp64 factors H(fx,fy) = E(fx) E(fy), E = exp(-i pi lambda z f^2) in FFT order;
+            # twiddles exp(-2 pi i k / n) rounded from fp64
+            n = Np
+            A = (aperture.to(torch.complex64) * wavefront)[0].permute(2, 0, 1).contiguous()
+            f1 = np.fft.ifftshift(np.arange(-n // 2, n // 2) / (self.sample_interval * n))
+            e1 = self.wave_lengths[:, None] * np.pi * -1. * np.square(f1)[None, :] * self.sensor_distance      # (3, n) fp64
+            ang = -2.0 * np.pi * np.arange(n) / n
+            c["A"] = torch.view_as_real(A).contiguous().to(dev)
+            c["Hx"] = torch.tensor(np.stack([np.cos(e1), np.sin(e1)], axis=-1), dtype=torch.float64, device=dev).contiguous()
+            c["tw"] = torch.tensor(np.stack([np.cos(ang), np.sin(ang)], axis=-1).astype(np.float32), device=dev).contiguous()
+            c["delta_c"] = (ctypes.c_double * 3)(*[float(v) for v in delta.reshape(-1)])
+            ok = tuple(self.mask_1.shape) == (self.patch_size, self.patch_size, 3)
+            c["mask1"] = self.mask_1.to(device=dev, dtype=torch.float64).contiguous() if ok else None
+            c["mask2"] = self.mask_2.to(device=dev, dtype=torch.float64).contiguous() if ok else None
+            c["lib"] = lib
         self._const[key] = c
         return c
 
@@ -286,8 +352,23 @@ class OpticsZernike(nn.Module):
             self._plans[(device, n)] = plan
         return plan
 
+    def _psf_kernels(self, height_map: torch.Tensor, flags: int):
+        """(psf, loss) through csrc/lens_psf.cu, or None when the geometry is outside what the kernels cover (padded
+        size with a prime factor above 31, masks of another size): the caller then uses the torch expression."""
+        c = self._constants(height_map.device)
+        if not c["kernels"] or (flags and c["mask1"] is None):
+            return None
+        noise = None
+        if self.height_tolerance is not None:                      # PhasePlate._build, Utils.py:396-406: same torch.rand call
+            noise = ((-self.height_tolerance - self.height_tolerance)
+                     * torch.rand(list(height_map.shape), dtype=height_map.dtype, device=height_map.device)
+                     + self.height_tolerance)
+        R = self.wave_res[0]
+        return LensPsf.apply(height_map.reshape(R, R), noise, c, flags, R, self.patch_size, c["lib"])
+
     def _psf(self, height_map: torch.Tensor) -> torch.Tensor:
-        """height map (1,R,R,1) -> normalised PSF (1,P,P,3)  (Lens.py:180-239)."""
+        """height map (1,R,R,1) -> normalised PSF (1,P,P,3)  (Lens.py:180-239), torch expression (geometries the kernels
+        do not cover)."""
         c = self._constants(height_map.device)
         if self.height_tolerance is not None:                      # PhasePlate._build, Utils.py:396-406
             height_map = height_map + ((-self.height_tolerance - self.height_tolerance)
@@ -353,13 +434,17 @@ class OpticsZernike(nn.Module):
             coeffs[:] = 0
             coeffs[3] = -22
         height_map = self._project(coeffs).unsqueeze(0).unsqueeze(-1)
-        psf = self._psf(height_map)
-
-        loss = None
-        if prueba == "1" or prueba == "3":
-            loss = torch.norm((psf * self.mask_1) - psf)
-        if prueba == "2" or prueba == "3":
-            psf = psf * self.mask_2
+        flags = (1 if prueba in ("1", "3") else 0) | (2 if prueba in ("2", "3") else 0)
+        fused = self._psf_kernels(height_map, flags) if height_map.is_cuda else None
+        if fused is not None:
+            psf, loss = fused
+        else:
+            psf = self._psf(height_map)
+            loss = None
+            if prueba == "1" or prueba == "3":
+                loss = torch.norm((psf * self.mask_1) - psf)
+            if prueba == "2" or prueba == "3":
+                psf = psf * self.mask_2
 
         sensor = self._sensor(input_img, psf)
         np.random.uniform(low=0.001, high=0.02)                     # noise_sigma is drawn and discarded (Lens.py:295)

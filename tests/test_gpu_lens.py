@@ -109,3 +109,51 @@ def test_crop_abs_resize_matches_torch_expression(P, B):
     (out * w).sum().backward()
     assert torch.equal(out, ref)
     assert torch.allclose(b.grad, a.grad, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("wave,patch", [(128, 64), (896, 256), (160, 64)])
+@pytest.mark.parametrize("prueba", [None, "3"])
+def test_psf_kernels_match_oracle_with_tolerance_noise(wave, patch, prueba):
+    """csrc/lens_psf.cu (phase plate + pruned mixed-radix Fresnel propagation + down-sampling + normalisation, masks and
+    loss) against oracle/lens_oracle.py::psf_from_height_map, forward and dL/dcoeffs, with the height-tolerance noise live:
+    the module draws it with the reference's torch.rand call (Utils.py:401-404), the oracle is given the same field.
+    wave 896 -> 1344 = 2^6*3*7, 128 -> 192 = 2^6*3, 160 -> 240 = 2^4*3*5."""
+    terms = 10
+    if prueba is not None and patch != 256:
+        pytest.skip("the reference's disc masks are 256 x 256 (Lens.py:113-129)")
+    dev = torch.device("cuda", 0)
+    coeffs = torch.zeros(terms, 1, 1)
+    coeffs[3], coeffs[4], coeffs[6] = -22.0 * (wave / 896) ** 2, 0.4, -0.2
+    cam = OpticsZernike(input_shape=[1, patch, patch, 3], device=dev, wave_resolution=(wave, wave), patch_size=patch,
+                        sample_interval=3e-6, zernike_terms=terms, height_tolerance=20e-9).to(dev)
+    with torch.no_grad():
+        cam.zernike_coeffs_train.copy_(coeffs[3])
+        cam.zernike_coeffs_no_train2.copy_(coeffs[4:])
+    assert cam._constants(dev)["kernels"]
+    flags = 3 if prueba == "3" else 0
+    torch.manual_seed(11)
+    height = cam.get_Heith_Map().unsqueeze(-1)
+    psf, loss = cam._psf_kernels(height, flags)
+    g = torch.Generator().manual_seed(3)
+    wpsf = torch.rand(1, patch, patch, 3, generator=g, dtype=torch.float64)
+    obj = (psf.double() * wpsf.cuda()).sum() * 1e3 + (loss if loss is not None else 0.0)
+    obj.backward()
+    grad = cam.zernike_coeffs_train.grad.clone()
+
+    torch.manual_seed(11)                                           # the same noise field as the module drew
+    noise = ((-20e-9 - 20e-9) * torch.rand([1, wave, wave, 1], dtype=torch.float32, device=dev) + 20e-9).cpu()
+    cfg = lo.LensConfig(wave_res=wave, patch=patch, sample_interval=3e-6)
+    vol = torch.tensor(zern.zernike_volume(wave, terms, 1e-6).astype(np.float32))
+    cz = coeffs.clone().requires_grad_(True)
+    hm = torch.sum(cz * vol, dim=0)[None, :, :, None]
+    ref = lo.psf_from_height_map(hm, cfg, noise)
+    ref_loss = None
+    if prueba == "3":
+        ref_loss = torch.norm((ref * cam.mask_1.cpu()) - ref)
+        ref = ref * cam.mask_2.cpu()
+    ((ref.double() * wpsf).sum() * 1e3 + (ref_loss if ref_loss is not None else 0.0)).backward()
+    assert psf.dtype == ref.dtype
+    assert rel_l2(psf, ref) <= 1e-4
+    if ref_loss is not None:
+        assert abs(float(loss) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
+    assert abs(float(grad) - float(cz.grad[3])) <= 1e-3 * abs(float(cz.grad[3]))
