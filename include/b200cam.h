@@ -238,6 +238,30 @@ int b200cam_lens_psf_bwd(const double* grad_psf_out, const double* grad_loss, co
                          const float* tw, const double* mask1, const double* mask2, int flags, float* grad_h, void* workspace,
                          size_t workspace_bytes, int R, int P, void* stream);
 
+/* Sensor image of the Image_Caption camera: img_psf_conv (Image_Caption/Camera/Utils.py:251-297) + the batch-global
+ * normalisation (Lens.py:312) with the padding, |.|, crop and nearest resize inside the transform kernels.  P = patch size
+ * (64, 128, 256 or 512), transform size n = 2P (b200cam_init(n) first).  The 4x zero-padded image and the 4x convolution
+ * output of the reference never exist: zero rows / columns are pruned from every pass.
+ *   b200cam_lens_sensor_fwd   raw[b][c][i][j] = conv[pt + max(i,1)][pt + max(j,1)], conv = ifft2(fft2(pad(img)) * OTF), pt = P/2
+ *                             (signed: the sensor value is |raw|; = Utils.py:279-295), gmax = max(gmax, max |raw|) by integer
+ *                             atomics (zero it first; all-reduce it across ranks for a sharded batch)
+ *       img [B][3][P][P]; kernel [3][n][n] = the PSF zero-padded with its centre at (n/2, n/2) (psf2otf, Utils.py:127-158);
+ *       otf  b200cam_otf_bytes(n) out; spectrum b200cam_spectrum_bytes(n, B) out (row spectra of the images, for the backward)
+ *   b200cam_lens_normalise    y = |raw| / gmax                                                         (Lens.py:312)
+ *   b200cam_lens_sensor_dot   dot_ties[0] = sum(grad_y * y), dot_ties[1] = #{ |raw| == gmax } over this rank's batch
+ *   b200cam_lens_sensor_bwd   adjoint: dL/dconv = sign(raw) (grad_y / gmax - [|raw| == gmax] coef), coef = s / (gmax n) a device
+ *                             scalar from the (all-reduced) dot_ties; grad_kernel [3][n][n] summed over the batch (crop it to
+ *                             the PSF window), grad_img [B][3][P][P] or NULL
+ * workspace: b200cam_lens_sensor_workspace_bytes(P, B), shared by the four calls of a step. */
+size_t b200cam_lens_sensor_workspace_bytes(int P, int B);
+int b200cam_lens_sensor_fwd(const float* img, const float* kernel, float* raw, float* gmax, float* otf, float* spectrum, void* workspace,
+                            size_t workspace_bytes, int B, int P, void* stream);
+int b200cam_lens_normalise(const float* raw, const float* gmax, float* y, long long count, void* stream);
+int b200cam_lens_sensor_dot(const float* grad_y, const float* raw, const float* gmax, float* dot_ties, void* workspace, size_t workspace_bytes,
+                            int B, int P, void* stream);
+int b200cam_lens_sensor_bwd(const float* grad_y, const float* raw, const float* gmax, const float* coef, const float* otf, const float* spectrum,
+                            float* grad_kernel, float* grad_img, void* workspace, size_t workspace_bytes, int B, int P, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1336,6 +1336,46 @@ using namespace b200cam;
         default: return B200CAM_E_BAD_SIZE;       \
     }
 
+namespace b200cam {
+// ---- entry points for the other translation units of the library (lens_conv.cu) --------------------------------------
+const float2* lens_twiddle(int N) { return b200cam_supported(N) ? twiddle(N) : nullptr; }
+// OTF of a centred n x n kernel in the library's layout (rows + columns, sign twist, 1/N^2): psf2otf, Image_Caption/Camera/Utils.py:127-158
+int lens_otf(int N, const float* kern, float2* otf, cudaStream_t s) {
+    const float2* tw = lens_twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    switch (N) {
+        case 128: return otf_impl<128>(kern, otf, tw, 1.0f / (128.f * 128.f), s);
+        case 256: return otf_impl<256>(kern, otf, tw, 1.0f / (256.f * 256.f), s);
+        case 512: return otf_impl<512>(kern, otf, tw, 1.0f / (512.f * 512.f), s);
+        case 1024: return otf_impl<1024>(kern, otf, tw, 1.0f / (1024.f * 1024.f), s);
+        default: return B200CAM_E_BAD_SIZE;
+    }
+}
+template <int N>
+static int grad_kernel_tail_impl(const float2* partial, float2* stp, float* grad_kern, int nchunks, const float2* tw, cudaStream_t s) {
+    using T = Tile<N>;
+    launch_k(Pdl{}, k_cols_reduce_inv<N>, 3 * T::NC, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s,
+        ColsReduceInvParams{partial, stp, tw, nchunks, 1.0f / (static_cast<float>(N) * N), nullptr, nullptr, nullptr, nullptr, 0});
+    LAUNCH_CHECK();
+    launch_k(Pdl{}, k_rows_c2r<N>, dim3(N / T::ROWS, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s,
+        RowsC2RParams{stp, grad_kern, tw, nullptr, 1.0f, nullptr, nullptr, 0});
+    LAUNCH_CHECK();
+    return 0;
+}
+// chunk partials of sum_b G conj(X) -> dL/dkernel in the centred frame (the tail of conv_bwd_impl)
+int lens_grad_kernel_tail(int N, const float2* partial, float2* stp, float* grad_kern, int nchunks, cudaStream_t s) {
+    const float2* tw = lens_twiddle(N);
+    if (tw == nullptr) return B200CAM_E_NOT_INIT;
+    switch (N) {
+        case 128: return grad_kernel_tail_impl<128>(partial, stp, grad_kern, nchunks, tw, s);
+        case 256: return grad_kernel_tail_impl<256>(partial, stp, grad_kern, nchunks, tw, s);
+        case 512: return grad_kernel_tail_impl<512>(partial, stp, grad_kern, nchunks, tw, s);
+        case 1024: return grad_kernel_tail_impl<1024>(partial, stp, grad_kern, nchunks, tw, s);
+        default: return B200CAM_E_BAD_SIZE;
+    }
+}
+}  // namespace b200cam
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 extern "C" {

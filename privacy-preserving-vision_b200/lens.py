@@ -160,6 +160,63 @@ class GlobalMaxNormalise(torch.autograd.Function):
         return g / m - ties * (owner * s / (m * n)), None
 
 
+class LensSensor(torch.autograd.Function):
+    """sensor = |img_psf_conv(img, psf)| / max over the whole batch (Utils.py:251-297 + Lens.py:312) on the pruned kernels of
+    ``csrc/lens_conv.cu``: the zero-padded image and the padded convolution output are never materialised.  With a process
+    group the maximum is all-reduced (MAX) and, in the backward, sum(g*y) and the tie count (SUM): N ranks reproduce the
+    one-GPU result, the arg-max term landing on the rank(s) that hold the maximum."""
+
+    @staticmethod
+    def forward(ctx, img: torch.Tensor, kpad: torch.Tensor, plan: F.DevicePlan, group):
+        import torch.distributed as dist
+        dev, n = plan.device, plan.N
+        P = n // 2
+        x = F._as_f32(img.detach(), dev)
+        k = F._as_f32(kpad.detach(), dev).reshape(3, n, n)
+        B = x.shape[0]
+        lib = plan.lib
+        raw = torch.empty_like(x)
+        y = torch.empty_like(x)
+        gmax = torch.zeros(1, dtype=torch.float32, device=dev)
+        otf = torch.empty(plan.otf_floats, dtype=torch.float32, device=dev)
+        spectrum = torch.empty(lib.b200cam_spectrum_bytes(n, B) // 4, dtype=torch.float32, device=dev)
+        ws = torch.empty(lib.b200cam_lens_sensor_workspace_bytes(P, B), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(plan.index):
+            _lib.check(lib.b200cam_lens_sensor_fwd(_lib.ptr(x), _lib.ptr(k), _lib.ptr(raw), _lib.ptr(gmax), _lib.ptr(otf),
+                                                   _lib.ptr(spectrum), _lib.ptr(ws), ws.numel(), B, P, F._stream()))
+            if group is not None and dist.is_initialized():
+                dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+            _lib.check(lib.b200cam_lens_normalise(_lib.ptr(raw), _lib.ptr(gmax), _lib.ptr(y), raw.numel(), F._stream()))
+        ctx.plan, ctx.group, ctx.kshape = plan, group, kpad.shape
+        ctx.spectrum = spectrum if any(ctx.needs_input_grad[:2]) else None
+        ctx.save_for_backward(raw, gmax, otf)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        plan: F.DevicePlan = ctx.plan
+        raw, gmax, otf = ctx.saved_tensors
+        dev, n = plan.device, plan.N
+        P, B = n // 2, raw.shape[0]
+        lib = plan.lib
+        gy = F._as_f32(g, dev)
+        dot = torch.empty(2, dtype=torch.float32, device=dev)
+        grad_k = torch.empty(3, n, n, dtype=torch.float32, device=dev)
+        grad_img = torch.empty_like(raw) if ctx.needs_input_grad[0] else None
+        ws = torch.empty(lib.b200cam_lens_sensor_workspace_bytes(P, B), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(plan.index):
+            _lib.check(lib.b200cam_lens_sensor_dot(_lib.ptr(gy), _lib.ptr(raw), _lib.ptr(gmax), _lib.ptr(dot), _lib.ptr(ws), ws.numel(),
+                                                   B, P, F._stream()))
+            if ctx.group is not None and dist.is_initialized():
+                dist.all_reduce(dot, op=dist.ReduceOp.SUM, group=ctx.group)
+            coef = (dot[0] / (gmax[0] * dot[1].clamp(min=1.0))).reshape(1)      # s / (m n); torch.max splits exact ties evenly
+            _lib.check(lib.b200cam_lens_sensor_bwd(_lib.ptr(gy), _lib.ptr(raw), _lib.ptr(gmax), _lib.ptr(coef), _lib.ptr(otf),
+                                                   _lib.ptr(ctx.spectrum), _lib.ptr(grad_k), _lib.ptr(grad_img), _lib.ptr(ws),
+                                                   ws.numel(), B, P, F._stream()))
+        return grad_img, grad_k.reshape(ctx.kshape), None, None
+
+
 class LensPsf(torch.autograd.Function):
     """height map (R,R) [+ tolerance noise] -> normalised PSF (1,P,P,3) and the energy loss, Lens.py:176-274, on the
     b200cam kernels of ``csrc/lens_psf.cu`` (phase plate, pruned mixed-radix Fresnel propagation, intensity, area
@@ -410,7 +467,8 @@ class OpticsZernike(nn.Module):
         n = 2 * P
         pad = (n - P) / 2
         pt, pb = int(np.ceil(pad)), int(np.floor(pad))
-        x = TF.pad(img.to(torch.float32), [pt, pb, pt, pb])
+        fused = P in (64, 128, 256, 512)
+        x = None if fused else TF.pad(img.to(torch.float32), [pt, pb, pt, pb])
         # psf2otf (Utils.py:127-158): pad so that the PSF centre lands on n/2, the kernel's "centred frame"
         if (n - P) % 2 != 0:
             kt, kb = int(np.ceil(pad)), int(np.floor(pad))
@@ -418,8 +476,11 @@ class OpticsZernike(nn.Module):
             kt, kb = int(pad) + 1, int(pad) - 1
         k = TF.pad(psf[0].permute(2, 0, 1).to(torch.float32), [kt, kb, kt, kb])          # (3, n, n)
         plan = self._plan(img.device, n)
+        if fused:      # padding, |.|, crop, resize and the batch-global max inside the transform kernels (csrc/lens_conv.cu)
+            return LensSensor.apply(img, k, plan, self._process_group)
         # |.|, the [pt+1 : n-pb] crop to (P-1)^2 and the nearest resize back to P (out[i] = crop[max(i-1,0)]) in one pass
-        return CropAbsResize.apply(CircConv.apply(x, k, plan), P, pt + 1, plan)
+        out = CropAbsResize.apply(CircConv.apply(x, k, plan), P, pt + 1, plan)
+        return GlobalMaxNormalise.apply(out, self._process_group)
 
     # ------------------------------------------------------------------ reference API
     def forward(self, input_img, new_zernike=None, prueba=None, psf_lab=None, enfoco=None):
@@ -448,8 +509,7 @@ class OpticsZernike(nn.Module):
 
         sensor = self._sensor(input_img, psf)
         np.random.uniform(low=0.001, high=0.02)                     # noise_sigma is drawn and discarded (Lens.py:295)
-        sensor = GlobalMaxNormalise.apply(sensor, self._process_group)
-        return sensor, psf, coeffs, loss
+        return sensor, psf, coeffs, loss                            # (the batch-global max of Lens.py:312 is inside _sensor)
 
     def load_pretrained_from_numpy(self, path):
         weights = np.load(path)['optics_trained_weights']

@@ -157,3 +157,37 @@ def test_psf_kernels_match_oracle_with_tolerance_noise(wave, patch, prueba):
     if ref_loss is not None:
         assert abs(float(loss) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
     assert abs(float(grad) - float(cz.grad[3])) <= 1e-3 * abs(float(cz.grad[3]))
+
+
+@pytest.mark.parametrize("P,B", [(64, 3), (128, 2), (256, 5)])
+def test_fused_padded_sensor_matches_oracle(P, B):
+    """csrc/lens_conv.cu (zero padding, |.|, crop, nearest resize and batch-global max inside the transform kernels) against
+    oracle.lens_oracle.sensor_image + the global max (Utils.py:251-297, Lens.py:312): sensor, dL/dpsf and dL/dimg.  One image
+    carries a spike placed so that the maximum lands in crop row 0 - the row the nearest resize duplicates, i.e. an exact tie."""
+    from b200cam.lens import LensSensor
+    from b200cam import functional as F
+    import torch.nn.functional as TF
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(21 + P)
+    img = torch.rand(B, 3, P, P, generator=g)
+    psf = torch.rand(1, P, P, 3, generator=g) ** 8
+    psf = psf / psf.sum(dim=[1, 2], keepdim=True)
+    psf[0, P // 2, P // 2, 1] += 0.5                         # a strong centre tap: the spike below maps (almost) onto itself
+    img[1, 1, 0, 7] += 40.0                                  # the tap sits one past the centre: conv row pt+1 = crop row 0 -> output rows 0 and 1
+    w = torch.rand(B, 3, P, P, generator=g)
+
+    xo, po = img.clone().requires_grad_(True), psf.clone().requires_grad_(True)
+    raw = lo.sensor_image(xo, po)
+    ref = raw / raw.max()
+    (ref * w).sum().backward()
+
+    n = 2 * P
+    xg, pg = img.to(dev).requires_grad_(True), psf.to(dev).requires_grad_(True)
+    k = TF.pad(pg[0].permute(2, 0, 1), [P // 2 + 1, P // 2 - 1, P // 2 + 1, P // 2 - 1])
+    out = LensSensor.apply(xg, k, F.DevicePlan(n, dev, tables=False), None)
+    (out * w.to(dev)).sum().backward()
+    assert float(out.max()) == 1.0
+    assert int((out == 1.0).sum()) >= 2                      # the duplicated row: an exact tie
+    assert rel_l2(out, ref) <= 1e-4
+    assert rel_l2(pg.grad, po.grad) <= 1e-3
+    assert rel_l2(xg.grad, xo.grad) <= 1e-3
