@@ -517,6 +517,15 @@ __global__ void __launch_bounds__(EW_THREADS) k_zernike_bwd(ZernikeBwdParams p) 
     DeviceExec ex;
     zernike_bwd_body(ex, p, red);
 }
+__global__ void __launch_bounds__(EW_THREADS) k_zernike_bwd_fin(const float* partial, float* gcoef, int T, int splits) {
+    pdl_gate();
+    const int j = blockIdx.x * EW_THREADS + threadIdx.x;
+    if (j < T) {
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += partial[j * splits + s];
+        gcoef[j] = acc;
+    }
+}
 
 __global__ void __launch_bounds__(EW_THREADS) k_crop_abs_resize_fwd(CropAbsResizeParams p) {
     pdl_gate();
@@ -555,9 +564,11 @@ struct DeviceState {
     int conv_slots[11] = {0}, accum_slots[11] = {0};     // resident CTAs of the persistent column kernels
     cudaEvent_t chain_ev = nullptr;                      // orders a caller stream behind the first PSF-chain kernel
     int r2c_fit[11] = {0}, c2r_fit[11] = {0};            // resident CTAs per SM of the persistent row kernels
+    float* scratch = nullptr;                            // SCRATCH_FLOATS floats: slice partials of the Zernike adjoint
     int prow_fit = 0, pconv_g3 = 0, pacc_g3 = 0;         // plane kernels (N = 256): resident CTAs per SM / co-resident cluster triples
     unsigned* err_host = nullptr; unsigned* err_dev = nullptr;   // device error word (mapped pinned host memory)
 };
+constexpr int SCRATCH_FLOATS = 16384;
 static DeviceState g_state[MAX_DEV];
 static std::mutex g_mutex;
 
@@ -1431,6 +1442,7 @@ int b200cam_init(int N) {
         g_state[dev].err_host = h;
         g_state[dev].err_dev = d;
     }
+    if (g_state[dev].scratch == nullptr) CK(cudaMalloc(&g_state[dev].scratch, sizeof(float) * SCRATCH_FLOATS));
     if (g_state[dev].bar == nullptr) {
         unsigned* bar = nullptr;
         CK(cudaMalloc(&bar, 4 * sizeof(unsigned)));
@@ -1588,10 +1600,24 @@ int b200cam_zernike_bwd(const float* grad_h, const float* Z, float* grad_coef, i
     if (!grad_h || !Z || !grad_coef) return B200CAM_E_NULL;
     if (!aligned16(Z) || !aligned16(grad_h)) return B200CAM_E_ALIGN;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    launch_k(k_zernike_bwd, T, EW_THREADS, 0, s, ZernikeBwdParams{reinterpret_cast<const float4*>(grad_h),
-                                                            reinterpret_cast<const float4*>(Z), grad_coef,
-                                                            static_cast<int>(NN / 4)});
+    // few terms: slice every plane over enough CTAs to fill the device (partials in the per-device scratch, b200cam_init)
+    const DeviceState* st = cur_state();
+    int splits = 1;
+    if (T < 2 * 148 && st != nullptr && st->scratch != nullptr) {
+        splits = (4 * 148 + T - 1) / T;
+        const int most = static_cast<int>(NN / 4 / (8 * EW_THREADS));
+        if (splits > most) splits = most;
+        if (splits > 64) splits = 64;
+        if (splits < 1 || T * splits > SCRATCH_FLOATS) splits = 1;
+    }
+    launch_k(k_zernike_bwd, dim3(T, splits), EW_THREADS, 0, s, ZernikeBwdParams{reinterpret_cast<const float4*>(grad_h),
+                                                            reinterpret_cast<const float4*>(Z), splits > 1 ? st->scratch : grad_coef,
+                                                            static_cast<int>(NN / 4), splits});
     LAUNCH_CHECK();
+    if (splits > 1) {
+        launch_k(k_zernike_bwd_fin, (T + EW_THREADS - 1) / EW_THREADS, EW_THREADS, 0, s, st->scratch, grad_coef, T, splits);
+        LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -1836,22 +1836,28 @@ B200_HD void zernike_fwd_body(Exec& ex, const ZernikeFwdParams& p, int* flag) {
     }
 }
 
-// Z2  zernike_bwd : gcoef_j = sum_p Z_j[p] * gh[p].  grid T (one term per CTA), block EW_THREADS; fixed-order tree.
+// Z2  zernike_bwd : gcoef_j = sum_p Z_j[p] * gh[p].  grid (T, splits), block EW_THREADS; fixed-order tree.
+//     splits > 1 (few terms, e.g. the single trainable defocus term of the Image_Caption camera): CTA (j, s) reduces the
+//     s-th slice of the plane into partial[j * splits + s]; k_zernike_bwd_fin adds the slices in order.
 struct ZernikeBwdParams {
     const float4* gh;      // [NN4]
     const float4* Z;       // [T][NN4]
-    float* gcoef;          // [T]
+    float* gcoef;          // [T]  (splits == 1) or the partials [T][splits]
     int NN4;
+    int splits = 1;
 };
 
 template <class Exec>
 B200_HD void zernike_bwd_body(Exec& ex, const ZernikeBwdParams& p, float* red) {
     const int j = ex.bx();
+    const int slice = (p.NN4 + p.splits - 1) / p.splits;
+    const int q0 = ex.by() * slice;
+    const int q1 = q0 + slice < p.NN4 ? q0 + slice : p.NN4;
     ex.phase([&](int tid) {
         const float4* z = p.Z + static_cast<size_t>(j) * p.NN4;
         float acc = 0.f;
-        int q = tid;
-        for (; q + 7 * EW_THREADS < p.NN4; q += 8 * EW_THREADS) {
+        int q = q0 + tid;
+        for (; q + 7 * EW_THREADS < q1; q += 8 * EW_THREADS) {
             float4 a[8], g[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) a[i] = ld_ro(z + q + i * EW_THREADS);
@@ -1860,7 +1866,7 @@ B200_HD void zernike_bwd_body(Exec& ex, const ZernikeBwdParams& p, float* red) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc += (a[i].x * g[i].x + a[i].y * g[i].y) + (a[i].z * g[i].z + a[i].w * g[i].w);
         }
-        for (; q < p.NN4; q += EW_THREADS) {
+        for (; q < q1; q += EW_THREADS) {
             const float4 a = ld_ro(z + q), g = ld_ro(p.gh + q);
             acc += (a.x * g.x + a.y * g.y) + (a.z * g.z + a.w * g.w);
         }
@@ -1872,7 +1878,7 @@ B200_HD void zernike_bwd_body(Exec& ex, const ZernikeBwdParams& p, float* red) {
         });
     }
     ex.phase([&](int tid) {
-        if (tid == 0) p.gcoef[j] = red[0];
+        if (tid == 0) p.gcoef[j * p.splits + ex.by()] = red[0];
     });
 }
 

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_lrows_r2c(Load load
 
 // ---- KB: per spectral column FFT_v -> x OTF (or conj) -> IFFT_v over the live rows [PT, PT + P).  grid (colgroups, nchunks) ----
 template <int N>
-__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_lcols_conv(const float2* in, float2* out, const float2* __restrict__ otf,
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 512 ? 2 : 1) k_lcols_conv(const float2* in, float2* out, const float2* __restrict__ otf,
                                                                       const float2* __restrict__ tw, int B, int nchunks, int conj_otf) {
     using P = Plan<N>;
     using T = Tile<N>;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(RowsR2CSmem<N>::THREADS) k_lrows_c2r(const flo
 
 // ---- KD: sum over the chunk's images of G * conj(X) per spectral column (live rows only).  grid (colgroups, nchunks) --------
 template <int N>
-__global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_lcols_accum(const float2* __restrict__ stx, const float2* __restrict__ stg,
+__global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 512 ? 2 : 1) k_lcols_accum(const float2* __restrict__ stx, const float2* __restrict__ stg,
                                                                        float2* __restrict__ partial, const float2* __restrict__ tw, int B,
                                                                        int nchunks) {
     using P = Plan<N>;
@@ -277,13 +277,19 @@ __global__ void __launch_bounds__(ColsSmem<N>::THREADS) k_lcols_accum(const floa
     for (int b = b0; b < b1; ++b) {
         if (live && a < P::R2) {
             const size_t off = (static_cast<size_t>(b) * TOTAL + cu) * N;
-            float2 vx[P::R1], vg[P::R1];
+            // the two operands one after the other: the load phase then holds R1 values, not 2 R1 (two CTAs per SM)
+            {
+                float2 v[P::R1];
 #pragma unroll
-            for (int i = 0; i < P::R1; ++i) vx[i] = (i >= I0 && i < I1) ? __ldg(stx + off + P::R2 * i + a) : make_float2(0.f, 0.f);
+                for (int i = 0; i < P::R1; ++i) v[i] = (i >= I0 && i < I1) ? __ldg(stx + off + P::R2 * i + a) : make_float2(0.f, 0.f);
+                P::stepA(v, a, Ex + jc * P::E_SIZE, tw);
+            }
+            {
+                float2 v[P::R1];
 #pragma unroll
-            for (int i = 0; i < P::R1; ++i) vg[i] = (i >= I0 && i < I1) ? __ldg(stg + off + P::R2 * i + a) : make_float2(0.f, 0.f);
-            P::stepA(vx, a, Ex + jc * P::E_SIZE, tw);
-            P::stepA(vg, a, Eg + jc * P::E_SIZE, tw);
+                for (int i = 0; i < P::R1; ++i) v[i] = (i >= I0 && i < I1) ? __ldg(stg + off + P::R2 * i + a) : make_float2(0.f, 0.f);
+                P::stepA(v, a, Eg + jc * P::E_SIZE, tw);
+            }
         }
         __syncthreads();
         if (live && a < P::R1) {
@@ -350,14 +356,28 @@ __global__ void __launch_bounds__(EWT) k_ldot(const float4* __restrict__ g, cons
         part[2 * blockIdx.x + 1] = b;
     }
 }
-__global__ void k_ldot_final(const double* __restrict__ part, int nblocks, float* __restrict__ out) {      // one thread: nblocks <= 1184
+__global__ void __launch_bounds__(EWT) k_ldot_final(const double* __restrict__ part, int nblocks, float* __restrict__ out) {   // one CTA, fixed order
+    __shared__ double ra[EWT];
+    __shared__ double rb[EWT];
     double a = 0.0, b = 0.0;
-    for (int i = 0; i < nblocks; ++i) {
+    for (int i = threadIdx.x; i < nblocks; i += EWT) {
         a += part[2 * i];
         b += part[2 * i + 1];
     }
-    out[0] = static_cast<float>(a);
-    out[1] = static_cast<float>(b);
+    ra[threadIdx.x] = a;
+    rb[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = EWT / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            ra[threadIdx.x] += ra[threadIdx.x + o];
+            rb[threadIdx.x] += rb[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = static_cast<float>(ra[0]);
+        out[1] = static_cast<float>(rb[0]);
+    }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
@@ -518,7 +538,7 @@ int b200cam_lens_sensor_dot(const float* grad_y, const float* raw, const float* 
     const int grid = ew_grid(n4);
     k_ldot<<<grid, EWT, 0, s>>>(reinterpret_cast<const float4*>(grad_y), reinterpret_cast<const float4*>(raw), gmax, n4, ws.dpart);
     LLAUNCH();
-    k_ldot_final<<<1, 1, 0, s>>>(ws.dpart, grid, dot_ties);
+    k_ldot_final<<<1, EWT, 0, s>>>(ws.dpart, grid, dot_ties);
     LLAUNCH();
     return 0;
 }

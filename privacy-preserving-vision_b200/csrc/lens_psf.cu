@@ -117,18 +117,20 @@ __device__ __forceinline__ void stage(const float2* __restrict__ in, float2* __r
                                       int lines, int pitch) {
     const int nb = n / R;
     const int twstep = n / (Ns * R);
-    for (int w = threadIdx.x; w < lines * nb; w += blockDim.x) {
-        const int line = w / nb, j = w - line * nb;
-        const float2* src = in + line * pitch;
-        float2* dst = out + line * pitch;
-        const int k = j % Ns;
+    const float inv_ns = 1.0f / static_cast<float>(Ns);
+    const int per = blockDim.x / lines;                       // threads per line (lines divides the block size)
+    const int line = threadIdx.x / per, t0 = threadIdx.x - line * per;
+    const float2* src = in + line * pitch;
+    float2* dst = out + line * pitch;
+    for (int j = t0; j < nb; j += per) {
+        const int k = j - __float2int_rz((static_cast<float>(j) + 0.5f) * inv_ns) * Ns;      // j % Ns (j < 2^20: exact)
         float2 v[R];
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = src[j + t * nb];
         if (Ns > 1) {
 #pragma unroll
             for (int t = 1; t < R; ++t) {
-                const float2 wv = __ldg(tw + t * k * twstep);
+                const float2 wv = tw[t * k * twstep];
                 v[t] = DIR < 0 ? cmul(v[t], wv) : cmulc(v[t], wv);
             }
         }
@@ -155,7 +157,7 @@ __device__ void stage_generic(int r, const float2* __restrict__ in, float2* __re
         for (int t = 0; t < r; ++t) {
             float2 x = src[j + t * nb];
             if (Ns > 1 && t > 0) {
-                const float2 wv = __ldg(tw + t * k * twstep);
+                const float2 wv = tw[t * k * twstep];
                 x = DIR < 0 ? cmul(x, wv) : cmulc(x, wv);
             }
             v[t] = x;
@@ -164,7 +166,7 @@ __device__ void stage_generic(int r, const float2* __restrict__ in, float2* __re
         for (int a = 0; a < r; ++a) {
             float2 acc = v[0];
             for (int b = 1; b < r; ++b) {
-                const float2 wv = __ldg(tw + ((a * b) % r) * rstep);
+                const float2 wv = tw[((a * b) % r) * rstep];
                 const float2 p = DIR < 0 ? cmul(v[b], wv) : cmulc(v[b], wv);
                 acc.x += p.x;
                 acc.y += p.y;
@@ -210,11 +212,14 @@ struct Geom {
     FftPlan plan;
     double delta[3];   // 2 pi / lambda * (n_lambda - 1)   (Utils.py:192-197)
 };
-__device__ __forceinline__ int src_index(const Geom& g, int k) { return static_cast<int>((static_cast<long long>(k) * g.R) / (g.up * g.P)); }
+// 32-bit arithmetic: k < up * P <= 10 * R and R <= 4096 (make_geom), so k * R < 2^31
+__device__ __forceinline__ int src_index(const Geom& g, int k) {
+    return static_cast<int>((static_cast<unsigned>(k) * static_cast<unsigned>(g.R)) / static_cast<unsigned>(g.up * g.P));
+}
 // first k of the up-sampled axis that maps to source index y:  ceil(y * U / R)
 __device__ __forceinline__ int first_k(const Geom& g, int y) {
-    const long long U = static_cast<long long>(g.up) * g.P;
-    return static_cast<int>((static_cast<long long>(y) * U + g.R - 1) / g.R);
+    const unsigned U = static_cast<unsigned>(g.up * g.P);
+    return static_cast<int>((static_cast<unsigned>(y) * U + static_cast<unsigned>(g.R) - 1u) / static_cast<unsigned>(g.R));
 }
 
 // ---- forward ---------------------------------------------------------------------------------------------------
@@ -230,6 +235,8 @@ struct RowsFwdParams {
 __global__ void __launch_bounds__(THREADS) k_lens_rows_fwd(Geom g, RowsFwdParams p) {
     float2* a = reinterpret_cast<float2*>(lens_smem);
     float2* b = a + ROW_LINES * g.n;
+    float2* stw = b + ROW_LINES * g.n;                               // the twiddle table, in shared memory (random 8-byte look-ups)
+    for (int i = threadIdx.x; i < g.n; i += blockDim.x) stw[i] = __ldg(p.tw + i);
     const int lam = blockIdx.y;
     const int y0 = blockIdx.x * ROW_LINES;
     for (int i = threadIdx.x; i < ROW_LINES * g.n; i += blockDim.x) a[i] = make_float2(0.f, 0.f);
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(THREADS) k_lens_rows_fwd(Geom g, RowsFwdParams
         }
     }
     __syncthreads();
-    const float2* res = fft_lines<-1>(a, b, p.tw, g.plan, ROW_LINES, g.n);
+    const float2* res = fft_lines<-1>(a, b, stw, g.plan, ROW_LINES, g.n);
     for (int i = threadIdx.x; i < ROW_LINES * g.n; i += blockDim.x) {
         const int l = i / g.n, u = i - l * g.n;
         const int y = y0 + l;
@@ -269,6 +276,8 @@ struct ColsParams {
 __global__ void __launch_bounds__(THREADS) k_lens_cols(Geom g, ColsParams p) {
     float2* a = reinterpret_cast<float2*>(lens_smem);
     float2* b = a + COL_LINES * g.n;
+    float2* stw = b + COL_LINES * g.n;                               // the twiddle table, in shared memory (random 8-byte look-ups)
+    for (int i = threadIdx.x; i < g.n; i += blockDim.x) stw[i] = __ldg(p.tw + i);
     const int lam = blockIdx.y;
     const int u0 = blockIdx.x * COL_LINES;
     for (int i = threadIdx.x; i < COL_LINES * g.n; i += blockDim.x) a[i] = make_float2(0.f, 0.f);
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(THREADS) k_lens_cols(Geom g, ColsParams p) {
         if (u0 + c < g.n) a[c * g.n + g.pad + y] = p.W[(static_cast<size_t>(lam) * g.R + y) * g.n + u0 + c];
     }
     __syncthreads();
-    float2* res = fft_lines<-1>(a, b, p.tw, g.plan, COL_LINES, g.n);
+    float2* res = fft_lines<-1>(a, b, stw, g.plan, COL_LINES, g.n);
     float2* other = res == a ? b : a;
     for (int i = threadIdx.x; i < COL_LINES * g.n; i += blockDim.x) {
         const int c = i / g.n, v = i - c * g.n;
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(THREADS) k_lens_cols(Geom g, ColsParams p) {
         }
     }
     __syncthreads();
-    const float2* out = fft_lines<+1>(res, other, p.tw, g.plan, COL_LINES, g.n);
+    const float2* out = fft_lines<+1>(res, other, stw, g.plan, COL_LINES, g.n);
     for (int i = threadIdx.x; i < COL_LINES * g.R; i += blockDim.x) {
         const int y = i / COL_LINES, c = i - y * COL_LINES;
         if (u0 + c < g.n) p.W[(static_cast<size_t>(lam) * g.R + y) * g.n + u0 + c] = out[c * g.n + g.pad + y];
@@ -310,6 +319,8 @@ struct RowsInvParams {
 __global__ void __launch_bounds__(THREADS) k_lens_rows_inv(Geom g, RowsInvParams p) {
     float2* a = reinterpret_cast<float2*>(lens_smem);
     float2* b = a + ROW_LINES * g.n;
+    float2* stw = b + ROW_LINES * g.n;                               // the twiddle table, in shared memory (random 8-byte look-ups)
+    for (int i = threadIdx.x; i < g.n; i += blockDim.x) stw[i] = __ldg(p.tw + i);
     const int lam = blockIdx.y;
     const int y0 = blockIdx.x * ROW_LINES;
     for (int i = threadIdx.x; i < ROW_LINES * g.n; i += blockDim.x) {
@@ -318,7 +329,7 @@ __global__ void __launch_bounds__(THREADS) k_lens_rows_inv(Geom g, RowsInvParams
         a[i] = y < g.R ? p.W[(static_cast<size_t>(lam) * g.R + y) * g.n + u] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    float2* res = fft_lines<+1>(a, b, p.tw, g.plan, ROW_LINES, g.n);
+    float2* res = fft_lines<+1>(a, b, stw, g.plan, ROW_LINES, g.n);
     float* inten = reinterpret_cast<float*>(res == a ? b : a);      // [ROW_LINES][R]
     const float sc = 1.0f / (static_cast<float>(g.n) * static_cast<float>(g.n));
     for (int i = threadIdx.x; i < ROW_LINES * g.R; i += blockDim.x) {
@@ -484,6 +495,8 @@ __global__ void __launch_bounds__(THREADS) k_lens_rows_bwd(Geom g, RowsBwdParams
     __shared__ float red[32];
     float2* a = reinterpret_cast<float2*>(lens_smem);
     float2* b = a + ROW_LINES * g.n;
+    float2* stw = b + ROW_LINES * g.n;                               // the twiddle table, in shared memory (random 8-byte look-ups)
+    for (int i = threadIdx.x; i < g.n; i += blockDim.x) stw[i] = __ldg(p.tw + i);
     const int lam = blockIdx.y;
     const int y0 = blockIdx.x * ROW_LINES;
     float part = 0.f;
@@ -509,7 +522,7 @@ __global__ void __launch_bounds__(THREADS) k_lens_rows_bwd(Geom g, RowsBwdParams
         }
     }
     __syncthreads();
-    const float2* res = fft_lines<-1>(a, b, p.tw, g.plan, ROW_LINES, g.n);
+    const float2* res = fft_lines<-1>(a, b, stw, g.plan, ROW_LINES, g.n);
     for (int i = threadIdx.x; i < ROW_LINES * g.n; i += blockDim.x) {
         const int l = i / g.n, u = i - l * g.n;
         const int y = y0 + l;
@@ -528,7 +541,9 @@ struct HGradParams {
 __global__ void __launch_bounds__(THREADS) k_lens_hgrad(Geom g, HGradParams p) {
     float2* a = reinterpret_cast<float2*>(lens_smem);
     float2* b = a + ROW_LINES * g.n;
-    double* acc = reinterpret_cast<double*>(b + ROW_LINES * g.n);      // [ROW_LINES][R]
+    float2* stw = b + ROW_LINES * g.n;                               // the twiddle table, in shared memory (random 8-byte look-ups)
+    for (int i = threadIdx.x; i < g.n; i += blockDim.x) stw[i] = __ldg(p.tw + i);
+    double* acc = reinterpret_cast<double*>(stw + g.n);      // [ROW_LINES][R]
     const int y0 = blockIdx.x * ROW_LINES;
     const double sc = 1.0 / (static_cast<double>(g.n) * static_cast<double>(g.n));
     for (int i = threadIdx.x; i < ROW_LINES * g.R; i += blockDim.x) acc[i] = 0.0;
@@ -540,7 +555,7 @@ __global__ void __launch_bounds__(THREADS) k_lens_hgrad(Geom g, HGradParams p) {
             a[i] = y < g.R ? p.W[(static_cast<size_t>(lam) * g.R + y) * g.n + u] : make_float2(0.f, 0.f);
         }
         __syncthreads();
-        const float2* res = fft_lines<+1>(a, b, p.tw, g.plan, ROW_LINES, g.n);
+        const float2* res = fft_lines<+1>(a, b, stw, g.plan, ROW_LINES, g.n);
         for (int i = threadIdx.x; i < ROW_LINES * g.R; i += blockDim.x) {
             const int l = i / g.R, x = i - l * g.R;
             const int y = y0 + l;
@@ -570,7 +585,7 @@ static int pool_factor(int R, int P) {      // area_downsampling_tf, Utils.py:21
 }
 
 static bool make_geom(int R, int P, const double* delta, Geom* g) {
-    if (R < 8 || R % 4 != 0 || P < 1 || P > R) return false;
+    if (R < 8 || R > 4096 || R % 4 != 0 || P < 1 || P > R) return false;
     g->R = R;
     g->pad = R / 4;
     g->n = R + 2 * g->pad;
@@ -608,9 +623,9 @@ struct Ws {
     }
 };
 
-static size_t rows_smem(const Geom& g) { return sizeof(float2) * 2 * ROW_LINES * g.n; }
+static size_t rows_smem(const Geom& g) { return sizeof(float2) * (2 * ROW_LINES + 1) * g.n; }
 static size_t hgrad_smem(const Geom& g) { return rows_smem(g) + sizeof(double) * ROW_LINES * g.R; }
-static size_t cols_smem(const Geom& g) { return sizeof(float2) * 2 * COL_LINES * g.n; }
+static size_t cols_smem(const Geom& g) { return sizeof(float2) * (2 * COL_LINES + 1) * g.n; }
 
 template <class K>
 static cudaError_t optin(K kernel, size_t bytes) {

@@ -338,6 +338,31 @@ class OpticsZernike(nn.Module):
             return F.zernike_project(coeffs, vol, self._plan(vol.device, 256))      # any plan of that device will do
         return torch.sum(coeffs * vol, dim=0)
 
+    def _height_map(self, coeffs: torch.Tensor) -> torch.Tensor:
+        """h = sum_j coef_j Z_j for the module's own coefficient vector.  As shipped only the defocus term (#3) is trainable
+        (Lens.py:90-96): the partial sum of the T-1 frozen terms is cached - keyed on the frozen parameters' version counters,
+        so an in-place update or load_state_dict refreshes it - and a step reads one basis plane each way instead of the
+        whole T x R x R volume (1.12 GB at 350 x 896^2)."""
+        vol = self.zernike_volume
+        frozen_ok = (not self.zernike_coeffs_no_train.requires_grad and not self.zernike_coeffs_no_train2.requires_grad
+                     and coeffs.is_cuda and vol.is_cuda and vol.shape[0] > 4)
+        if not frozen_ok:
+            return self._project(coeffs)
+        key = (self.zernike_coeffs_no_train._version, self.zernike_coeffs_no_train2._version,
+               self.zernike_coeffs_no_train.data_ptr(), self.zernike_coeffs_no_train2.data_ptr(), vol.data_ptr())
+        if getattr(self, "_frozen_key", None) != key:
+            with torch.no_grad():
+                c = coeffs.detach().clone()
+                c[3] = 0
+                self._frozen_sum = self._project(c)
+            self._frozen_key = key
+        return self._frozen_sum + self._project_one(self.zernike_coeffs_train.reshape(1, 1, 1), vol[3:4])
+
+    def _project_one(self, coef: torch.Tensor, plane: torch.Tensor) -> torch.Tensor:
+        if plane.dtype == torch.float32 and plane.is_contiguous() and plane[0].numel() % 4 == 0:
+            return F.zernike_project(coef, plane, self._plan(plane.device, 256))
+        return torch.sum(coef * plane, dim=0)
+
     def get_Heith_Map(self):
         coeffs = torch.cat((self.zernike_coeffs_no_train, self.zernike_coeffs_train.unsqueeze(0),
                             self.zernike_coeffs_no_train2), 0)
@@ -494,7 +519,9 @@ class OpticsZernike(nn.Module):
             coeffs = coeffs.clone()
             coeffs[:] = 0
             coeffs[3] = -22
-        height_map = self._project(coeffs).unsqueeze(0).unsqueeze(-1)
+            height_map = self._project(coeffs).unsqueeze(0).unsqueeze(-1)
+        else:
+            height_map = self._height_map(coeffs).unsqueeze(0).unsqueeze(-1)
         flags = (1 if prueba in ("1", "3") else 0) | (2 if prueba in ("2", "3") else 0)
         fused = self._psf_kernels(height_map, flags) if height_map.is_cuda else None
         if fused is not None:
