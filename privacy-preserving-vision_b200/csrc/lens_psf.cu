@@ -28,7 +28,8 @@ namespace lens {
 constexpr int MAX_STAGES = 12;
 constexpr int MAX_GENERIC = 31;
 constexpr int ROW_LINES = 2;       // image rows per CTA in the row passes
-constexpr int COL_LINES = 4;       // spectral columns per CTA in the column pass (32-byte segments per row)
+constexpr int COL_LINES = 2;       // spectral columns per CTA in the column pass (16-byte segments per row; 4 CTAs per SM)
+constexpr int COL_PAD = 16 / COL_LINES;   // line pitch n + COL_PAD: the transposing loads / stores of a half warp hit 32 distinct banks
 constexpr int THREADS = 256;
 
 struct FftPlan {
@@ -275,19 +276,20 @@ struct ColsParams {
 };
 __global__ void __launch_bounds__(THREADS) k_lens_cols(Geom g, ColsParams p) {
     float2* a = reinterpret_cast<float2*>(lens_smem);
-    float2* b = a + COL_LINES * g.n;
-    float2* stw = b + COL_LINES * g.n;                               // the twiddle table, in shared memory (random 8-byte look-ups)
+    const int pitch = g.n + COL_PAD;
+    float2* b = a + COL_LINES * pitch;
+    float2* stw = b + COL_LINES * pitch;                               // the twiddle table, in shared memory (random 8-byte look-ups)
     for (int i = threadIdx.x; i < g.n; i += blockDim.x) stw[i] = __ldg(p.tw + i);
     const int lam = blockIdx.y;
     const int u0 = blockIdx.x * COL_LINES;
-    for (int i = threadIdx.x; i < COL_LINES * g.n; i += blockDim.x) a[i] = make_float2(0.f, 0.f);
+    for (int i = threadIdx.x; i < COL_LINES * pitch; i += blockDim.x) a[i] = make_float2(0.f, 0.f);
     __syncthreads();
     for (int i = threadIdx.x; i < COL_LINES * g.R; i += blockDim.x) {
         const int y = i / COL_LINES, c = i - y * COL_LINES;
-        if (u0 + c < g.n) a[c * g.n + g.pad + y] = p.W[(static_cast<size_t>(lam) * g.R + y) * g.n + u0 + c];
+        if (u0 + c < g.n) a[c * pitch + g.pad + y] = p.W[(static_cast<size_t>(lam) * g.R + y) * g.n + u0 + c];
     }
     __syncthreads();
-    float2* res = fft_lines<-1>(a, b, stw, g.plan, COL_LINES, g.n);
+    float2* res = fft_lines<-1>(a, b, stw, g.plan, COL_LINES, pitch);
     float2* other = res == a ? b : a;
     for (int i = threadIdx.x; i < COL_LINES * g.n; i += blockDim.x) {
         const int c = i / g.n, v = i - c * g.n;
@@ -297,15 +299,15 @@ __global__ void __launch_bounds__(THREADS) k_lens_cols(Geom g, ColsParams p) {
             const float hr = static_cast<float>(hu.x * hv.x - hu.y * hv.y);
             float hi = static_cast<float>(hu.x * hv.y + hu.y * hv.x);
             if (p.conj_h) hi = -hi;
-            const float2 z = res[i];
-            res[i] = make_float2(z.x * hr - z.y * hi, z.x * hi + z.y * hr);
+            const float2 z = res[c * pitch + v];
+            res[c * pitch + v] = make_float2(z.x * hr - z.y * hi, z.x * hi + z.y * hr);
         }
     }
     __syncthreads();
-    const float2* out = fft_lines<+1>(res, other, stw, g.plan, COL_LINES, g.n);
+    const float2* out = fft_lines<+1>(res, other, stw, g.plan, COL_LINES, pitch);
     for (int i = threadIdx.x; i < COL_LINES * g.R; i += blockDim.x) {
         const int y = i / COL_LINES, c = i - y * COL_LINES;
-        if (u0 + c < g.n) p.W[(static_cast<size_t>(lam) * g.R + y) * g.n + u0 + c] = out[c * g.n + g.pad + y];
+        if (u0 + c < g.n) p.W[(static_cast<size_t>(lam) * g.R + y) * g.n + u0 + c] = out[c * pitch + g.pad + y];
     }
 }
 
@@ -625,7 +627,7 @@ struct Ws {
 
 static size_t rows_smem(const Geom& g) { return sizeof(float2) * (2 * ROW_LINES + 1) * g.n; }
 static size_t hgrad_smem(const Geom& g) { return rows_smem(g) + sizeof(double) * ROW_LINES * g.R; }
-static size_t cols_smem(const Geom& g) { return sizeof(float2) * (2 * COL_LINES + 1) * g.n; }
+static size_t cols_smem(const Geom& g) { return sizeof(float2) * (2 * COL_LINES * (g.n + COL_PAD) + g.n); }
 
 template <class K>
 static cudaError_t optin(K kernel, size_t bytes) {
