@@ -22,8 +22,10 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 // completed and its writes are visible (no-ops for a kernel launched without the attribute)
 __constant__ int c_pdl_trigger = 0;      // 1: signal the dependents at kernel entry (B200CAM_PDL_TRIGGER=1); 0: at completion
 __device__ __forceinline__ void pdl_gate() {
+#if defined(B200CAM_PDL_BUILD)
     if (c_pdl_trigger) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
+#endif
 }
 #define SMEM2 reinterpret_cast<float2*>(smem_raw)
 
@@ -42,12 +44,12 @@ __global__ void __launch_bounds__(RowsStreamSmem<N>::THREADS) k_rows_r2c_persist
     DeviceExec ex;
     rows_r2c_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
 }
-template <int N>
+template <int N, bool ONE_PASS>
 __global__ void __launch_bounds__(RowsC2RStreamSmem<N>::THREADS, N <= 256 ? 4 : 1) k_rows_c2r_persist(RowsC2RParams p, int tiles_total, unsigned* err) {
     pdl_gate();
     DeviceExec ex;
     ex.err = err;
-    rows_c2r_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
+    rows_c2r_stream_body<N, DeviceExec, ONE_PASS>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
 }
 template <int N>
 __global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 256 ? 4 : (N == 512 ? 2 : 1)) k_cols_conv(ColsConvParams p) {
@@ -616,7 +618,8 @@ static cudaError_t init_kernels() {
     if ((e = optin(k_rows_r2c<N>, RowsR2CSmem<N>::BYTES))) return e;
     if ((e = optin(k_rows_c2r<N>, RowsR2CSmem<N>::BYTES))) return e;
     if ((e = optin(k_rows_r2c_persist<N>, RowsStreamSmem<N>::BYTES))) return e;
-    if ((e = optin(k_rows_c2r_persist<N>, RowsC2RStreamSmem<N>::BYTES))) return e;
+    if ((e = optin(k_rows_c2r_persist<N, false>, RowsC2RStreamSmem<N>::BYTES))) return e;
+    if ((e = optin(k_rows_c2r_persist<N, true>, RowsC2RStreamSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_conv<N>, ColsSmem<N>::BYTES_CONV))) return e;
     if ((e = optin(k_cols_fwd<N>, ColsSmem<N>::BYTES))) return e;
     if ((e = optin(k_cols_accum<N>, ColsSmem<N>::BYTES))) return e;
@@ -653,7 +656,7 @@ template <int N>
 static cudaError_t row_fits(int* r2c, int* c2r) {
     cudaError_t e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(r2c, k_rows_r2c_persist<N>, RowsStreamSmem<N>::THREADS, RowsStreamSmem<N>::BYTES))) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(c2r, k_rows_c2r_persist<N>, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(c2r, k_rows_c2r_persist<N, false>, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES);
 }
 template <int N>
 static cudaError_t column_slots(int sms, int* conv, int* accum) {
@@ -1050,7 +1053,7 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     const int nchunks = conv_chunks(N, B);
     static const int per_sm = [] { const char* e = getenv("B200CAM_C2R_PER_SM"); const int v = e ? atoi(e) : 4; return v; }();
     // one-pass normalise (RowsC2RParams::arrive): the persistent inverse-row kernel writes conv / max directly
-    static const int one_pass = [] { const char* e = getenv("B200CAM_ONE_PASS"); return e ? atoi(e) : 1; }();
+    static const int one_pass = [] { const char* e = getenv("B200CAM_ONE_PASS"); return e ? atoi(e) : 0; }();
     constexpr bool FUSABLE = (Plan<N>::R1 <= 16) && (Plan<N>::LANES == Plan<N>::R2);
     const bool fused = FUSABLE && one_pass && per_sm > 0;
     launch_k(k_cols_conv<N>, dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s, 
@@ -1062,13 +1065,16 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
             const int grid = persistent_grid(rows_fit(N, true), per_sm, total);
             static const int discard = [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }();
             const DeviceState* st = cur_state();
-            launch_k(k_rows_c2r_persist<N>, grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s, 
-                RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, tie_count, tie_pos, 0, discard, fused ? ws.arrive : nullptr,
-                              fused ? 3 * (N / T::ROWS) : 0, epi}, total, st != nullptr ? st->err_dev : nullptr);
+            const RowsC2RParams cp{ws.st2, sensor, tw, img_max, 1.0f, tie_count, tie_pos, 0, discard, fused ? ws.arrive : nullptr,
+                                   fused ? 3 * (N / T::ROWS) : 0, epi};
             if (fused) {
+                launch_k(k_rows_c2r_persist<N, true>, grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s, cp, total,
+                         st != nullptr ? st->err_dev : nullptr);
                 LAUNCH_CHECK();
                 return 0;
             }
+            launch_k(k_rows_c2r_persist<N, false>, grid, RowsC2RStreamSmem<N>::THREADS, RowsC2RStreamSmem<N>::BYTES, s, cp, total,
+                     st != nullptr ? st->err_dev : nullptr);
         } else {
             launch_k(k_rows_c2r<N>, rgrid, RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
                 RowsC2RParams{ws.st2, sensor, tw, img_max, 1.0f, nullptr, nullptr, 0});
@@ -1304,7 +1310,7 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     LAUNCH_CHECK();
     launch_k(Pdl{}, k_cols_reduce_inv<N>, 3 * T::NC + B, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s, 
         ColsReduceInvParams{ws.partial, ws.stp, tw, nchunks, 1.0f / (static_cast<float>(N) * N),
-                            ws.dot_lanes, img_max, tie_count, ws.coef, B});
+                            ws.dot_lanes, img_max, tie_count, ws.coef, B, img, tie_pos});
     LAUNCH_CHECK();
     launch_k(Pdl{}, k_rows_c2r<N>, dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
         RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});

@@ -90,6 +90,15 @@ B200_HD void discard_line(const void* p128) {
 #endif
 }
 
+// ---- pull a 128-byte line into L2 ahead of a later gather (fire and forget) -------------------------------------
+B200_HD void prefetch_l2(const void* p128) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p128) : "memory");
+#else
+    (void)p128;
+#endif
+}
+
 // ---- float max through integer atomics (order independent => deterministic) --------------
 B200_HD void atomic_max_float(float* addr, float v) {
 #if defined(__CUDA_ARCH__)

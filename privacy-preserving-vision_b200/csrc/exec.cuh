@@ -103,6 +103,11 @@ struct HandOff {
         }
         return __shfl_sync(0xffffffffu, ok, 0) != 0;
     }
+    static __device__ __forceinline__ int peek(const int* counter) {       // one relaxed L2 read, no waiting
+        int n;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(n) : "l"(counter) : "memory");
+        return n;
+    }
     static __device__ __forceinline__ float load_float(const float* p) {
         float v;
         asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
@@ -156,6 +161,14 @@ struct DeviceExec {
     __device__ __forceinline__ void arrive(int* counter) { HandOff::arrive(counter); }
     __device__ __forceinline__ bool wait_count(const int* counter, int target) { return HandOff::wait_count(counter, target); }
     __device__ __forceinline__ float load_coherent(const float* p) { return HandOff::load_float(p); }
+    __device__ __forceinline__ int peek_count(const int* counter) { return HandOff::peek(counter); }
+    // block maximum, first half: the warp's maximum lands in red[warp] (the emulator keeps one slot per thread)
+    __device__ __forceinline__ void stage_max(float v, float* red, int tid) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+    }
+    __device__ __forceinline__ int staged(int nthreads) const { return nthreads / 32; }
     __device__ __forceinline__ void report(unsigned code) { if (err != nullptr) atomicExch(err, code); }
 };
 // A "virtual block" of a cooperative kernel: the CTA plays block (vbx, vby) of a body written for
@@ -226,6 +239,9 @@ struct HostExec {
     void arrive(int* counter) { *counter += 1; }
     bool wait_count(const int*, int) { return true; }
     float load_coherent(const float* p) { return *p; }
+    int peek_count(const int* counter) { return *counter; }
+    void stage_max(float v, float* red, int tid) { red[tid] = v; }
+    int staged(int nthreads) const { return nthreads; }
     void report(unsigned) {}
 };
 

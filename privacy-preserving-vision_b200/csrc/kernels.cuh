@@ -603,7 +603,9 @@ struct RowsC2RStreamSmem {
     static constexpr int THREADS = R::THREADS;
 };
 
-template <int N, class Exec>
+// ONE_PASS = false compiles the stash of the one-pass mode away (it costs the two-pass kernel its registers: 128 with spills
+// instead of 96, 35 us instead of 22 us at B = 64)
+template <int N, class Exec, bool ONE_PASS = true>
 B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem, int total_tiles, int nctas) {
     using P = Plan<N>;
     using T = Tile<N>;
@@ -627,18 +629,22 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
     };
 
     // one-pass normalise (see RowsC2RParams::arrive): every lane holds a full transform output (LANES == R2) of <= 16 values
-    constexpr bool FUSABLE = (P::R1 <= 16) && (P::LANES == P::R2);
+    constexpr bool FUSABLE = ONE_PASS && (P::R1 <= 16) && (P::LANES == P::R2);
     const bool fused = FUSABLE && p.arrivals > 0 && p.arrive != nullptr && p.img_max != nullptr && p.out != nullptr;
     // the previous tile's outputs wait here (registers, or thread-private local memory where the compiler spills them: tensor
     // memory would be the natural stash, but a kernel that contains tcgen05.alloc is limited to ONE CTA per SM by the
     // launch machinery - measured: grid 592 -> 148)
     struct OutState { float2 v[P::R1]; };
-    OutState keep[Exec::IS_HOST ? S::THREADS : 1], cur[Exec::IS_HOST ? S::THREADS : 1];
+    OutState keep[(Exec::IS_HOST && FUSABLE) ? S::THREADS : 1], cur[(Exec::IS_HOST && FUSABLE) ? S::THREADS : 1];
     // write the stashed tile `tt` as conv / max of its image; the positions that attain the max are recorded for the backward
-    auto finish = [&](int tid, int tt) {
+    // `have`: the image's arrival count was already seen complete by this thread (pre_cnt) and `m_pre` read AFTER that
+    auto finish = [&](int tid, int tt, bool have, float m_pre) {
         const int fplane = tt / TILES, fy0 = (tt % TILES) * T::ROWS, img = fplane / 3;
-        if (!ex.wait_count(p.arrive + img, p.arrivals)) ex.report(1u);
-        const float m = ex.load_coherent(p.img_max + img);
+        float m = m_pre;
+        if (!have) {
+            if (!ex.wait_count(p.arrive + img, p.arrivals)) ex.report(1u);
+            m = ex.load_coherent(p.img_max + img);
+        }
         const float inv = 1.0f / m;
         const int j = tid / P::LANES, a = tid % P::LANES;
         const float2 (&v)[P::R1] = keep[ex.slot(tid)].v;
@@ -677,10 +683,17 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
         }
     });
     int it = 0;
+    // one-pass mode: the arrival count and the maximum of the PREVIOUS tile's image are fetched at the top of the iteration
+    // (two dependent L2 round trips that fly while this tile is transformed) instead of inside finish()
+    int pre_cnt = 0;
+    float pre_max = 0.f;
     for (int t = first; t < total_tiles; t += nctas, ++it) {
         const int buf = it & 1;
         const int plane = t / TILES, y0 = (t % TILES) * T::ROWS;
         ex.phase([&](int tid) {
+            if constexpr (FUSABLE && !Exec::IS_HOST) {
+                if (fused && it > 0) pre_cnt = ex.peek_count(p.arrive + ((t - nctas) / TILES) / 3);
+            }
             if (t + nctas < total_tiles) {        // the other buffer was consumed before the last block barrier
                 if (tid == 0) ex.bulk_expect(bars + (buf ^ 1), T::NC * Q::SEG * 8);
                 issue(tid, t + nctas, buf ^ 1);
@@ -705,6 +718,9 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
         });
         ex.warp_phase([&](int tid) {
             const int j = tid / P::LANES, b = tid % P::LANES;
+            if constexpr (FUSABLE && !Exec::IS_HOST) {
+                if (fused && it > 0 && pre_cnt >= p.arrivals) pre_max = ex.load_coherent(p.img_max + ((t - nctas) / TILES) / 3);
+            }
             if (b < P::R1) {
                 RowState<N>& s = st[ex.slot(tid)];
 #pragma unroll
@@ -740,19 +756,19 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
                     mx = fmaxf(mx, fmaxf(e, o));
                 }
             }
-            red[tid] = mx;
+            ex.stage_max(mx, red, tid);
         });
         if (p.img_max != nullptr) {
             ex.phase([&](int tid) {
                 if (tid == 0) {
                     float mx = red[0];
-                    for (int k = 1; k < S::THREADS; ++k) mx = fmaxf(mx, red[k]);
+                    for (int k = 1; k < ex.staged(S::THREADS); ++k) mx = fmaxf(mx, red[k]);
                     atomic_max_float(p.img_max + plane / 3, mx);
                     if (fused) ex.arrive(p.arrive + plane / 3);        // release: the max above is visible before the count
                 }
                 if constexpr (FUSABLE) {
                     if (fused) {
-                        if (it > 0) finish(tid, t - nctas);            // the previous tile's image is complete by now
+                        if (it > 0) finish(tid, t - nctas, !Exec::IS_HOST && pre_cnt >= p.arrivals, pre_max);   // complete by now
 #pragma unroll
                         for (int i = 0; i < P::R1; ++i) keep[ex.slot(tid)].v[i] = cur[ex.slot(tid)].v[i];
                     }
@@ -761,7 +777,7 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
         }
     }
     if constexpr (FUSABLE) {
-        if (fused && it > 0) ex.phase([&](int tid) { finish(tid, first + (it - 1) * nctas); });
+        if (fused && it > 0) ex.phase([&](int tid) { finish(tid, first + (it - 1) * nctas, false, 0.f); });
     }
 }
 
@@ -994,6 +1010,11 @@ struct ColsReduceInvParams {
     const int* tie_count;    // [B]
     float* coef;             // [B]
     int B;
+    // the side-job CTA of image b also pulls the planes that the arg-max term (K8) is about to gather from - x_b[c*] for every
+    // recorded arg-max - into L2: K8 runs two small kernels later and would otherwise pay a DRAM miss per gather (the images
+    // were last read a whole step ago)
+    const float* x = nullptr;        // nullable [B][3][N][N]
+    const int* tie_pos = nullptr;    // [B][MAX_TIES]
 };
 
 // grid 3*NC (one spectral column per CTA), block N (thread = v): the chunk sum is spread over N threads with
@@ -1021,6 +1042,16 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
         constexpr int PER_IMAGE = TOTAL * P::R1;
         float* red = reinterpret_cast<float*>(E);
         const int b = cu - TOTAL;
+        if (p.x != nullptr && p.tie_pos != nullptr) {
+            ex.phase([&](int t) {
+                const int n = p.tie_count[b] < C2R_MAX_TIES ? p.tie_count[b] : C2R_MAX_TIES;
+                for (int k = 0; k < n; ++k) {
+                    const int c = p.tie_pos[b * C2R_MAX_TIES + k] / (N * N);
+                    const char* plane = reinterpret_cast<const char*>(p.x + (static_cast<size_t>(b) * 3 + c) * N * N);
+                    for (int line = t; line < N * N * 4 / 128; line += N) prefetch_l2(plane + static_cast<size_t>(line) * 128);
+                }
+            });
+        }
         ex.phase([&](int t) {
             const float* src = p.dot_lanes + static_cast<size_t>(b) * PER_IMAGE;
             float s = 0.f;

@@ -51,6 +51,7 @@ class DevicePlan:
         self.peer_comm = None          # parallel.PeerComm: fused NVLink all-reduce instead of the NCCL call
         self.otf_cache = None          # (psf tensor, its OTF) left by the last asynchronous psf_synth
         self.otf_event = None          # recorded on the side stream once that OTF is complete
+        self.field_event = None        # recorded on the side stream once |U|^2 is complete (what finish_psf needs)
         self._side_stream = None       # runs the PSF-independent half of the sensor forward beside the PSF chain
         self._aux_stream = None
         self.pending_finish = None     # (psf, stats) still to be written by finish_psf()
@@ -144,6 +145,8 @@ class PsfSynth(torch.autograd.Function):
                 _lib.check(plan.lib.b200cam_psf_field(
                     _lib.ptr(hc), _lib.ptr(plan.A), _lib.ptr(plan.Ht), plan.kappa, _lib.ptr(field),
                     _lib.ptr(ws), ws.numel(), N, launch, _stream(), _HOLD_ROWS))
+                plan.field_event = torch.cuda.Event()          # |U|^2 and its partial sums are in the workspace
+                plan.field_event.record(stream)
                 otf = torch.empty(plan.otf_floats, dtype=torch.float32, device=plan.device)
                 _lib.check(plan.lib.b200cam_psf_otf_early(_lib.ptr(otf), _lib.ptr(ws), ws.numel(), N, launch))
                 plan.otf_event = torch.cuda.Event()

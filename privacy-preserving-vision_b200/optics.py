@@ -191,12 +191,16 @@ class Camera(nn.Module):
             # the spectral product only needs the OTF: the PSF itself and the two regularisers are written on a
             # normal-priority stream while the sensor kernels run, and joined at the end
             ev, plan.otf_event = plan.otf_event, None
+            # psf / regularisers: beside the OTF kernels (both only read |U|^2), i.e. before the spectral product fills
+            # every SM - a finalise that straggles into the one-pass inverse-row kernel keeps part of that kernel's
+            # persistent grid from becoming resident and its per-image max exchange then waits (measured 50 vs 35 us)
+            aux = plan.aux_stream()
+            fev, plan.field_event = plan.field_event, None
+            aux.wait_event(fev if fev is not None else ev)
+            plan.finish_psf(aux)
             cur.wait_event(ev)
             self.centering_loss = self._pending_centering
             y = F.sensor_conv(img, psf, self._plan(psf.device), rows, epi)
-            aux = plan.aux_stream()
-            aux.wait_event(ev)
-            plan.finish_psf(aux)
             cur.wait_stream(aux)
             cur.wait_stream(side)
             return y
