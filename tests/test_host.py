@@ -137,3 +137,21 @@ def test_caption_camera_loads_both_reference_checkpoint_layouts():
     shipped = {k: v.detach().clone() + 1.0 for k, v in cam.state_dict().items()}
     cam.load_reference_state_dict(shipped)
     assert torch.equal(cam.zernike_coeffs_no_train2.detach(), full[4:] + 1.0)
+
+
+@pytest.mark.skipif(not Path("/root/reference/Image_Caption/Camera/Model.pth").exists(), reason="/root/reference not mounted")
+def test_caption_camera_loads_the_real_reference_checkpoint():
+    """SURVEY 8 f3 with the checkpoint the reference ships: Image_Caption/Camera/Model.pth holds {'model': {optics.
+    zernike_coeffs_no_train (3,1,1), optics.zernike_coeffs_train (347,1,1)}} - the 3 + (T-3) layout of train.py:71-78 at
+    T = 350, which the shipped module's own load_state_dict rejects.  Loaded here into a T = 350 camera (small wave grid:
+    the coefficient vector, not the basis, is what the checkpoint defines)."""
+    from b200cam.lens import OpticsZernike
+    ck = torch.load("/root/reference/Image_Caption/Camera/Model.pth", map_location="cpu", weights_only=False)
+    ref = ck["model"]
+    cam = OpticsZernike(input_shape=[None, 16, 16, 3], device="cpu", zernike_terms=350, patch_size=16,
+                        wave_resolution=[32, 32], sample_interval=3e-6, height_tolerance=None)
+    cam.load_reference_state_dict(ck)
+    got = torch.cat((cam.zernike_coeffs_no_train, cam.zernike_coeffs_train.unsqueeze(0), cam.zernike_coeffs_no_train2), 0)
+    want = torch.cat((ref["optics.zernike_coeffs_no_train"], ref["optics.zernike_coeffs_train"]), 0)
+    assert got.shape == (350, 1, 1) and torch.equal(got.detach(), want)
+    assert float(cam.zernike_coeffs_train) == float(ref["optics.zernike_coeffs_train"][0])

@@ -10,7 +10,9 @@ from oracle import lens_oracle as lo
 from oracle import ref_shim
 import b200cam.zernike as zern
 
-CASES = {"caption_w128_p64_b2": dict(wave=128, patch=64, B=2, terms=10)}
+CASES = {"caption_w128_p64_b2": dict(wave=128, patch=64, B=2, terms=10),
+         # the shipped geometry (train.py:64-66: wave 896 -> 1344^2 propagation, patch 256 -> 512^2 convolution), few terms
+         "caption_w896_p256_b2": dict(wave=896, patch=256, B=2, terms=10)}
 
 
 def inputs(case):
