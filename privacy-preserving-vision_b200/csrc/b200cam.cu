@@ -801,7 +801,7 @@ struct SensorWs {
         const size_t plane = static_cast<size_t>(N / 2 + 1) * N;
         stx = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
         st2 = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
-        arrive = c.take<int>(B);
+        arrive = c.take<int>(static_cast<size_t>(B) * 64);     // one-pass normalise: a row of 64 key slots per image
         if (backward) {
             stg = c.take<float2>(static_cast<size_t>(B) * 3 * plane);
             const int max_chunks = (N == 256 && PLANE_MAX_G3 > MAX_CHUNKS) ? PLANE_MAX_G3 : MAX_CHUNKS;
@@ -1052,12 +1052,15 @@ static int sensor_finish_impl(const float* psf, float* sensor, float* img_max, i
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     const int nchunks = conv_chunks(N, B);
     static const int per_sm = [] { const char* e = getenv("B200CAM_C2R_PER_SM"); const int v = e ? atoi(e) : 4; return v; }();
-    // one-pass normalise (RowsC2RParams::arrive): the persistent inverse-row kernel writes conv / max directly
+    // one-pass normalise (RowsC2RParams::arrive, B200CAM_ONE_PASS=1): the persistent inverse-row kernel writes conv / max
+    // directly.  OFF by default: measured on one box against the two-pass path (B = 64, N = 256, graph replay) the kernel takes
+    // 50-56 us against 21.6 + 16-19 us - and 52.9 us even with the maximum exchange skipped, i.e. it is the stash of the
+    // previous tile's outputs (128 registers / thread at 4 CTAs per SM) that costs the time, not the waiting.
     static const int one_pass = [] { const char* e = getenv("B200CAM_ONE_PASS"); return e ? atoi(e) : 0; }();
     constexpr bool FUSABLE = (Plan<N>::R1 <= 16) && (Plan<N>::LANES == Plan<N>::R2);
     const bool fused = FUSABLE && one_pass && per_sm > 0;
     launch_k(k_cols_conv<N>, dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES_CONV, s, 
-        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f, fused ? ws.arrive : nullptr, fused ? B : 0});
+        ColsConvParams{srow, ws.st2, otf, tw, nullptr, B, nchunks, 0, 1.0f, fused ? ws.arrive : nullptr, fused ? 64 * B : 0});
     LAUNCH_CHECK();
     {
         if (per_sm > 0) {

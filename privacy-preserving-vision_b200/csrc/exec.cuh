@@ -108,6 +108,44 @@ struct HandOff {
         asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(n) : "l"(counter) : "memory");
         return n;
     }
+    // "the value is its own flag": a 4-byte word that is zero until its producer has stored a non-zero key - no fence, no
+    // atomic, no separate counter (the low-latency protocol of the peer all-reduce, used here between CTAs)
+    static __device__ __forceinline__ void store_key(unsigned* p, unsigned key) {
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(key) : "memory");
+    }
+    static __device__ __forceinline__ unsigned load_key(const unsigned* p) {
+        unsigned v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    }
+    // order-preserving, never-zero key of a float (not NaN) and back
+    static __device__ __forceinline__ unsigned float_key(float v) {
+        const unsigned b = __float_as_uint(v);
+        return (b & 0x80000000u) ? ~b : (b | 0x80000000u);      // negative: ~b in [0x007fffff, 0x7fffffff]; never 0 (b = ~0 is a NaN)
+    }
+    static __device__ __forceinline__ float key_float(unsigned k) {
+        return __uint_as_float((k & 0x80000000u) ? k & 0x7fffffffu : ~k);
+    }
+    // all lanes: poll the slot row until every live word is non-zero, return the decoded maximum; false = gave up after ~2 s
+    static __device__ __forceinline__ bool wait_keys(const unsigned* row, int lane, unsigned k0, unsigned k1, float* out) {
+        bool ok = true;
+        long long t0 = 0;
+        for (int spin = 0;; ++spin) {
+            if (__all_sync(0xffffffffu, k0 != 0u && k1 != 0u)) break;
+            if (k0 == 0u) k0 = load_key(row + lane);
+            if (k1 == 0u) k1 = load_key(row + 32 + lane);
+            if (spin == 64) t0 = clock64();
+            if (spin > 64 && clock64() - t0 > 4000000000LL) { ok = false; break; }
+        }
+        unsigned k = k0 > k1 ? k0 : k1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned other = __shfl_xor_sync(0xffffffffu, k, o);
+            k = other > k ? other : k;
+        }
+        *out = key_float(k);
+        return ok;
+    }
     static __device__ __forceinline__ float load_float(const float* p) {
         float v;
         asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
@@ -162,6 +200,11 @@ struct DeviceExec {
     __device__ __forceinline__ bool wait_count(const int* counter, int target) { return HandOff::wait_count(counter, target); }
     __device__ __forceinline__ float load_coherent(const float* p) { return HandOff::load_float(p); }
     __device__ __forceinline__ int peek_count(const int* counter) { return HandOff::peek(counter); }
+    __device__ __forceinline__ void key_store(unsigned* p, float v) { HandOff::store_key(p, HandOff::float_key(v)); }
+    __device__ __forceinline__ unsigned key_load(const unsigned* p) { return HandOff::load_key(p); }
+    __device__ __forceinline__ bool key_wait(const unsigned* row, int lane, unsigned k0, unsigned k1, float* out) {
+        return HandOff::wait_keys(row, lane, k0, k1, out);
+    }
     // block maximum, first half: the warp's maximum lands in red[warp] (the emulator keeps one slot per thread)
     __device__ __forceinline__ void stage_max(float v, float* red, int tid) {
 #pragma unroll
@@ -240,6 +283,9 @@ struct HostExec {
     bool wait_count(const int*, int) { return true; }
     float load_coherent(const float* p) { return *p; }
     int peek_count(const int* counter) { return *counter; }
+    void key_store(unsigned*, float) {}                      // the one-pass exchange between concurrent CTAs is device only
+    unsigned key_load(const unsigned*) { return 1u; }
+    bool key_wait(const unsigned*, int, unsigned, unsigned, float* out) { *out = 1.f; return true; }
     void stage_max(float v, float* red, int tid) { red[tid] = v; }
     int staged(int nthreads) const { return nthreads; }
     void report(unsigned) {}

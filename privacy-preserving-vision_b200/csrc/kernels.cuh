@@ -637,13 +637,20 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
     struct OutState { float2 v[P::R1]; };
     OutState keep[(Exec::IS_HOST && FUSABLE) ? S::THREADS : 1], cur[(Exec::IS_HOST && FUSABLE) ? S::THREADS : 1];
     // write the stashed tile `tt` as conv / max of its image; the positions that attain the max are recorded for the backward
-    // `have`: the image's arrival count was already seen complete by this thread (pre_cnt) and `m_pre` read AFTER that
-    auto finish = [&](int tid, int tt, bool have, float m_pre) {
+    // one-pass mode: the tiles of an image publish their maxima as never-zero keys in the image's slot row (zeroed by the
+    // column kernel before); a warp reads the row (k0: slots 0..31, k1: slots 32..), polls until every word is non-zero
+    // and takes the maximum - no atomic, no fence, no counter
+    constexpr int SLOTS = 64;                       // words per image row in p.arrive
+    static_assert(!FUSABLE || 3 * TILES <= SLOTS, "slot row too short");
+    constexpr int NS0 = 3 * TILES < 32 ? 3 * TILES : 32, NS1 = 3 * TILES > 32 ? 3 * TILES - 32 : 0;   // live slots per half row
+    // lanes without a slot carry the smallest key (1): "present", never the maximum
+    auto finish = [&](int tid, int tt, unsigned k0, unsigned k1) {
         const int fplane = tt / TILES, fy0 = (tt % TILES) * T::ROWS, img = fplane / 3;
-        float m = m_pre;
-        if (!have) {
-            if (!ex.wait_count(p.arrive + img, p.arrivals)) ex.report(1u);
-            m = ex.load_coherent(p.img_max + img);
+        float m = 0.f;
+        {
+            const unsigned* row = reinterpret_cast<const unsigned*>(p.arrive) + static_cast<size_t>(img) * SLOTS;
+            if (!ex.key_wait(row, tid & 31, k0, k1, &m)) ex.report(1u);
+            if (tt % (3 * TILES) == 0 && tid == 0) p.img_max[img] = m;      // kept for the backward
         }
         const float inv = 1.0f / m;
         const int j = tid / P::LANES, a = tid % P::LANES;
@@ -685,15 +692,11 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
     int it = 0;
     // one-pass mode: the arrival count and the maximum of the PREVIOUS tile's image are fetched at the top of the iteration
     // (two dependent L2 round trips that fly while this tile is transformed) instead of inside finish()
-    int pre_cnt = 0;
-    float pre_max = 0.f;
+    unsigned pre_k0 = 0u, pre_k1 = 0u;
     for (int t = first; t < total_tiles; t += nctas, ++it) {
         const int buf = it & 1;
         const int plane = t / TILES, y0 = (t % TILES) * T::ROWS;
         ex.phase([&](int tid) {
-            if constexpr (FUSABLE && !Exec::IS_HOST) {
-                if (fused && it > 0) pre_cnt = ex.peek_count(p.arrive + ((t - nctas) / TILES) / 3);
-            }
             if (t + nctas < total_tiles) {        // the other buffer was consumed before the last block barrier
                 if (tid == 0) ex.bulk_expect(bars + (buf ^ 1), T::NC * Q::SEG * 8);
                 issue(tid, t + nctas, buf ^ 1);
@@ -719,7 +722,11 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
         ex.warp_phase([&](int tid) {
             const int j = tid / P::LANES, b = tid % P::LANES;
             if constexpr (FUSABLE && !Exec::IS_HOST) {
-                if (fused && it > 0 && pre_cnt >= p.arrivals) pre_max = ex.load_coherent(p.img_max + ((t - nctas) / TILES) / 3);
+                if (fused && it > 0) {               // the previous tile's image: its keys fly in while this tile is transformed
+                    const unsigned* row = reinterpret_cast<const unsigned*>(p.arrive) + static_cast<size_t>(((t - nctas) / TILES) / 3) * SLOTS;
+                    pre_k0 = (tid & 31) < NS0 ? ex.key_load(row + (tid & 31)) : 1u;
+                    pre_k1 = (tid & 31) < NS1 ? ex.key_load(row + 32 + (tid & 31)) : 1u;
+                }
             }
             if (b < P::R1) {
                 RowState<N>& s = st[ex.slot(tid)];
@@ -763,12 +770,18 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
                 if (tid == 0) {
                     float mx = red[0];
                     for (int k = 1; k < ex.staged(S::THREADS); ++k) mx = fmaxf(mx, red[k]);
-                    atomic_max_float(p.img_max + plane / 3, mx);
-                    if (fused) ex.arrive(p.arrive + plane / 3);        // release: the max above is visible before the count
+                    if constexpr (FUSABLE && !Exec::IS_HOST) {
+                        if (fused)
+                            ex.key_store(reinterpret_cast<unsigned*>(p.arrive) + static_cast<size_t>(plane / 3) * SLOTS + t % (3 * TILES), mx);
+                        else
+                            atomic_max_float(p.img_max + plane / 3, mx);
+                    } else {
+                        atomic_max_float(p.img_max + plane / 3, mx);
+                    }
                 }
                 if constexpr (FUSABLE) {
                     if (fused) {
-                        if (it > 0) finish(tid, t - nctas, !Exec::IS_HOST && pre_cnt >= p.arrivals, pre_max);   // complete by now
+                        if (it > 0) finish(tid, t - nctas, pre_k0, pre_k1);            // the previous tile's image is complete by now
 #pragma unroll
                         for (int i = 0; i < P::R1; ++i) keep[ex.slot(tid)].v[i] = cur[ex.slot(tid)].v[i];
                     }
@@ -777,7 +790,7 @@ B200_HD void rows_c2r_stream_body(Exec& ex, const RowsC2RParams& p, float2* smem
         }
     }
     if constexpr (FUSABLE) {
-        if (fused && it > 0) ex.phase([&](int tid) { finish(tid, first + (it - 1) * nctas, false, 0.f); });
+        if (fused && it > 0) ex.phase([&](int tid) { finish(tid, first + (it - 1) * nctas, (tid & 31) < NS0 ? 0u : 1u, (tid & 31) < NS1 ? 0u : 1u); });
     }
 }
 
