@@ -6,7 +6,7 @@ import re
 import sys
 
 
-def main(path: str, marker: str = "k_tie_coef") -> None:
+def main(path: str, marker: str = "k_tie_term") -> None:
     with open(path) as f:
         lines = [ln for ln in f if not ln.startswith("==")]
     rows = list(csv.DictReader(lines))
