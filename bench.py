@@ -728,7 +728,7 @@ def run_caption_camera(args) -> None:
             "gpu_launches": launches * steps, "launches_per_step": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src,
-                         "scope": "whole step incl. the PSF synthesis (torch ops) - the path is FP32-compute bound, SURVEY 8a"},
+                         "scope": "whole step: PSF synthesis (1344^2 mixed-radix kernels), pruned 512^2 sensor convolution, backward into the trainable coefficient; algorithmic bytes 48*P^2 per image - the path is FP32-compute bound, SURVEY 8a"},
             "clocks": clocks,
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"3 fwd+bwd steps of batch {bs} (median), oracle/lens_oracle.py on torch CPU"}}

@@ -208,3 +208,37 @@ class Camera(nn.Module):
         cur.wait_stream(side)
         self.centering_loss = self._pending_centering
         return F.sensor_conv(img, psf, self._plan(psf.device), rows, epi)
+
+    # ------------------------------------------------------------------ CUDA-graph helper (no reference counterpart)
+    def graphed(self, sample_img: torch.Tensor, num_warmup_iters: int = 3):
+        """CUDA-graphed ``camera(img) -> (sensor, loss_rad, centering_loss)`` for a FIXED input shape.
+
+        An eager forward + backward of this module costs ~400 us of host time (16 kernel launches through ctypes, autograd,
+        stream bookkeeping) for ~175 us of device time at B = 64: training loops that run the camera in front of a
+        downstream net should not pay that every step.  The returned callable replays one captured graph for the forward
+        and one for the backward (``torch.cuda.make_graphed_callables``: static input / output / gradient buffers, inputs are
+        copied in, autograd sees an ordinary differentiable op), so the downstream net and the optimiser stay eager:
+
+            step = camera.graphed(images[:B])              # once; images: (B,3,N,N) fp32 or uint8 on the GPU
+            sensor, loss_rad, centering = step(images_b)   # every iteration
+            (task_loss(net(sensor)) + a * loss_rad + b * centering).backward()
+
+        The two regularisers are RETURNED (the module attributes ``loss_rad`` / ``centering_loss`` set during capture are not
+        connected to the replayed graph).  Capture before the module's first eager backward (PyTorch's rule for
+        ``make_graphed_callables``: gradient-accumulation nodes created on the default stream cannot join a capture).  Re-capture after changing N, the batch size, ``data_parallel`` or the epilogue
+        switches.  Parameter updates in place (optimiser steps, ``load_state_dict``) are picked up by the replays."""
+        if not (torch.is_tensor(sample_img) and sample_img.is_cuda):
+            raise RuntimeError("b200cam runs on CUDA (sm_100a) only; capture needs a sample batch on the GPU")
+
+        class _WithLosses(nn.Module):
+            def __init__(self, cam):
+                super().__init__()
+                self.cam = cam
+
+            def forward(self, img):
+                y = self.cam(img)
+                return y, self.cam.loss_rad, self.cam.centering_loss
+
+        wrapped = _WithLosses(self)
+        sample = sample_img.detach().clone()
+        return torch.cuda.make_graphed_callables(wrapped, (sample,), num_warmup_iters=num_warmup_iters)

@@ -394,3 +394,31 @@ def test_opt_in_sensor_noise_and_quantisation(N, B):
     with torch.no_grad():
         y2 = cam2(img.cuda(), noise=noise)
     assert rel_l2(y2, out["sensor"] + sigma * noise.cpu()) <= TOL_SENSOR
+
+
+def test_graphed_callable_matches_eager():
+    """Camera.graphed(): forward and backward replayed from CUDA graphs behind an ordinary autograd op - same sensor image,
+    regularisers and parameter gradient as the eager module (to rounding: the captured PSF chain is the multi-kernel one).
+    Captured BEFORE the module's first eager backward (torch.cuda.make_graphed_callables' rule: an AccumulateGrad node
+    created on the default stream would be dragged into the capture)."""
+    N, B, T = 128, 5, 10
+    torch.manual_seed(3)
+    cam = Camera(device=torch.device("cuda", 0), N=N, zernike_terms=T)
+    img, w = synth.images(B, N).cuda(), synth.upstream_grad(B, N).cuda()
+    step = cam.graphed(img)
+    grads = []
+    for it in range(2):                                    # the second replay sees the same inputs: identical results
+        cam.Zer_train.grad = None
+        yg, rad, cen = step(img)
+        ((yg * w).sum() + 0.3 * rad + 1.7 * cen).backward()
+        grads.append(cam.Zer_train.grad.clone())
+    graphed_y = yg.detach().clone()
+    img2 = synth.images(B, N, seed=77).cuda()              # new data through the static buffers
+    graphed_y2 = step(img2)[0].detach().clone()
+    cam.Zer_train.grad = None
+    y = cam(img)
+    ((y * w).sum() + 0.3 * cam.loss_rad + 1.7 * cam.centering_loss).backward()
+    assert torch.equal(grads[0], grads[1])
+    assert rel_l2(graphed_y, y) <= 1e-5
+    assert rel_l2(grads[0], cam.Zer_train.grad) <= 1e-4
+    assert rel_l2(graphed_y2, cam(img2)) <= 1e-5
