@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(RowsStreamSmem<N>::THREADS) k_rows_r2c_persist
     rows_r2c_stream_body<N>(ex, p, SMEM2, tiles_total, static_cast<int>(gridDim.x));
 }
 template <int N, bool ONE_PASS>
-__global__ void __launch_bounds__(RowsC2RStreamSmem<N>::THREADS, N <= 256 ? 4 : 1) k_rows_c2r_persist(RowsC2RParams p, int tiles_total, unsigned* err) {
+__global__ void __launch_bounds__(RowsC2RStreamSmem<N>::THREADS, N <= 256 ? 4 : (N == 512 ? 2 : 1)) k_rows_c2r_persist(RowsC2RParams p, int tiles_total, unsigned* err) {
     pdl_gate();
     DeviceExec ex;
     ex.err = err;
