@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 512 ? 2 : 1) k_lcol
             for (int i = 0; i < P::R1; ++i) v[i] = (i >= I0 && i < I1) ? in[col + P::R2 * i + a] : make_float2(0.f, 0.f);
             P::stepA(v, a, E1 + jc * P::E_SIZE, tw);
         }
-        __syncthreads();
+        __syncwarp();        // a column lives in one warp (LANES <= 32): no block barrier
         if (live && a < P::R1) {
             float2 v[P::R2];
             P::stepB(v, a, E1 + jc * P::E_SIZE);
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 512 ? 2 : 1) k_lcol
             for (int i = 0; i < P::R2; ++i) v[i] = cmul(v[i], k[i]);
             P::stepC(v, a, E2 + jc * P::E_SIZE, tw);
         }
-        __syncthreads();
+        __syncwarp();        // a column lives in one warp (LANES <= 32): no block barrier
         if (live && a < P::R2) {
             float2 v[P::R1];
             P::stepD(v, a, E2 + jc * P::E_SIZE);
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 512 ? 2 : 1) k_lcol
                 P::stepA(v, a, Eg + jc * P::E_SIZE, tw);
             }
         }
-        __syncthreads();
+        __syncwarp();
         if (live && a < P::R1) {
             float2 vx[P::R2], vg[P::R2];
             P::stepB(vx, a, Ex + jc * P::E_SIZE);
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(ColsSmem<N>::THREADS, N <= 512 ? 2 : 1) k_lcol
                 acc[i].y += t.y;
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     if (live && a < P::R1) {
         float2* dst = partial + (static_cast<size_t>(blockIdx.y) * TOTAL + cu) * N;
@@ -395,7 +395,8 @@ __global__ void __launch_bounds__(EWT) k_ldot_final(const double* __restrict__ p
 constexpr int MAX_LCHUNKS = 16;
 static int lchunks(int N, int B) {
     const int colgroups = (3 * (N / 2 + 1) + 7) / 8;
-    int n = (4 * 148 + colgroups - 1) / colgroups;
+    const int per_sm = N <= 512 ? 2 : 1;                       // resident CTAs per SM (launch bounds of the column kernels)
+    int n = (per_sm * 148) / colgroups;                        // one wave: a second, partly filled wave costs as much as a full one
     if (n > MAX_LCHUNKS) n = MAX_LCHUNKS;
     if (n > B) n = B;
     return n < 1 ? 1 : n;
