@@ -51,10 +51,12 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="timed loop only (for ncu): no breakdown / e2e / cpu legs")
-    ap.add_argument("--config", default="2", choices=["1", "2", "3cam", "5"],
+    ap.add_argument("--config", default="2", choices=["1", "2", "3cam", "4cam", "5"],
                     help="BASELINE.json config: 1 = forward only, batch 8 (CPU-reference shape); 2 = fwd+bwd batch 64 (headline, "
                          "default); 3cam = the Image_Caption camera of config 3 (896/256/T=350, batch 128) without the caption "
-                         "nets; 5 = hi-res sweep (use --size 512|1024; the batch defaults to what fits the bench comfortably)")
+                         "nets; 4cam = the camera half of config 4 (global batch 512 split over the ranks: STRONG scaling, all-reduce of dL/dh; the "
+                         "FAN heat-map regressor is the reference's own model and is not on the GPU box: \"downstream\": \"absent\"); "
+                         "5 = hi-res sweep (use --size 512|1024; the batch defaults to what fits the bench comfortably)")
     args = ap.parse_args()
     if args.config == "1":
         args.batch = 8 if args.batch == 64 else args.batch
@@ -65,6 +67,9 @@ def parse():
             args.batch = 32 if args.size == 512 else 8
     if args.config == "3cam" and args.batch == 64:
         args.batch = 128
+    if args.config == "4cam":                       # BASELINE config 4: global batch 512 over the ranks
+        world = int(os.environ.get("WORLD_SIZE", str(max(1, args.gpus))))
+        args.batch = max(1, 512 // max(1, world))
     return args
 
 
@@ -118,8 +123,12 @@ def cpu_port_rate(N: int, B: int, budget_s: float, steps: int | None = None, war
 def workload_config(args, world: int, launch: str) -> dict:
     N, B, R = args.size, args.batch, max(1, args.input_sets)
     what = "forward only" if args.config == "1" else "fwd+bwd into height map"
+    extra = {}
+    if args.config == "4cam":
+        what += " (camera half of the optical encoder + heat-map regressor step, global batch 512)"
+        extra = {"downstream": "absent"}     # FAN (Face-DeId/core/wing.py) is the reference's own cuDNN model; not on the GPU box
     return {"workload": f"Face-DeId Camera {what}, batch {B}/GPU of {N}x{N} RGB, random height map",
-            "baseline_config": args.config,
+            "baseline_config": args.config, **extra,
             "global_batch": B * world, "size": N, "parallelism": f"dp{world}" if world > 1 else "single",
             "l2": (f"{R} distinct resident input sets rotated: {R * 2 * B * 3 * N * N * 4 / 1e6:.0f} MB of inputs "
                    + ("(larger than the 126 MB L2)" if R * 2 * B * 3 * N * N * 4 > 126e6 else "(SMALLER than L2 - not a valid bench size)")),
@@ -598,8 +607,8 @@ def run_b200(args) -> None:
             torch_cuda = {"error": str(exc)[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.config == "4cam" else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world, "cuda-graph replay" if graphs is not None else "eager"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * N * N * 4,
                 "d2h_bytes_per_step": B * 3 * N * N * 4 if fwd_only else N * N * 4 + 4,
