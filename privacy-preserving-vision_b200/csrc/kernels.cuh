@@ -814,43 +814,45 @@ struct NormaliseParams {
 
 // Four independent float4 per thread and iteration (the kernel is a pure stream: keep loads in flight).
 // y = conv * (1/max) instead of a division per element; the arg-max element itself is written as exactly 1.
+// A CTA works on a slice of ONE image at a time (unit = image x slice): the maximum is loaded once per unit and no
+// per-element index division is left (the flat-index version spent ~120 instructions per float4, 11.6 M warp instructions).
 template <class Exec>
 B200_HD void normalise_body(Exec& ex, const NormaliseParams& p, int grid_x) {
     ex.phase([&](int tid) {
         constexpr int U = 4;
-        const long long nthr = static_cast<long long>(grid_x) * ex.nthreads();
+        const int B = static_cast<int>(p.n4 / p.per_image4);
+        const int spi = grid_x / B > 1 ? grid_x / B : 1;               // slices per image
+        const int nthr = ex.nthreads();
+        const int stride = spi * nthr;
         float4* y4 = reinterpret_cast<float4*>(p.y);
-        for (long long i0 = static_cast<long long>(ex.bx()) * ex.nthreads() + tid; i0 < p.n4; i0 += U * nthr) {
-            float4 v[U];
-            float m[U];
+        for (int unit = ex.bx(); unit < B * spi; unit += grid_x) {
+            const int b = unit / spi, sl = unit - b * spi;
+            const float m = ld_ro(p.img_max + b);
+            const float inv = 1.0f / m;
+            float4* img4 = y4 + static_cast<size_t>(b) * p.per_image4;
+            for (int i0 = sl * nthr + tid; i0 < p.per_image4; i0 += U * stride) {
+                float4 v[U];
 #pragma unroll
-            for (int k = 0; k < U; ++k) {
-                const long long i = i0 + k * nthr;
-                if (i < p.n4) {
-                    v[k] = y4[i];
-                    m[k] = ld_ro(p.img_max + static_cast<int>(i / p.per_image4));
-                }
-            }
+                for (int k = 0; k < U; ++k)
+                    if (i0 + k * stride < p.per_image4) v[k] = img4[i0 + k * stride];
 #pragma unroll
-            for (int k = 0; k < U; ++k) {
-                const long long i = i0 + k * nthr;
-                if (i >= p.n4) continue;
-                const int b = static_cast<int>(i / p.per_image4);
-                const float inv = 1.0f / m[k];
-                float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+                for (int k = 0; k < U; ++k) {
+                    const int i = i0 + k * stride;
+                    if (i >= p.per_image4) continue;
+                    float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (e[q] == m[k]) {
-                        const int slot = atomic_add_int(p.tie_count + b, 1);
-                        if (slot < MAX_TIES)
-                            p.tie_pos[b * MAX_TIES + slot] = static_cast<int>(i % p.per_image4) * 4 + q;
-                        e[q] = 1.0f;
-                    } else {
-                        e[q] *= inv;
+                    for (int q = 0; q < 4; ++q) {
+                        if (e[q] == m) {
+                            const int slot = atomic_add_int(p.tie_count + b, 1);
+                            if (slot < MAX_TIES) p.tie_pos[b * MAX_TIES + slot] = i * 4 + q;
+                            e[q] = 1.0f;
+                        } else {
+                            e[q] *= inv;
+                        }
+                        e[q] = apply_epilogue(p.epi, e[q], (static_cast<size_t>(b) * p.per_image4 + i) * 4 + q);
                     }
-                    e[q] = apply_epilogue(p.epi, e[q], static_cast<size_t>(i) * 4 + q);
+                    img4[i] = make_float4(e[0], e[1], e[2], e[3]);
                 }
-                y4[i] = make_float4(e[0], e[1], e[2], e[3]);
             }
         }
     });
