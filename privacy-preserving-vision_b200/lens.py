@@ -493,6 +493,10 @@ class OpticsZernike(nn.Module):
         pad = (n - P) / 2
         pt, pb = int(np.ceil(pad)), int(np.floor(pad))
         fused = P in (64, 128, 256, 512)
+        if not fused and not _lib.load_library().b200cam_supported(n):
+            # patch sizes whose padded transform is not a power of two (the constructor default 368 -> 736): the reference's
+            # own expression on the GPU (torch.fft), so that every constructor-valid geometry runs
+            return GlobalMaxNormalise.apply(self._sensor_torch(img.to(torch.float32), psf, n, pt, pb), self._process_group)
         x = None if fused else TF.pad(img.to(torch.float32), [pt, pb, pt, pb])
         # psf2otf (Utils.py:127-158): pad so that the PSF centre lands on n/2, the kernel's "centred frame"
         if (n - P) % 2 != 0:
@@ -506,6 +510,21 @@ class OpticsZernike(nn.Module):
         # |.|, the [pt+1 : n-pb] crop to (P-1)^2 and the nearest resize back to P (out[i] = crop[max(i-1,0)]) in one pass
         out = CropAbsResize.apply(CircConv.apply(x, k, plan), P, pt + 1, plan)
         return GlobalMaxNormalise.apply(out, self._process_group)
+
+    @staticmethod
+    def _sensor_torch(img: torch.Tensor, psf: torch.Tensor, n: int, pt: int, pb: int) -> torch.Tensor:
+        """img_psf_conv (Utils.py:251-297) as torch ops on the image's device - only for patch sizes the kernels do not cover."""
+        P = img.shape[2]
+        pad = (n - P) / 2
+        lo, hi = (int(np.ceil(pad)), int(np.floor(pad))) if (n - P) % 2 != 0 else (int(pad) + 1, int(pad) - 1)
+        kern = TF.pad(psf[0].permute(2, 0, 1).to(torch.float32), [lo, hi, lo, hi])
+        split = n - (n + 1) // 2
+        order = torch.cat((torch.arange(split, n), torch.arange(split))).to(img.device)
+        otf = torch.fft.fftn(kern[:, order][:, :, order].to(torch.complex64), dim=[-1, -2])
+        x = TF.pad(img, [pt, pb, pt, pb])
+        res = torch.abs(torch.fft.ifftn(torch.fft.fftn(x, dim=[-1, -2]) * otf[None], dim=[-1, -2]))
+        res = res[:, :, pt + 1:n - pb, pt + 1:n - pb]
+        return TF.interpolate(res, size=[P, P], mode="nearest")
 
     # ------------------------------------------------------------------ reference API
     def forward(self, input_img, new_zernike=None, prueba=None, psf_lab=None, enfoco=None):

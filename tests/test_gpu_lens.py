@@ -191,3 +191,33 @@ def test_fused_padded_sensor_matches_oracle(P, B):
     assert rel_l2(out, ref) <= 1e-4
     assert rel_l2(pg.grad, po.grad) <= 1e-3
     assert rel_l2(xg.grad, xo.grad) <= 1e-3
+
+
+def test_constructor_default_geometry_runs():
+    """the constructor defaults (wave 736 -> 1104 = 2^4*3*23 propagation, patch 368 -> 736^2 convolution) are not
+    powers of two: the PSF runs on the generic-radix kernels, the sensor convolution on the reference's torch expression on the
+    GPU; both against the oracle."""
+    wave, patch, terms, B = 736, 368, 8, 2
+    g = torch.Generator().manual_seed(8)
+    img = torch.rand(B, 3, patch, patch, generator=g)
+    img[0, 1, 200, 120] += 3.0
+    w = torch.rand(B, 3, patch, patch, generator=g)
+    coeffs = torch.zeros(terms, 1, 1)
+    coeffs[3], coeffs[5] = -15.0, 0.3
+    dev = torch.device("cuda", 0)
+    cam = OpticsZernike(input_shape=[1, patch, patch, 3], device=dev, zernike_terms=terms, sample_interval=2e-6,
+                        height_tolerance=None).to(dev)                  # wave_resolution / patch_size: the defaults
+    with torch.no_grad():
+        cam.zernike_coeffs_train.copy_(coeffs[3])
+        cam.zernike_coeffs_no_train2.copy_(coeffs[4:])
+    assert cam._constants(dev)["kernels"]
+    sensor, psf, _, _ = cam(img.cuda())
+    (sensor * w.cuda()).sum().backward()
+    cfg = lo.LensConfig(wave_res=wave, patch=patch, sample_interval=2e-6)
+    vol = torch.tensor(zern.zernike_volume(wave, terms, 1e-6).astype(np.float32))
+    cz = coeffs.clone().requires_grad_(True)
+    out = lo.lens_forward(img, cz, vol, cfg)
+    (out["sensor"] * w).sum().backward()
+    assert rel_l2(psf, out["psf"]) <= 1e-4
+    assert rel_l2(sensor, out["sensor"]) <= 1e-4
+    assert abs(float(cam.zernike_coeffs_train.grad) - float(cz.grad[3])) <= 1e-3 * abs(float(cz.grad[3]))
