@@ -773,12 +773,13 @@ static int accum_chunks(int N, int B) {
 }
 
 struct PsfWs {
-    float2* st; float* I; float* gtot; float* part_rows; float* part_ew; int* arrive; unsigned* bar;
+    float2* st; float* I; float* gtot; float* part_rows; float* part_ew; int* arrive; unsigned* bar; float2* otf_rows;
     size_t bytes;
     PsfWs(void* p, int N) {
         Carver c(p);
         const size_t NN = static_cast<size_t>(N) * N;
         st = c.take<float2>(3 * NN);
+        otf_rows = c.take<float2>(3 * static_cast<size_t>(N / 2 + 1) * N);   // row spectra of |U|^2, written by the inverse-row kernel
         I = c.take<float>(3 * NN);
         gtot = c.take<float>(3 * NN);
         part_rows = c.take<float>(3 * N);
@@ -876,6 +877,11 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 // launch sequences
 // ------------------------------------------------------------------------------------------
 // first part of the PSF synthesis: pupil -> propagated field U, |U|^2 (workspace) and S = sum |U|^2 (stats[0])
+// B200CAM_OTF_ROWS=0: the OTF's row transform as a kernel of its own (k_rows_r2c on the 3 planes) instead of inside k_crows_inv
+static bool fuse_otf_rows() {
+    static const bool on = [] { const char* e = getenv("B200CAM_OTF_ROWS"); return !(e && e[0] == '0'); }();
+    return on;
+}
 template <int N>
 static int psf_field_impl(const float* h, const float2* A, const float2* Ht, const float* kappa, float2* field,
                           void* ws_ptr, cudaStream_t s, cudaStream_t dependent = nullptr, bool has_dependent = false) {
@@ -900,7 +906,7 @@ static int psf_field_impl(const float* h, const float2* A, const float2* Ht, con
         CColsMixParams{ws.st, Ht, tw, 0, 1.0f / (3.0f * N * N)});
     LAUNCH_CHECK();
     launch_k(Pdl{}, k_crows_inv<N, IntensityEpilogue>, rgrid, CRowsSmem<N>::THREADS, CRowsSmem<N>::BYTES, s, 
-        CRowsInvParams{ws.st, tw}, IntensityEpilogue{field, ws.I, ws.part_rows, ws.arrive, N});
+        CRowsInvParams{ws.st, tw}, IntensityEpilogue{field, ws.I, ws.part_rows, ws.arrive, N, fuse_otf_rows() ? ws.otf_rows : nullptr});
     LAUNCH_CHECK();
     return 0;
 }
@@ -985,6 +991,18 @@ static int otf_impl(const float* src, float2* otf, const float2* tw, float scale
     const int total = 3 * T::NC;
     launch_k(Pdl{}, k_cols_fwd<N>, (total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s, 
         ColsFwdParams{otf, tw, total, 1, scale, sum_partials, npartials});
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// column half of the OTF alone: the row spectra were written by k_crows_inv (IntensityEpilogue::otf_rows)
+template <int N>
+static int otf_cols_impl(const float2* rows, float2* otf, const float2* tw, float scale, cudaStream_t s, const float* sum_partials,
+                         int npartials) {
+    using T = Tile<N>;
+    const int total = 3 * T::NC;
+    launch_k(Pdl{}, k_cols_fwd<N>, (total + T::COLS - 1) / T::COLS, ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s,
+        ColsFwdParams{otf, tw, total, 1, scale, sum_partials, npartials, rows});
     LAUNCH_CHECK();
     return 0;
 }
@@ -1652,6 +1670,11 @@ int b200cam_psf_otf_early(float* otf, void* workspace, size_t workspace_bytes, i
     const float2* tw = twiddle(N);
     if (tw == nullptr) return B200CAM_E_NOT_INIT;
     // |U|^2 / S is the PSF: the OTF does not have to wait for psf_finish to write it out
+    if (fuse_otf_rows()) {
+        DISPATCH_N(N, (otf_cols_impl<NN_>(PsfWs(workspace, NN_).otf_rows, reinterpret_cast<float2*>(otf), tw,
+                                          1.0f / (static_cast<float>(NN_) * NN_), s, PsfWs(workspace, NN_).part_rows,
+                                          3 * (NN_ / Tile<NN_>::CROWS))));
+    }
     DISPATCH_N(N, (otf_impl<NN_>(PsfWs(workspace, NN_).I, reinterpret_cast<float2*>(otf), tw,
                                  1.0f / (static_cast<float>(NN_) * NN_), s, PsfWs(workspace, NN_).part_rows,
                                  3 * (NN_ / Tile<NN_>::CROWS))));

@@ -380,6 +380,7 @@ struct ColsFwdParams {
     // does not have to wait for psf_finalise.  Every CTA adds the same values in the same order.
     const float* sum_partials;
     int npartials;
+    const float2* in = nullptr;   // nullable: read the columns from here instead of `st` (out of place)
 };
 
 template <int N, class Exec>
@@ -409,7 +410,7 @@ B200_HD void cols_fwd_body(Exec& ex, const ColsFwdParams& p, float2* smem) {
         const int jc = tid / P::LANES, a = tid % P::LANES;
         const int col = col0 + jc;
         if (col < p.total_cols && a < P::R2) {
-            const float2* src = p.st + static_cast<size_t>(col) * N;
+            const float2* src = (p.in != nullptr ? p.in : p.st) + static_cast<size_t>(col) * N;
             float2 v[P::R1];
 #pragma unroll
             for (int i = 0; i < P::R1; ++i) v[i] = src[P::R2 * i + a];
@@ -1513,6 +1514,10 @@ struct IntensityEpilogue {
     float* partial;     // [3][N/CROWS]
     int* arrive;        // counter of psf_finalise, zeroed here (it runs next in the stream)
     int N;
+    // nullable [3][NC][N]: the CTA also row-transforms its rows of |U|^2 (pairs of real rows as one complex transform) into the
+    // transposed half spectrum the OTF's column pass starts from - the first half of rfft2(psf) (Utils.py:9) without a kernel
+    // of its own in the latency chain of the step's head
+    float2* otf_rows = nullptr;
     B200_HD float operator()(int l, int y, int x, float2 v) const {
         const size_t i = (static_cast<size_t>(l) * N + y) * N + x;
         U[i] = v;
@@ -1535,6 +1540,7 @@ B200_HD void crows_inv_body(Exec& ex, const CRowsInvParams& p, const Epi& epi, f
     const int y0 = tile * T::CROWS;
     float2* E = smem + S::E_OFF;
     float2* F = smem + S::F_OFF;
+    float* Irow = reinterpret_cast<float*>(F);                     // [CROWS][N] intensities (OTF row transform)
     float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
     ex.phase([&](int tid) {
         constexpr int ITEMS = T::CROWS * N / S::THREADS;         // loads first, stores after (latency chain)
@@ -1566,10 +1572,48 @@ B200_HD void crows_inv_body(Exec& ex, const CRowsInvParams& p, const Epi& epi, f
             float2 v[P::R1];
             P::stepD(v, a, E + j * P::E_SIZE);
 #pragma unroll
-            for (int i = 0; i < P::R1; ++i) s += epi(l, y0 + j, P::R2 * i + a, v[i]);
+            for (int i = 0; i < P::R1; ++i) {
+                const float in = epi(l, y0 + j, P::R2 * i + a, v[i]);
+                s += in;
+                if (epi.otf_rows != nullptr) Irow[j * N + P::R2 * i + a] = in;     // F is free: phase 2 consumed it
+            }
         }
         red[tid] = s;
     });
+    if (epi.otf_rows != nullptr) {
+        // rows (2jp, 2jp+1) of |U|^2 as ONE complex transform, un-mixed by Hermitian symmetry - as K1 (rows_r2c) does
+        constexpr int PAIRS = T::CROWS / 2;
+        static_assert(T::CROWS % 2 == 0, "row pairs");
+        ex.phase([&](int tid) {
+            const int jp = tid / P::LANES, a = tid % P::LANES;
+            if (jp < PAIRS && a < P::R2) {
+                float2 v[P::R1];
+#pragma unroll
+                for (int i = 0; i < P::R1; ++i)
+                    v[i] = make_float2(Irow[(2 * jp) * N + P::R2 * i + a], Irow[(2 * jp + 1) * N + P::R2 * i + a]);
+                P::stepA(v, a, E + jp * P::E_SIZE, p.tw);
+            }
+        });
+        ex.phase([&](int tid) {
+            const int jp = tid / P::LANES, b = tid % P::LANES;
+            if (jp < PAIRS && b < P::R1) {
+                float2 q[P::R2];
+                P::stepB(q, b, E + jp * P::E_SIZE);
+#pragma unroll
+                for (int i = 0; i < P::R2; ++i) F[jp * N + b + P::R1 * i] = q[i];     // the intensities are consumed: reuse F
+            }
+        });
+        ex.phase([&](int tid) {
+            for (int w = tid; w < PAIRS * T::NC; w += S::THREADS) {
+                const int u = w / PAIRS, jp = w % PAIRS;
+                const float2 z1 = F[jp * N + u];
+                const float2 z2 = F[jp * N + ((N - u) & (N - 1))];
+                const float4 o = make_float4(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y),    // row 2jp
+                                             0.5f * (z1.y + z2.y), -0.5f * (z1.x - z2.x));  // row 2jp + 1
+                *reinterpret_cast<float4*>(epi.otf_rows + (static_cast<size_t>(l) * T::NC + u) * N + y0 + 2 * jp) = o;
+            }
+        });
+    }
     ex.phase([&](int tid) {
         if (tid == 0) {
             float s = 0.f;
