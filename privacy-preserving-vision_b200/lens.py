@@ -358,6 +358,13 @@ class OpticsZernike(nn.Module):
             self._frozen_key = key
         return self._frozen_sum + self._project_one(self.zernike_coeffs_train.reshape(1, 1, 1), vol[3:4])
 
+    def invalidate_cache(self) -> None:
+        """Drop the cached partial sum of the frozen Zernike terms.  In-place updates of the frozen parameters and
+        ``load_state_dict`` are detected through the tensors' version counters; writes through ``param.data`` are not -
+        call this after such a write."""
+        self._frozen_key = None
+        self._frozen_sum = None
+
     def _project_one(self, coef: torch.Tensor, plane: torch.Tensor) -> torch.Tensor:
         if plane.dtype == torch.float32 and plane.is_contiguous() and plane[0].numel() % 4 == 0:
             return F.zernike_project(coef, plane, self._plan(plane.device, 256))
