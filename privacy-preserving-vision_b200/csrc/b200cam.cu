@@ -1325,18 +1325,29 @@ static int sensor_bwd_impl(const float* g, const float* img, const float* sensor
     LAUNCH_CHECK();
     const int nchunks = accum_chunks(N, B);
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
+    // arg-max term of the amax backward: the spatial gather kernel k_tie_term after the inverse rows (default), or folded into
+    // k_cols_reduce_inv in the (u, y) domain (B200CAM_TIE_SPECTRAL=1: one launch less, no 17 MB gather - but the staging of the
+    // tie list inside that kernel is a chain of dependent loads: measured 17.7 us against 5.7 + 10.6 us, step 168.6-174 us
+    // against 165.8-171.5 us, so it stays opt-in; the CPU emulator runs this form)
+    static const int tie_spectral = [] { const char* e = getenv("B200CAM_TIE_SPECTRAL"); return e ? atoi(e) : 0; }();
+    const int dot_count = colgroups * ColsSmem<N>::WARPS;
+    const bool spectral = tie_spectral != 0 && static_cast<size_t>(dot_count) <= static_cast<size_t>(3) * T::NC * 32;
+    float* dot_warps = spectral ? ws.dot_lanes : nullptr;          // the same workspace slice, [B][colgroups][WARPS]
     launch_k(k_cols_accum<N>, dim3(colgroups, nchunks), ColsSmem<N>::THREADS, ColsSmem<N>::BYTES, s, 
         ColsAccumParams{srow, ws.stg, ws.partial, tw, img_max, otf, ws.dot_lanes, B, nchunks,
-                        grad_img == nullptr ? [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }() : 0});
+                        grad_img == nullptr ? [] { const char* e = getenv("B200CAM_DISCARD"); return e ? atoi(e) : 1; }() : 0, dot_warps});
     LAUNCH_CHECK();
-    launch_k(Pdl{}, k_cols_reduce_inv<N>, 3 * T::NC + B, ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s, 
+    // the side-job CTAs (coef[b]) are only needed by the spatial kernels: k_tie_term, and k_tie_term_img of the optional dL/dimg
+    const bool side_job = !spectral || grad_img != nullptr;
+    launch_k(Pdl{}, k_cols_reduce_inv<N>, 3 * T::NC + (side_job ? B : 0), ReduceInvSmem<N>::THREADS, ReduceInvSmem<N>::BYTES, s, 
         ColsReduceInvParams{ws.partial, ws.stp, tw, nchunks, 1.0f / (static_cast<float>(N) * N),
-                            ws.dot_lanes, img_max, tie_count, ws.coef, B, img, tie_pos});
+                            side_job ? ws.dot_lanes : nullptr, img_max, tie_count, ws.coef, B, spectral ? nullptr : img, tie_pos,
+                            spectral ? srow : nullptr, dot_warps, dot_count});
     LAUNCH_CHECK();
     launch_k(Pdl{}, k_rows_c2r<N>, dim3(tiles, 3), RowsR2CSmem<N>::THREADS, RowsR2CSmem<N>::BYTES, s, 
         RowsC2RParams{ws.stp, grad_psf, tw, nullptr, 1.0f});
     LAUNCH_CHECK();
-    {   // arg-max term of the amax backward (spatial form), ties of channel c handled by the CTAs of row c
+    if (!spectral) {   // arg-max term of the amax backward (spatial form), ties of channel c handled by the CTAs of row c
         const int per_ch = N * N / 2 / EW_THREADS < 592 ? N * N / 2 / EW_THREADS : 592;   // two adjacent pixels per thread
         launch_k(Pdl{}, k_tie_term, dim3(per_ch, 3), EW_THREADS, 0, s, TieTermParams{grad_psf, img, tie_count, tie_pos, ws.coef, B, N});
         LAUNCH_CHECK();

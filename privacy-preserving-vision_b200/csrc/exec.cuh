@@ -212,6 +212,12 @@ struct DeviceExec {
         if ((tid & 31) == 0) red[tid >> 5] = v;
     }
     __device__ __forceinline__ int staged(int nthreads) const { return nthreads / 32; }
+    // sum over the warp (fixed tree), lane 0 stores; every lane of the warp must call it
+    __device__ __forceinline__ void warp_sum_store(float v, float* dst, int tid) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) *dst = v;
+    }
     __device__ __forceinline__ void report(unsigned code) { if (err != nullptr) atomicExch(err, code); }
 };
 // A "virtual block" of a cooperative kernel: the CTA plays block (vbx, vby) of a body written for
@@ -288,6 +294,10 @@ struct HostExec {
     bool key_wait(const unsigned*, int, unsigned, unsigned, float* out) { *out = 1.f; return true; }
     void stage_max(float v, float* red, int tid) { red[tid] = v; }
     int staged(int nthreads) const { return nthreads; }
+    void warp_sum_store(float v, float* dst, int tid) {       // the phase loop visits the lanes of a warp in order
+        if ((tid & 31) == 0) *dst = 0.f;
+        *dst += v;
+    }
     void report(unsigned) {}
 };
 

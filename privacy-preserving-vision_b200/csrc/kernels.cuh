@@ -882,6 +882,9 @@ struct ColsAccumParams {
     int B;
     int nchunks;            // = gridDim.y: chunk y owns images [B*y/nchunks, B*(y+1)/nchunks) (balanced split)
     int discard_stg;        // stg is dead after this pass: drop its lines from L2 instead of writing them back
+    // nullable [B][gridDim.x][WARPS]: the Parseval partials summed over each warp (one store per warp and image instead of one
+    // per thread) - what the spectral arg-max term of K7 reads; dot_lanes is not written then
+    float* dot_warps = nullptr;
 };
 
 template <int N>
@@ -970,6 +973,7 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
             if constexpr (S::STAGED_ACCUM) {
                 if (b + 1 < b1) fetch(tid, b + 1);   // both slices are consumed (warp sync above): refill them
             }
+            float dpart = 0.f;
             if (cu < TOTAL && bb < P::R1) {
                 AccumState<N>& s = st[ex.slot(tid)];
                 const float inv_m = p.img_max != nullptr ? 1.0f / ld_ro(p.img_max + b) : 1.0f;
@@ -992,9 +996,12 @@ B200_HD void cols_accum_body(Exec& ex, const ColsAccumParams& p, float2* smem, A
                 if (p.otf != nullptr) {
                     const int u = cu % T::NC;
                     const float wt = (u == 0 || u == N / 2) ? 1.0f : 2.0f;
-                    p.dot_lanes[(static_cast<size_t>(b) * TOTAL + cu) * P::R1 + bb] = wt * (d2.x + d2.y);
+                    dpart = wt * (d2.x + d2.y);
+                    if (p.dot_warps == nullptr) p.dot_lanes[(static_cast<size_t>(b) * TOTAL + cu) * P::R1 + bb] = dpart;
                 }
             }
+            if (p.otf != nullptr && p.dot_warps != nullptr)      // every lane of the warp: a CTA's tail columns contribute 0
+                ex.warp_sum_store(dpart, p.dot_warps + (static_cast<size_t>(b) * ((TOTAL + S::COLS - 1) / S::COLS) + ex.bx()) * S::WARPS + tid / 32, tid);
         });
     }
     ex.warp_phase([&](int tid) {
@@ -1031,7 +1038,17 @@ struct ColsReduceInvParams {
     // were last read a whole step ago)
     const float* x = nullptr;        // nullable [B][3][N][N]
     const int* tie_pos = nullptr;    // [B][MAX_TIES]
+    // Arg-max term of the amax backward folded into this pass (srow != nullptr; replaces K8 tie_term and its launch):
+    //   gpsf[c][p] -= sum_t coef_t x_b[c][(p*_t - p + N/2) mod N]
+    // is, after the row transform in x and BEFORE the one in y, a flipped copy of the image's own row-spectrum column:
+    //   st[c][u][y'] -= scale N coef_t (-1)^u e^{-2 pi i u px_t / N} conj( X~_b[c][u][(py_t + N/2 - y') mod N] )
+    // (X~ = srow, the row spectra kept from the forward) - no transform, 8 contiguous bytes per tie and output element.
+    // coef_t comes from the warp partials of K6 (dot_warps), summed in a fixed order by the thread that stages the tie.
+    const float2* srow = nullptr;    // nullable [B*3][NC][N]
+    const float* dot_warps = nullptr;   // [B][dot_count]
+    int dot_count = 0;
 };
+constexpr int RINV_PASS = 64;        // images staged per pass of the tie list (<= RINV_PASS * MAX_TIES entries)
 
 // grid 3*NC (one spectral column per CTA), block N (thread = v): the chunk sum is spread over N threads with
 // coalesced 8N-byte reads; the first LANES threads then run the inverse transform of the column.
@@ -1039,7 +1056,10 @@ struct ColsReduceInvParams {
 template <int N>
 struct ReduceInvSmem {
     static constexpr int THREADS = N;
-    static constexpr int FLOAT2S = N + Plan<N>::E_SIZE;
+    static constexpr int TIE_OFF = N + Plan<N>::E_SIZE;                       // float2 units
+    // tie list of one pass: per entry {coef * phase (float2), image, source row} + per image {count, coef}
+    static constexpr int TIE_FLOAT2S = RINV_PASS * 8 * 2 + RINV_PASS + 2;      // ... + per image {count, sum(g conv)} as 2 x 4 bytes
+    static constexpr int FLOAT2S = TIE_OFF + TIE_FLOAT2S;
     static constexpr int BYTES = FLOAT2S * 8;
 };
 
@@ -1055,7 +1075,7 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
     if (cu >= TOTAL) {
         // extra CTAs (grid = 3*NC + B when dot_lanes is given): CTA TOTAL + b reduces image b's Parseval partials, beside -
         // not in front of - the column work of the other CTAs
-        constexpr int PER_IMAGE = TOTAL * P::R1;
+        const int PER_IMAGE = p.dot_warps != nullptr ? p.dot_count : TOTAL * P::R1;
         float* red = reinterpret_cast<float*>(E);
         const int b = cu - TOTAL;
         if (p.x != nullptr && p.tie_pos != nullptr) {
@@ -1069,7 +1089,7 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
             });
         }
         ex.phase([&](int t) {
-            const float* src = p.dot_lanes + static_cast<size_t>(b) * PER_IMAGE;
+            const float* src = (p.dot_warps != nullptr ? p.dot_warps : p.dot_lanes) + static_cast<size_t>(b) * PER_IMAGE;
             float s = 0.f;
             int i = t;
             for (; i + 7 * N < PER_IMAGE; i += 8 * N) {              // eight loads in flight; fixed order: deterministic
@@ -1100,18 +1120,115 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
         });
         return;
     }
+    // ---- arg-max term (see ColsReduceInvParams::srow): its staging runs INSIDE the phases of the column work ----
+    using RS = ReduceInvSmem<N>;
+    const bool spectral = p.srow != nullptr && p.dot_warps != nullptr && p.tie_pos != nullptr;
+    const int c = cu / T::NC;
+    float2* t_w = smem + RS::TIE_OFF;                                            // [PASS*8] coef * phase
+    int* t_meta = reinterpret_cast<int*>(smem + RS::TIE_OFF + RINV_PASS * 8);    // [PASS*8][2] image, source row
+    int* t_cnt = reinterpret_cast<int*>(smem + RS::TIE_OFF + RINV_PASS * 8 * 2); // [PASS + 1] ties of this channel per image
+    float* t_sdot = reinterpret_cast<float*>(t_cnt + RINV_PASS + 1);             // [PASS] sum(g_b conv_b)
+    float2 acc = make_float2(0.f, 0.f);                                          // thread y' (device: lives across the passes)
+    float2 acc_host[Exec::IS_HOST ? N : 1];
+    if constexpr (Exec::IS_HOST)
+        for (int i = 0; i < N; ++i) acc_host[i] = make_float2(0.f, 0.f);
+    // (1) ties of this channel per image of the pass
+    auto tie_count = [&](int t, int b0, int nb) {
+        for (int i = t; i < nb; i += N) {
+            const int b = b0 + i;
+            const int n = p.tie_count[b] < C2R_MAX_TIES ? p.tie_count[b] : C2R_MAX_TIES;
+            int cnt = 0;
+            for (int k = 0; k < n; ++k) cnt += (p.tie_pos[b * C2R_MAX_TIES + k] / (N * N) == c) ? 1 : 0;
+            t_cnt[i] = cnt;
+        }
+    };
+    // (2) sum(g_b * conv_b) of the images that have an arg-max here: one warp per image, the lanes stride over the warp
+    //     partials of K6, fixed shuffle tree (a single thread adding them one after the other pays a load latency each)
+    auto tie_sdot = [&](int t, int b0, int nb) {
+        constexpr int NW = N / 32 > 0 ? N / 32 : 1;
+        for (int i = t / 32; i < nb; i += NW) {
+            if (t_cnt[i] == 0) continue;                                        // uniform over the warp
+            const float* d = p.dot_warps + static_cast<size_t>(b0 + i) * p.dot_count;
+            float part = 0.f;
+            for (int q0 = t % 32; q0 < p.dot_count; q0 += 8 * 32) {             // eight loads in flight per lane, fixed order
+                float vals[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) vals[k] = q0 + 32 * k < p.dot_count ? ld_ro(d + q0 + 32 * k) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) part += vals[k];
+            }
+            ex.warp_sum_store(part, t_sdot + i, t);
+        }
+    };
+    // (3) the list {coef * phase, image, source row}; ordered by image: the sum order is fixed
+    auto tie_list = [&](int t, int b0, int nb) {
+        for (int i = t; i < nb; i += N) {
+            if (t_cnt[i] == 0) continue;
+            int k0 = 0;
+            for (int q = 0; q < i; ++q) k0 += t_cnt[q];
+            const int b = b0 + i;
+            const int nt = p.tie_count[b] > 0 ? p.tie_count[b] : 1;
+            const float m = ld_ro(p.img_max + b);
+            const float coef = t_sdot[i] / (static_cast<float>(nt) * m * m) * p.scale * static_cast<float>(N);
+            const int n = p.tie_count[b] < C2R_MAX_TIES ? p.tie_count[b] : C2R_MAX_TIES;
+            for (int k = 0; k < n; ++k) {
+                const int pos = p.tie_pos[b * C2R_MAX_TIES + k];
+                if (pos / (N * N) != c) continue;
+                const int py = (pos % (N * N)) / N, px = pos % N;
+                const float2 ph = ld_ro(p.tw + ((u * px) & (N - 1)));              // e^{-2 pi i u px / N}
+                const float sg = (u & 1) ? -coef : coef;
+                t_w[k0] = make_float2(sg * ph.x, sg * ph.y);
+                t_meta[2 * k0] = b;
+                t_meta[2 * k0 + 1] = (py + N / 2) & (N - 1);
+                ++k0;
+            }
+        }
+        if (t == 0) {
+            int tot = 0;
+            for (int q = 0; q < nb; ++q) tot += t_cnt[q];
+            t_cnt[RINV_PASS] = tot;
+        }
+    };
+    // (4) thread y': the listed row-spectrum columns, flipped; eight gathers in flight, fixed order
+    auto tie_gather = [&](int y) {
+        const int tot = t_cnt[RINV_PASS];
+        float2 a2 = Exec::IS_HOST ? acc_host[Exec::IS_HOST ? y : 0] : acc;
+        constexpr int G = 12;                      // gathers in flight per thread
+        for (int e0 = 0; e0 < tot; e0 += G) {
+            // Unconditional loads (clamped index) and unconditional FMAs (zero weight past the end): a conditional use lets
+            // the compiler sink each load next to its use - measured: 4 of 8 loads exposed their full latency one by one
+            float2 xs[G], ws[G];
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                const int e = e0 + k < tot ? e0 + k : tot - 1;
+                xs[k] = ld_ro(p.srow + (static_cast<size_t>(t_meta[2 * e] * 3 + c) * T::NC + u) * N + ((t_meta[2 * e + 1] - y) & (N - 1)));
+                const float2 w = t_w[e];
+                ws[k] = e0 + k < tot ? w : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < G; ++k) {                                       // w * conj(xs)
+                a2.x += ws[k].x * xs[k].x + ws[k].y * xs[k].y;
+                a2.y += ws[k].y * xs[k].x - ws[k].x * xs[k].y;
+            }
+        }
+        if constexpr (Exec::IS_HOST) acc_host[Exec::IS_HOST ? y : 0] = a2;
+        else acc = a2;
+    };
+    const int nb0 = p.B < RINV_PASS ? p.B : RINV_PASS;
+
     ex.phase([&](int v) {
         const float2* src = p.partial + static_cast<size_t>(cu) * N + v;
         const size_t step = static_cast<size_t>(TOTAL) * N;
         float2 s = make_float2(0.f, 0.f);
-        int ch = 0;
-        for (; ch + 4 <= p.nchunks; ch += 4) {          // fixed order: deterministic
-            const float2 t0 = ld_ro(src + (ch + 0) * step), t1 = ld_ro(src + (ch + 1) * step);
-            const float2 t2 = ld_ro(src + (ch + 2) * step), t3 = ld_ro(src + (ch + 3) * step);
-            s = cadd(cadd(cadd(cadd(s, t0), t1), t2), t3);
+        for (int ch0 = 0; ch0 < p.nchunks; ch0 += 8) {   // eight chunk loads in flight; fixed order: deterministic
+            float2 tv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tv[k] = ch0 + k < p.nchunks ? ld_ro(src + (ch0 + k) * step) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = cadd(s, tv[k]);
         }
-        for (; ch < p.nchunks; ++ch) s = cadd(s, ld_ro(src + ch * step));
         line[v] = cscale(s, ((u + v) & 1) ? -p.scale : p.scale);
+        if (spectral) tie_count(v, 0, nb0);
     });
     ex.phase([&](int b) {
         if (b < P::R1) {
@@ -1120,15 +1237,31 @@ B200_HD void cols_reduce_inv_body(Exec& ex, const ColsReduceInvParams& p, float2
             for (int i = 0; i < P::R2; ++i) q[i] = line[b + P::R1 * i];
             P::stepC(q, b, E, p.tw);
         }
+        if (spectral) tie_sdot(b, 0, nb0);
     });
     ex.phase([&](int a) {
         if (a < P::R2) {
             float2 q[P::R1];
             P::stepD(q, a, E);
-            float2* dst = p.st + static_cast<size_t>(cu) * N;
+            float2* dst = spectral ? line : p.st + static_cast<size_t>(cu) * N;     // spectral: the tie term is subtracted first
 #pragma unroll
             for (int i = 0; i < P::R1; ++i) dst[P::R2 * i + a] = q[i];
         }
+        if (spectral) tie_list(a, 0, nb0);
+    });
+    if (!spectral) return;
+    ex.phase([&](int y) { tie_gather(y); });
+    for (int b0 = RINV_PASS; b0 < p.B; b0 += RINV_PASS) {       // further passes (batches above RINV_PASS images)
+        const int nb = p.B - b0 < RINV_PASS ? p.B - b0 : RINV_PASS;
+        ex.phase([&](int t) { tie_count(t, b0, nb); });
+        ex.phase([&](int t) { tie_sdot(t, b0, nb); });
+        ex.phase([&](int t) { tie_list(t, b0, nb); });
+        ex.phase([&](int y) { tie_gather(y); });
+    }
+    ex.phase([&](int y) {
+        const float2 a2 = Exec::IS_HOST ? acc_host[Exec::IS_HOST ? y : 0] : acc;
+        const float2 v = line[y];
+        p.st[static_cast<size_t>(cu) * N + y] = make_float2(v.x - a2.x, v.y - a2.y);
     });
 }
 

@@ -130,28 +130,26 @@ int sensor_bwd_impl(int B, const float* g, const float* img, const float* sensor
     });
     const int colgroups = (3 * T::NC + T::COLS - 1) / T::COLS;
     std::vector<AccumState<N>> states(ColsSmem<N>::THREADS);
+    // the arg-max term of the amax backward is folded into cols_reduce_inv (spectral form, the library's default): the warp
+    // partials of the Parseval dot product replace the per-thread ones, the spatial tie_term kernel is not run
+    const int dot_count = colgroups * ColsSmem<N>::WARPS;
+    std::vector<float> dot_warps(static_cast<size_t>(B) * dot_count);
     grid2(colgroups, used_chunks, ColsSmem<N>::THREADS, [&](HostExec& ex) {
         cols_accum_body<N>(ex, ColsAccumParams{srow, stg.data(), partial.data(), tw.data(), img_max, otf,
-                                               dot_lanes.data(), B, nchunks}, smem.data(), states.data());
+                                               dot_lanes.data(), B, nchunks, 0, dot_warps.data()}, smem.data(), states.data());
     });
     std::vector<float2> rsmem(ReduceInvSmem<N>::FLOAT2S);
-    grid2(3 * T::NC + B, 1, ReduceInvSmem<N>::THREADS, [&](HostExec& ex) {
+    const bool side_job = grad_img != nullptr;
+    grid2(3 * T::NC + (side_job ? B : 0), 1, ReduceInvSmem<N>::THREADS, [&](HostExec& ex) {
         cols_reduce_inv_body<N>(ex, ColsReduceInvParams{partial.data(), stp.data(), tw.data(), used_chunks,
-                                                        1.0f / (static_cast<float>(N) * N), dot_lanes.data(), img_max,
-                                                        tie_count, coef.data(), B}, rsmem.data());
+                                                        1.0f / (static_cast<float>(N) * N), side_job ? dot_lanes.data() : nullptr, img_max,
+                                                        tie_count, coef.data(), B, nullptr, tie_pos, srow, dot_warps.data(), dot_count},
+                                rsmem.data());
     });
     grid2(tiles, 3, RowsR2CSmem<N>::THREADS, [&](HostExec& ex) {
         rows_c2r_body<N>(ex, RowsC2RParams{stp.data(), grad_psf, tw.data(), nullptr, 1.0f}, smem.data());
     });
-    {
-        const int per_ch = N * N / 2 / EW_THREADS < 592 ? N * N / 2 / EW_THREADS : 592;   // two adjacent pixels per thread
-        std::vector<float> s_coef(TIE_PASS * MAX_TIES);
-        std::vector<int> s_meta(3 * TIE_PASS * MAX_TIES), s_cnt(TIE_PASS + 1);
-        grid2(per_ch, 3, EW_THREADS, [&](HostExec& ex) {
-            tie_term_body(ex, TieTermParams{grad_psf, img, tie_count, tie_pos, coef.data(), B, N}, per_ch, s_coef.data(),
-                          s_meta.data(), s_cnt.data());
-        });
-    }
+    (void)img;
     if (grad_img != nullptr) {
         const int cchunks = conv_chunks(N, B);
         std::vector<ConvState<N>> cst(ColsSmem<N>::THREADS);
