@@ -1342,10 +1342,11 @@ B200_HD void tie_term_body(Exec& ex, const TieTermParams& p, int grid_x, float* 
                         }
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
-                            if (e + q < k) {
-                                acc0 += s_coef[e + q] * v0[q];
-                                acc1 += s_coef[e + q] * v1[q];
-                            }
+                            // unconditional FMAs (zero weight past the end): with a conditional use the compiler sinks each
+                            // load next to its use and the gathers expose their latency one by one (seen in SASS, round 2)
+                            const float cf = e + q < k ? s_coef[e + q] : 0.f;
+                            acc0 += cf * v0[q];
+                            acc1 += cf * v1[q];
                         }
                     }
                     float2* dst = reinterpret_cast<float2*>(p.gpsf + c * NN + py * N + px);
