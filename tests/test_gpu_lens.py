@@ -221,3 +221,45 @@ def test_constructor_default_geometry_runs():
     assert rel_l2(psf, out["psf"]) <= 1e-4
     assert rel_l2(sensor, out["sensor"]) <= 1e-4
     assert abs(float(cam.zernike_coeffs_train.grad) - float(cz.grad[3])) <= 1e-3 * abs(float(cz.grad[3]))
+
+
+def test_caption_camera_step_is_graph_capturable():
+    """Forward + backward of the caption camera captured in a CUDA graph (no host sync, no allocation outside the graph pool
+    in any b200cam_lens_* call) replays to the eager result."""
+    wave, patch, terms, B = 128, 64, 10, 3
+    dev = torch.device("cuda", 0)
+    cam = OpticsZernike(input_shape=[1, patch, patch, 3], device=dev, wave_resolution=(wave, wave), patch_size=patch,
+                        sample_interval=3e-6, zernike_terms=terms, height_tolerance=None).to(dev)
+    with torch.no_grad():
+        cam.zernike_coeffs_train.fill_(-0.45)
+    g = torch.Generator().manual_seed(12)
+    img = torch.rand(B, 3, patch, patch, generator=g).to(dev)
+    img[1, 0, 30, 21] += 4.0
+    w = torch.rand(B, 3, patch, patch, generator=g).to(dev)
+    out = {}
+
+    def step():
+        cam.zernike_coeffs_train.grad = None
+        sensor, psf, _, _ = cam(img)
+        torch.autograd.backward([sensor], [w])
+        out["sensor"] = sensor
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+        eager_y, eager_g = out["sensor"].detach().clone(), cam.zernike_coeffs_train.grad.clone()
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    out.clear()
+    cam.zernike_coeffs_train.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    y_static = out["sensor"]
+    for _ in range(2):
+        cam.zernike_coeffs_train.grad.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert rel_l2(y_static, eager_y) <= 1e-6
+        assert abs(float(cam.zernike_coeffs_train.grad) - float(eager_g)) <= 1e-5 * abs(float(eager_g))
