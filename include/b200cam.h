@@ -79,6 +79,13 @@ size_t b200cam_zernike_workspace_bytes(int T, long long NN);
 int b200cam_zernike_fwd(const float* coef, const float* Z, float* h, void* workspace, size_t workspace_bytes, int T,
                         long long NN, void* stream);
 int b200cam_zernike_bwd(const float* grad_h, const float* Z, float* grad_coef, int T, long long NN, void* stream);
+/* The same with the support of the basis: `active` (device, nactive ints, ascending) lists the float4 positions - index into
+ * [NN/4] - at which at least one Z_j is non-zero.  The Zernike basis is zero outside the unit disc (21 % of the square): only
+ * the listed positions are read, h is zero elsewhere.  NULL = every position (the calls above). */
+int b200cam_zernike_fwd_ex(const float* coef, const float* Z, float* h, void* workspace, size_t workspace_bytes, int T,
+                           long long NN, void* stream, const int* active, int nactive);
+int b200cam_zernike_bwd_ex(const float* grad_h, const float* Z, float* grad_coef, int T, long long NN, void* stream,
+                           const int* active, int nactive);
 
 /* PSF synthesis, forward.  Replaces Camera.get_psf + the regularisers
  * (Face-DeId/Camera/Optics.py:89-120 and :124-125):

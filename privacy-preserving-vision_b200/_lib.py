@@ -43,6 +43,9 @@ _SIGNATURES = {
     "b200cam_zernike_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_longlong]),
     "b200cam_zernike_fwd": (ctypes.c_int, [_f, _f, _f, _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p]),
     "b200cam_zernike_bwd": (ctypes.c_int, [_f, _f, _f, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p]),
+    "b200cam_zernike_fwd_ex": (ctypes.c_int, [_f, _f, _f, _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p,
+                                              _f, ctypes.c_int]),
+    "b200cam_zernike_bwd_ex": (ctypes.c_int, [_f, _f, _f, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, _f, ctypes.c_int]),
     "b200cam_psf_field": (ctypes.c_int, [_f, _f, _f, ctypes.POINTER(ctypes.c_float), _f,
                                          _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "b200cam_psf_otf_early": (ctypes.c_int, [_f, _f, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),

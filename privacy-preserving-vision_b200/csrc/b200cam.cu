@@ -1615,48 +1615,63 @@ size_t b200cam_zernike_workspace_bytes(int T, long long NN) {
     return static_cast<size_t>(zernike_ks(T, NN4)) * NN4 * sizeof(float4) + static_cast<size_t>(xblocks) * sizeof(int) + 256;
 }
 
-int b200cam_zernike_fwd(const float* coef, const float* Z, float* h, void* workspace, size_t workspace_bytes, int T,
-                        long long NN, void* stream) {
+int b200cam_zernike_fwd_ex(const float* coef, const float* Z, float* h, void* workspace, size_t workspace_bytes, int T,
+                           long long NN, void* stream, const int* active, int nactive) {
     if (T < 1 || NN < 4 || NN % 4 != 0 || NN / 4 > 0x7fffffffLL) return B200CAM_E_BAD_SIZE;
     if (!coef || !Z || !h || !workspace) return B200CAM_E_NULL;
     if (workspace_bytes < b200cam_zernike_workspace_bytes(T, NN)) return B200CAM_E_WORKSPACE;
     if (!aligned16(Z) || !aligned16(h) || !aligned16(workspace)) return B200CAM_E_ALIGN;
+    if (active != nullptr && (nactive < 1 || nactive > NN / 4)) return B200CAM_E_BAD_SIZE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int NN4 = static_cast<int>(NN / 4);
-    const int xblocks = (NN4 + EW_THREADS - 1) / EW_THREADS, ks = zernike_ks(T, NN4);
+    const int nq = active != nullptr ? nactive : NN4;
+    const int xblocks = (nq + EW_THREADS - 1) / EW_THREADS, ks = zernike_ks(T, NN4);
     Carver c(workspace);
-    int* arrive = c.take<int>(xblocks);                       // zero on entry (caller zero-fills the workspace once), left zero
+    int* arrive = c.take<int>((NN4 + EW_THREADS - 1) / EW_THREADS);   // zero on entry (caller zero-fills the workspace once), left zero
     float4* partial = c.take<float4>(static_cast<size_t>(ks) * NN4);
+    if (active != nullptr) CK(cudaMemsetAsync(h, 0, sizeof(float) * static_cast<size_t>(NN), s));   // outside the support h = 0
     launch_k(k_zernike_fwd, dim3(xblocks, ks), EW_THREADS, 0, s, 
-        ZernikeFwdParams{coef, reinterpret_cast<const float4*>(Z), partial, reinterpret_cast<float4*>(h), arrive, T, NN4, ks});
+        ZernikeFwdParams{coef, reinterpret_cast<const float4*>(Z), partial, reinterpret_cast<float4*>(h), arrive, T, NN4, ks, active, nactive});
     LAUNCH_CHECK();
     return 0;
 }
 
-int b200cam_zernike_bwd(const float* grad_h, const float* Z, float* grad_coef, int T, long long NN, void* stream) {
+int b200cam_zernike_fwd(const float* coef, const float* Z, float* h, void* workspace, size_t workspace_bytes, int T,
+                        long long NN, void* stream) {
+    return b200cam_zernike_fwd_ex(coef, Z, h, workspace, workspace_bytes, T, NN, stream, nullptr, 0);
+}
+
+int b200cam_zernike_bwd_ex(const float* grad_h, const float* Z, float* grad_coef, int T, long long NN, void* stream, const int* active,
+                           int nactive) {
     if (T < 1 || NN < 4 || NN % 4 != 0 || NN / 4 > 0x7fffffffLL) return B200CAM_E_BAD_SIZE;
     if (!grad_h || !Z || !grad_coef) return B200CAM_E_NULL;
     if (!aligned16(Z) || !aligned16(grad_h)) return B200CAM_E_ALIGN;
+    if (active != nullptr && (nactive < 1 || nactive > NN / 4)) return B200CAM_E_BAD_SIZE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long nq = active != nullptr ? nactive : NN / 4;
     // few terms: slice every plane over enough CTAs to fill the device (partials in the per-device scratch, b200cam_init)
     const DeviceState* st = cur_state();
     int splits = 1;
     if (T < 2 * 148 && st != nullptr && st->scratch != nullptr) {
         splits = (4 * 148 + T - 1) / T;
-        const int most = static_cast<int>(NN / 4 / (8 * EW_THREADS));
+        const int most = static_cast<int>(nq / (8 * EW_THREADS));
         if (splits > most) splits = most;
         if (splits > 64) splits = 64;
         if (splits < 1 || T * splits > SCRATCH_FLOATS) splits = 1;
     }
     launch_k(k_zernike_bwd, dim3(T, splits), EW_THREADS, 0, s, ZernikeBwdParams{reinterpret_cast<const float4*>(grad_h),
                                                             reinterpret_cast<const float4*>(Z), splits > 1 ? st->scratch : grad_coef,
-                                                            static_cast<int>(NN / 4), splits});
+                                                            static_cast<int>(NN / 4), splits, active, nactive});
     LAUNCH_CHECK();
     if (splits > 1) {
         launch_k(k_zernike_bwd_fin, (T + EW_THREADS - 1) / EW_THREADS, EW_THREADS, 0, s, st->scratch, grad_coef, T, splits);
         LAUNCH_CHECK();
     }
     return 0;
+}
+
+int b200cam_zernike_bwd(const float* grad_h, const float* Z, float* grad_coef, int T, long long NN, void* stream) {
+    return b200cam_zernike_bwd_ex(grad_h, Z, grad_coef, T, NN, stream, nullptr, 0);
 }
 
 int b200cam_psf_field(const float* h, const float* A, const float* Ht, const float* kappa, float* field,

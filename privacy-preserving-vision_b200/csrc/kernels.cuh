@@ -2007,6 +2007,11 @@ struct ZernikeFwdParams {
     float4* h;             // [NN4]
     int* arrive;           // [gridDim.x]
     int T, NN4, KS;
+    // nullable: the float4 positions that are non-zero in at least one basis plane (the Zernike basis is zero outside the unit
+    // disc: 21 % of the square) - the grid then covers `nactive` positions instead of NN4; h must be zero elsewhere (the entry
+    // point clears it)
+    const int* active = nullptr;
+    int nactive = 0;
 };
 
 template <class Exec>
@@ -2014,9 +2019,11 @@ B200_HD void zernike_fwd_body(Exec& ex, const ZernikeFwdParams& p, int* flag) {
     const int k = ex.by();
     const int j0 = static_cast<int>(static_cast<long long>(p.T) * k / p.KS);
     const int j1 = static_cast<int>(static_cast<long long>(p.T) * (k + 1) / p.KS);
+    const int nq = p.active != nullptr ? p.nactive : p.NN4;
     ex.phase([&](int tid) {
-        const int q = ex.bx() * EW_THREADS + tid;
-        if (q < p.NN4) {
+        const int qi = ex.bx() * EW_THREADS + tid;
+        if (qi < nq) {
+            const int q = p.active != nullptr ? ld_ro(p.active + qi) : qi;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             int j = j0;
             for (; j + 8 <= j1; j += 8) {                 // eight independent 16-byte loads in flight per thread
@@ -2046,8 +2053,9 @@ B200_HD void zernike_fwd_body(Exec& ex, const ZernikeFwdParams& p, int* flag) {
     if (*flag) {
         ex.phase([&](int tid) {
             ex.threadfence();
-            const int q = ex.bx() * EW_THREADS + tid;
-            if (q < p.NN4) {
+            const int qi = ex.bx() * EW_THREADS + tid;
+            if (qi < nq) {
+                const int q = p.active != nullptr ? ld_ro(p.active + qi) : qi;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int kk = 0; kk < p.KS; ++kk) {
                     const float4 v = ex.load_cg4(p.partial + static_cast<size_t>(kk) * p.NN4 + q);
@@ -2069,29 +2077,36 @@ struct ZernikeBwdParams {
     float* gcoef;          // [T]  (splits == 1) or the partials [T][splits]
     int NN4;
     int splits = 1;
+    const int* active = nullptr;   // as ZernikeFwdParams::active: only these float4 positions are visited
+    int nactive = 0;
 };
 
 template <class Exec>
 B200_HD void zernike_bwd_body(Exec& ex, const ZernikeBwdParams& p, float* red) {
     const int j = ex.bx();
-    const int slice = (p.NN4 + p.splits - 1) / p.splits;
+    const int nq = p.active != nullptr ? p.nactive : p.NN4;
+    const int slice = (nq + p.splits - 1) / p.splits;
     const int q0 = ex.by() * slice;
-    const int q1 = q0 + slice < p.NN4 ? q0 + slice : p.NN4;
+    const int q1 = q0 + slice < nq ? q0 + slice : nq;
     ex.phase([&](int tid) {
         const float4* z = p.Z + static_cast<size_t>(j) * p.NN4;
         float acc = 0.f;
         int q = q0 + tid;
         for (; q + 7 * EW_THREADS < q1; q += 8 * EW_THREADS) {
             float4 a[8], g[8];
+            int at[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = ld_ro(z + q + i * EW_THREADS);
+            for (int i = 0; i < 8; ++i) at[i] = p.active != nullptr ? ld_ro(p.active + q + i * EW_THREADS) : q + i * EW_THREADS;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = ld_ro(p.gh + q + i * EW_THREADS);
+            for (int i = 0; i < 8; ++i) a[i] = ld_ro(z + at[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = ld_ro(p.gh + at[i]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc += (a[i].x * g[i].x + a[i].y * g[i].y) + (a[i].z * g[i].z + a[i].w * g[i].w);
         }
         for (; q < q1; q += EW_THREADS) {
-            const float4 a = ld_ro(z + q), g = ld_ro(p.gh + q);
+            const int at = p.active != nullptr ? ld_ro(p.active + q) : q;
+            const float4 a = ld_ro(z + at), g = ld_ro(p.gh + at);
             acc += (a.x * g.x + a.y * g.y) + (a.z * g.z + a.w * g.w);
         }
         red[tid] = acc;

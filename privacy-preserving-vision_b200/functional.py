@@ -93,6 +93,20 @@ class DevicePlan:
             self._zernike_ws = {key: ws}
         return ws
 
+    def zernike_support(self, Z: torch.Tensor):
+        """int32 list of the float4 positions at which some basis plane is non-zero (the Zernike basis vanishes outside the
+        unit disc), or None when (almost) every position is.  Computed once per volume (keyed on storage and version)."""
+        key = (Z.data_ptr(), Z._version, tuple(Z.shape))
+        cache = self.__dict__.setdefault("_zsupport", {})
+        if key not in cache:
+            if len(cache) >= 4:
+                cache.clear()
+            with torch.no_grad():
+                nz = (Z.reshape(Z.shape[0], -1, 4) != 0).any(dim=2).any(dim=0)
+                idx = torch.nonzero(nz).reshape(-1).to(torch.int32)
+            cache[key] = idx.contiguous() if 0 < idx.numel() < 0.95 * nz.numel() else None
+        return cache[key]
+
     def sensor_workspace(self, B: int) -> torch.Tensor:
         ws = self._sensor_ws.get(B)
         if ws is None:
@@ -206,10 +220,13 @@ class ZernikeProject(torch.autograd.Function):
         Z = _as_f32(volume.detach(), plan.device)
         h = torch.empty(volume.shape[1:], dtype=torch.float32, device=plan.device)
         ws = plan.zernike_workspace(T, NN)
+        active = plan.zernike_support(Z)
         with torch.cuda.device(plan.index):
-            _lib.check(plan.lib.b200cam_zernike_fwd(_lib.ptr(c), _lib.ptr(Z), _lib.ptr(h), _lib.ptr(ws), ws.numel(), T, NN, _stream()))
+            _lib.check(plan.lib.b200cam_zernike_fwd_ex(_lib.ptr(c), _lib.ptr(Z), _lib.ptr(h), _lib.ptr(ws), ws.numel(), T, NN, _stream(),
+                                                       _lib.ptr(active), active.numel() if active is not None else 0))
         ctx.plan = plan
         ctx.coef_shape = coef.shape
+        ctx.active = active
         ctx.save_for_backward(Z)
         return h
 
@@ -220,8 +237,10 @@ class ZernikeProject(torch.autograd.Function):
         T, NN = Z.shape[0], Z[0].numel()
         g = _as_f32(gh, plan.device)
         gc = torch.empty(T, dtype=torch.float32, device=plan.device)
+        active = ctx.active
         with torch.cuda.device(plan.index):
-            _lib.check(plan.lib.b200cam_zernike_bwd(_lib.ptr(g), _lib.ptr(Z), _lib.ptr(gc), T, NN, _stream()))
+            _lib.check(plan.lib.b200cam_zernike_bwd_ex(_lib.ptr(g), _lib.ptr(Z), _lib.ptr(gc), T, NN, _stream(),
+                                                       _lib.ptr(active), active.numel() if active is not None else 0))
         return gc.reshape(ctx.coef_shape), None, None
 
 
