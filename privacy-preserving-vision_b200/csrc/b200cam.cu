@@ -1601,7 +1601,7 @@ int b200cam_crop_abs_resize_bwd(const float* grad_out, const float* conv, float*
 // ---- Zernike projection ----------------------------------------------------------------------
 static int zernike_ks(int T, long long NN4) {
     const long long xblocks = (NN4 + EW_THREADS - 1) / EW_THREADS;
-    long long ks = (148 * 4 + xblocks - 1) / xblocks;        // about four CTAs per SM in total
+    long long ks = (148 * 4 + xblocks - 1) / xblocks;        // about four CTAs per SM in total (twelve: 47 -> 51 us at 300 x 256^2)
     if (ks > T) ks = T;
     if (ks > 32) ks = 32;
     if (ks < 1) ks = 1;
@@ -1651,13 +1651,15 @@ int b200cam_zernike_bwd_ex(const float* grad_h, const float* Z, float* grad_coef
     const long long nq = active != nullptr ? nactive : NN / 4;
     // few terms: slice every plane over enough CTAs to fill the device (partials in the per-device scratch, b200cam_init)
     const DeviceState* st = cur_state();
+    // A CTA that walks a whole plane alone is a chain of dependent load batches (measured 42 us for 300 x 256^2: 1.6 TB/s):
+    // slice every plane so that about eight CTAs per SM are in flight, whatever T is
     int splits = 1;
-    if (T < 2 * 148 && st != nullptr && st->scratch != nullptr) {
-        splits = (4 * 148 + T - 1) / T;
+    if (st != nullptr && st->scratch != nullptr) {
+        splits = (8 * 148 + T - 1) / T;
         const int most = static_cast<int>(nq / (8 * EW_THREADS));
         if (splits > most) splits = most;
         if (splits > 64) splits = 64;
-        if (splits < 1 || T * splits > SCRATCH_FLOATS) splits = 1;
+        if (splits < 1 || static_cast<long long>(T) * splits > SCRATCH_FLOATS) splits = 1;
     }
     launch_k(k_zernike_bwd, dim3(T, splits), EW_THREADS, 0, s, ZernikeBwdParams{reinterpret_cast<const float4*>(grad_h),
                                                             reinterpret_cast<const float4*>(Z), splits > 1 ? st->scratch : grad_coef,
