@@ -61,6 +61,35 @@ def test_abi_rejects_bad_arguments_before_touching_the_gpu(library):
     assert library.b200cam_zernike_bwd(null, null, null, 0, 65536, null) == -1
 
 
+def test_lens_abi_geometry_and_argument_checks_without_gpu(library):
+    """The Image_Caption entry points (round 2): geometry predicates, workspace sizes and argument validation run on the host
+    before anything is enqueued."""
+    null = ctypes.c_void_p(0)
+    d3 = (ctypes.c_double * 3)(1.0, 2.0, 3.0)
+    # padded size 3R/2 must factor into radices <= 31; R a multiple of 4; P <= R
+    assert [library.b200cam_lens_psf_supported(r, 64) for r in (896, 736, 128, 160, 130, 4 * 37 * 2)] == [1, 1, 1, 1, 0, 0]
+    assert library.b200cam_lens_psf_padded(896) == 1344 and library.b200cam_lens_psf_padded(736) == 1104
+    assert library.b200cam_lens_psf_workspace_bytes(896, 256) >= 3 * 896 * 1344 * 8
+    assert library.b200cam_lens_psf_workspace_bytes(130, 64) == 0
+    assert library.b200cam_lens_psf_fwd(null, null, null, d3, null, null, null, null, null, null, null, null, 0, null, null, null, 0,
+                                        130, 64, null) == -1
+    assert library.b200cam_lens_psf_fwd(null, null, null, d3, null, null, null, null, null, null, null, null, 0, null, null, null, 0,
+                                        896, 256, null) == -2
+    assert library.b200cam_lens_psf_bwd(null, null, null, null, null, null, null, d3, null, null, null, null, 0, null, null, 0,
+                                        896, 256, null) == -2
+    # sensor path: patch sizes 64 ... 512 (transform size 2P)
+    assert library.b200cam_lens_sensor_workspace_bytes(256, 128) >= 128 * 3 * 257 * 512 * 8
+    assert library.b200cam_lens_sensor_workspace_bytes(368, 8) == 0
+    assert library.b200cam_lens_sensor_fwd(null, null, null, null, null, null, null, 0, 4, 368, null) == -1
+    assert library.b200cam_lens_sensor_fwd(null, null, null, null, null, null, null, 0, 4, 256, null) == -2
+    assert library.b200cam_lens_sensor_bwd(null, null, null, null, null, null, null, null, null, 0, 4, 256, null) == -2
+    assert library.b200cam_lens_sensor_dot(null, null, null, null, null, 0, 4, 256, null) == -2
+    assert library.b200cam_lens_normalise(null, null, null, 16, null) == -2
+    # Zernike support-list variants
+    assert library.b200cam_zernike_fwd_ex(null, null, null, null, 0, 300, 65536, null, null, 0) == -2
+    assert library.b200cam_zernike_bwd_ex(null, null, null, 300, 6, null, null, 0) == -1
+
+
 def test_no_cpu_fallback():
     cam = Camera(N=64, zernike_terms=6)
     with pytest.raises(RuntimeError, match="CUDA"):
