@@ -116,6 +116,27 @@ class DevicePlan:
         return ws
 
 
+# B200CAM_NVTX=1: NVTX ranges around every autograd entry point of the camera (tracing) - they show up as named
+# spans in nsys / ncu timelines; off by default (a push / pop pair costs ~1 us of host time each)
+_NVTX = os.environ.get("B200CAM_NVTX", "0") == "1"
+
+
+def nvtx(name):
+    """Decorator: wrap a static forward / backward in an NVTX range when B200CAM_NVTX=1."""
+    def deco(fn):
+        if not _NVTX:
+            return fn
+
+        def wrapped(*args, **kwargs):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco
+
+
 # 1: the caller's image row pass is ordered behind the first PSF kernel (see b200cam_psf_field); B200CAM_HOLD_ROWS=0 lets
 # both start together (A/B switch)
 _HOLD_ROWS = 0 if os.environ.get("B200CAM_HOLD_ROWS", "1") == "0" else 1
@@ -135,6 +156,7 @@ def _as_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 
 class PsfSynth(torch.autograd.Function):
     @staticmethod
+    @nvtx("b200cam.PsfSynth.forward")
     def forward(ctx, h: torch.Tensor, plan: DevicePlan, stream: torch.cuda.Stream | None = None):
         """`stream`: enqueue the kernels there (after everything already on the current stream) and return WITHOUT
         joining - the caller must `current_stream().wait_stream(stream)` before using the outputs."""
@@ -177,6 +199,7 @@ class PsfSynth(torch.autograd.Function):
         return psf, stats[1], stats[2]
 
     @staticmethod
+    @nvtx("b200cam.PsfSynth.backward")
     def backward(ctx, g_psf, g_rad, g_cen):
         plan: DevicePlan = ctx.plan
         N = plan.N
@@ -213,6 +236,7 @@ class ZernikeProject(torch.autograd.Function):
     and its adjoint, one pass over the basis volume each way."""
 
     @staticmethod
+    @nvtx("b200cam.ZernikeProject.forward")
     def forward(ctx, coef: torch.Tensor, volume: torch.Tensor, plan: DevicePlan):
         T = volume.shape[0]
         NN = volume[0].numel()
@@ -231,6 +255,7 @@ class ZernikeProject(torch.autograd.Function):
         return h
 
     @staticmethod
+    @nvtx("b200cam.ZernikeProject.backward")
     def backward(ctx, gh):
         plan: DevicePlan = ctx.plan
         (Z,) = ctx.saved_tensors
@@ -282,6 +307,7 @@ def sensor_rows(img: torch.Tensor, plan: DevicePlan):
 
 class SensorConv(torch.autograd.Function):
     @staticmethod
+    @nvtx("b200cam.SensorConv.forward")
     def forward(ctx, img: torch.Tensor, psf: torch.Tensor, plan: DevicePlan, rows: RowSpectra | None = None, epilogue=None):
         """`epilogue`: None (the reference's read-out: nothing) or (noise, noise_scale, quant_bits) - the opt-in sensor
         noise + quantisation of include/b200cam.h (B200CAM_SENSOR_NOISE / _QUANT); straight-through in backward."""
@@ -337,6 +363,7 @@ class SensorConv(torch.autograd.Function):
         return sensor
 
     @staticmethod
+    @nvtx("b200cam.SensorConv.backward")
     def backward(ctx, g):
         plan: DevicePlan = ctx.plan
         N = plan.N

@@ -63,6 +63,7 @@ class CircConv(torch.autograd.Function):
     """out = irfft2(rfft2(img) * rfft2(roll(kernel, -N/2))) per channel, N a power of two (b200cam_conv_fwd/bwd)."""
 
     @staticmethod
+    @F.nvtx("b200cam.CircConv.forward")
     def forward(ctx, img: torch.Tensor, kernel: torch.Tensor, plan: F.DevicePlan):
         N = plan.N
         x = F._as_f32(img.detach(), plan.device)
@@ -82,6 +83,7 @@ class CircConv(torch.autograd.Function):
         return out
 
     @staticmethod
+    @F.nvtx("b200cam.CircConv.backward")
     def backward(ctx, g):
         plan: F.DevicePlan = ctx.plan
         N = plan.N
@@ -103,6 +105,7 @@ class CropAbsResize(torch.autograd.Function):
     convolution output, ``Image_Caption/Camera/Utils.py:289-295``, in one kernel each way (b200cam_crop_abs_resize_*)."""
 
     @staticmethod
+    @F.nvtx("b200cam.CropAbsResize.forward")
     def forward(ctx, conv: torch.Tensor, P: int, off: int, plan: F.DevicePlan):
         c = F._as_f32(conv.detach(), plan.device)
         B, C, n, _ = c.shape
@@ -115,6 +118,7 @@ class CropAbsResize(torch.autograd.Function):
         return out
 
     @staticmethod
+    @F.nvtx("b200cam.CropAbsResize.backward")
     def backward(ctx, g):
         plan: F.DevicePlan = ctx.plan
         (c,) = ctx.saved_tensors
@@ -134,6 +138,7 @@ class GlobalMaxNormalise(torch.autograd.Function):
     and the backward's arg-max term (-sum(g*y)/m at the arg-max) is routed to the rank that owns it."""
 
     @staticmethod
+    @F.nvtx("b200cam.GlobalMaxNormalise.forward")
     def forward(ctx, x: torch.Tensor, group):
         import torch.distributed as dist
         m_local = x.max()
@@ -146,6 +151,7 @@ class GlobalMaxNormalise(torch.autograd.Function):
         return y
 
     @staticmethod
+    @F.nvtx("b200cam.GlobalMaxNormalise.backward")
     def backward(ctx, g):
         import torch.distributed as dist
         y, m, m_local = ctx.saved_tensors
@@ -167,6 +173,7 @@ class LensSensor(torch.autograd.Function):
     one-GPU result, the arg-max term landing on the rank(s) that hold the maximum."""
 
     @staticmethod
+    @F.nvtx("b200cam.LensSensor.forward")
     def forward(ctx, img: torch.Tensor, kpad: torch.Tensor, plan: F.DevicePlan, group):
         import torch.distributed as dist
         dev, n = plan.device, plan.N
@@ -193,6 +200,7 @@ class LensSensor(torch.autograd.Function):
         return y
 
     @staticmethod
+    @F.nvtx("b200cam.LensSensor.backward")
     def backward(ctx, g):
         import torch.distributed as dist
         plan: F.DevicePlan = ctx.plan
@@ -224,6 +232,7 @@ class LensPsf(torch.autograd.Function):
     ``flags``: 1 = energy loss against mask_1 (prueba "1"/"3"), 2 = multiply by mask_2 (prueba "2"/"3")."""
 
     @staticmethod
+    @F.nvtx("b200cam.LensPsf.forward")
     def forward(ctx, h: torch.Tensor, noise, c: dict, flags: int, R: int, P: int, lib):
         dev = h.device
         hh = F._as_f32(h.detach(), dev).reshape(R, R)
@@ -247,6 +256,7 @@ class LensPsf(torch.autograd.Function):
         return (psf_out if flags & 2 else psf), (loss if flags & 1 else None)
 
     @staticmethod
+    @F.nvtx("b200cam.LensPsf.backward")
     def backward(ctx, g_psf, g_loss):
         psf, chan_sum, field, U, loss = ctx.saved_tensors
         c, flags, (R, P), lib = ctx.c, ctx.flags, ctx.geom, ctx.lib
