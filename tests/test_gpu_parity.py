@@ -422,3 +422,18 @@ def test_graphed_callable_matches_eager():
     assert rel_l2(graphed_y, y) <= 1e-5
     assert rel_l2(grads[0], cam.Zer_train.grad) <= 1e-4
     assert rel_l2(graphed_y2, cam(img2)) <= 1e-5
+
+
+@pytest.mark.parametrize("switch", ["B200CAM_TIE_SPECTRAL=1", "B200CAM_ONE_PASS=1", "B200CAM_OTF_ROWS=0", "B200CAM_PLANE=1",
+                                    "B200CAM_COOP=0", "B200CAM_HOLD_ROWS=0"])
+def test_opt_in_switches_keep_parity(switch):
+    """Every A/B switch of INTEGRATION.md section 4 selects another kernel path for the same maths: each must stay inside the
+    tolerances (the switches are read once per process, hence a subprocess per switch; tests/switch_parity_runner.py)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    k, v = switch.split("=")
+    res = subprocess.run([sys.executable, str(REPO / "tests" / "switch_parity_runner.py")], capture_output=True, text=True,
+                         timeout=600, env=dict(os.environ, **{k: v}))
+    assert res.returncode == 0 and "ok=True" in res.stdout, (res.stdout + res.stderr)[-2000:]
