@@ -434,9 +434,6 @@ class OpticsZernike(nn.Module):
             c["Hx"] = torch.tensor(np.stack([np.cos(e1), np.sin(e1)], axis=-1), dtype=torch.float64, device=dev).contiguous()
             c["tw"] = torch.tensor(np.stack([np.cos(ang), np.sin(ang)], axis=-1).astype(np.float32), device=dev).contiguous()
             c["delta_c"] = (ctypes.c_double * 3)(*[float(v) for v in delta.reshape(-1)])
-            ok = tuple(self.mask_1.shape) == (self.patch_size, self.patch_size, 3)
-            c["mask1"] = self.mask_1.to(device=dev, dtype=torch.float64).contiguous() if ok else None
-            c["mask2"] = self.mask_2.to(device=dev, dtype=torch.float64).contiguous() if ok else None
             c["lib"] = lib
         self._const[key] = c
         return c
@@ -455,8 +452,21 @@ class OpticsZernike(nn.Module):
         """(psf, loss) through csrc/lens_psf.cu, or None when the geometry is outside what the kernels cover (padded
         size with a prime factor above 31, masks of another size): the caller then uses the torch expression."""
         c = self._constants(height_map.device)
-        if not c["kernels"] or (flags and c["mask1"] is None):
+        if not c["kernels"]:
             return None
+        if flags:      # the disc masks are module attributes a caller may replace: follow them (fp64, on the device, contiguous)
+            mkey = (self.mask_1.data_ptr(), self.mask_1._version, self.mask_2.data_ptr(), self.mask_2._version)
+            if c.get("mask_key") != mkey:
+                ok = tuple(self.mask_1.shape) == tuple(self.mask_2.shape) == (self.patch_size, self.patch_size, 3)
+                dev = height_map.device
+                c["mask1"] = self.mask_1.to(device=dev, dtype=torch.float64).contiguous() if ok else None
+                c["mask2"] = self.mask_2.to(device=dev, dtype=torch.float64).contiguous() if ok else None
+                c["mask_key"] = mkey
+            if c["mask1"] is None:
+                return None
+        else:
+            c.setdefault("mask1", None)
+            c.setdefault("mask2", None)
         noise = None
         if self.height_tolerance is not None:                      # PhasePlate._build, Utils.py:396-406: same torch.rand call
             noise = ((-self.height_tolerance - self.height_tolerance)
