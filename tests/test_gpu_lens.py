@@ -159,7 +159,7 @@ def test_psf_kernels_match_oracle_with_tolerance_noise(wave, patch, prueba):
     assert abs(float(grad) - float(cz.grad[3])) <= 1e-3 * abs(float(cz.grad[3]))
 
 
-@pytest.mark.parametrize("P,B", [(64, 3), (128, 2), (256, 5)])
+@pytest.mark.parametrize("P,B", [(64, 3), (128, 2), (256, 5), (512, 2), (256, 40)])
 def test_fused_padded_sensor_matches_oracle(P, B):
     """csrc/lens_conv.cu (zero padding, |.|, crop, nearest resize and batch-global max inside the transform kernels) against
     oracle.lens_oracle.sensor_image + the global max (Utils.py:251-297, Lens.py:312): sensor, dL/dpsf and dL/dimg.  One image
