@@ -4,18 +4,20 @@ Same constructor signature, parameters / ``state_dict`` keys (``zernike_coeffs_n
 ``zernike_coeffs_no_train2`` (T-4,1,1), ``zernike_coeffs_train`` (1,1)), ``forward`` signature and
 4-tuple result ``(sensor_img, psf, zernike_coeffs_concat, loss)``.
 
-What runs where
-* the per-image work - the padded *linear* convolution of every image channel with its PSF
-  (``img_psf_conv``, ``Image_Caption/Camera/Utils.py:251-297``) and its backward into the PSF - runs in the
-  b200cam CUDA kernels (``b200cam_conv_fwd`` / ``b200cam_conv_bwd``: power-of-two 2*patch FFT size);
-* the batch-independent PSF synthesis (``Lens.py:158-239``: phase plate, spherical wavefront, aperture,
-  Fresnel propagation on a (5/4 * wave_res)^2 grid - 1344^2 = 2^6*3*7 for the shipped config, not a power of
-  two - area down-sampling, normalisation) is expressed in torch tensor ops on the module's device with the
-  reference's dtypes (fp64 phases, complex128 propagation) and uses the library FFT for the odd size.
-  A hand-written mixed-radix kernel for that step is listed as "next" in DESIGN.md;
-* ``abs`` / crop / nearest resize (``Utils.py:289-295``) and the batch-global max (``Lens.py:312``) are
-  element-wise torch ops around the kernel; with ``data_parallel(group)`` the max is all-reduced and its backward
-  term is routed to the owning rank, so N ranks reproduce the 1-GPU result.
+What runs where (everything below the Zernike coefficients is b200cam kernels, ``include/b200cam.h``)
+* height map: ``b200cam_zernike_fwd_ex / _bwd_ex`` over the support of the basis; the partial sum of the frozen terms (349 of 350 as
+  shipped) is cached, so a step reads one basis plane each way (``_height_map``);
+* PSF synthesis (``Lens.py:176-274``: phase plate with the reference's ``torch.rand`` tolerance noise, spherical wavefront,
+  aperture, Fresnel propagation on a (3/2 * wave_res)^2 grid - 1344^2 = 2^6*3*7 for the shipped config - intensity, area
+  down-sampling, per-channel normalisation, disc masks and energy loss) and its adjoint into the height map:
+  ``b200cam_lens_psf_fwd / _bwd`` (``csrc/lens_psf.cu``: pruned mixed-radix transforms, complex64), class ``LensPsf``;
+* sensor image (``img_psf_conv``, ``Utils.py:251-297`` + the batch-global max of ``Lens.py:312``): ``b200cam_lens_sensor_*``
+  (``csrc/lens_conv.cu``: zero padding, abs, crop, nearest resize and the maximum inside the transform kernels), class
+  ``LensSensor``; with ``data_parallel(group)`` the maximum, sum(g*y) and the tie count are all-reduced, so N ranks reproduce
+  the 1-GPU result;
+* geometries the kernels do not cover (padded size with a prime factor above 31; patch sizes whose doubled size is not a power of
+  two, e.g. the constructor default 368) use the reference's own torch expression on the GPU (``_psf``, ``_sensor_torch``,
+  ``CircConv`` / ``CropAbsResize`` / ``GlobalMaxNormalise``).
 
 Not reproduced: comet.ml summaries (``attach_summaries``), the ``psf_lab`` image file path, ``upsample=True``
 (1792^2 convolution, not a power of two) - they raise ``NotImplementedError`` - and the side effect of caching the
