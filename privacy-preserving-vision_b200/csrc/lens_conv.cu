@@ -48,19 +48,22 @@ struct GradLoad {       // dL/dconv from dL/dy: adjoint of / max, |.|, crop and 
         cf = __ldg(coef);
     }
     __device__ __forceinline__ float draw(size_t o) const {
-        const float rv = __ldg(raw + o);
-        float d = __ldg(g + o) * inv_m;
-        if (fabsf(rv) == m) d -= cf;
+        const float rv = __ldg(raw + o), gv = __ldg(g + o);
+        const float d = gv * inv_m - (fabsf(rv) == m ? cf : 0.f);
         return rv > 0.f ? d : (rv < 0.f ? -d : 0.f);
     }
     __device__ __forceinline__ float operator()(int plane, int r, int c, int P) const {
         if (r == 0 || c == 0) return 0.f;                  // conv row / column pt is cropped away
         const size_t base = static_cast<size_t>(plane) * P * P;
         float v = draw(base + static_cast<size_t>(r) * P + c);
-        if (c == 1) v += draw(base + static_cast<size_t>(r) * P);
-        if (r == 1) {
-            v += draw(base + c);
-            if (c == 1) v += draw(base);
+        // the nearest resize duplicates crop row 0 / column 0 into output row / column 0: only r == 1 / c == 1 collect two terms.
+        // Both tests are rare and warp-uniform enough to be branches, not selects around extra loads.
+        if (c == 1 || r == 1) {
+            if (c == 1) v += draw(base + static_cast<size_t>(r) * P);
+            if (r == 1) {
+                v += draw(base + c);
+                if (c == 1) v += draw(base);
+            }
         }
         return v;
     }
