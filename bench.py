@@ -778,18 +778,38 @@ def run_caption_camera(args) -> None:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     clocks = sampler.stop()
-    # end to end: pinned host images in, sensor checksum + coefficient gradient out
+    # end to end: pinned host images in, sensor checksum + coefficient gradient out; the host-to-device copy of step i+1 runs on
+    # a copy stream beside the compute of step i (two device buffers), as the config-2 e2e leg does
     out_host = torch.empty(2).pin_memory()
-    dbuf = torch.empty_like(imgs[0])
+    dbufs = [torch.empty_like(imgs[0]) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    cur = torch.cuda.current_stream(dev)
     e2e_steps = max(5, min(steps, 30))
+
+    def upload(i):
+        k = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[k])                  # the step that last read this buffer is done
+            dbufs[k].copy_(imgs_host[i % R], non_blocking=True)
+            ready[k].record(copy_stream)
+
     torch.cuda.synchronize()
+    for k in range(2):
+        freed[k].record(cur)
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
+    upload(0)
     for i in range(e2e_steps):
-        dbuf.copy_(imgs_host[i % R], non_blocking=True)
+        if i + 1 < e2e_steps:
+            upload(i + 1)
+        k = i % 2
+        cur.wait_event(ready[k])
         cam.zero_grad(set_to_none=True)
-        sensor, psf, coeffs, loss = cam(dbuf)
+        sensor, psf, coeffs, loss = cam(dbufs[k])
         torch.autograd.backward([sensor], [ws[i % R]])
+        freed[k].record(cur)
         out_host.copy_(torch.stack([sensor.detach().sum(), cam.zernike_coeffs_train.grad.reshape(-1)[0]]), non_blocking=True)
     t1.record()
     torch.cuda.synchronize()
