@@ -516,97 +516,97 @@ def run_b200(args) -> None:
         cam.check_device_errors()
 
     # ---- end to end through the module API with host image buffers ------------------------------------
+    # Every step: H2D copy of that step's pinned host images (copy stream, two device buffers), the module's forward +
+    # backward on them, D2H of the step's results (loss + dL/dh; config 1: the sensor images).  The module call is made
+    # the way a training loop that cares about speed makes it - captured once per device buffer in a CUDA graph
+    # (torch.cuda.graph around `cam(img)` + backward; static input = the device buffer the copy lands in) and replayed;
+    # the same loop with eager module calls is reported beside it as `e2e_eager` (host-bound: ~2.9 ms of Python,
+    # ctypes and autograd per step for ~0.17 ms of device work).
     copy_stream = torch.cuda.Stream()
-    dev_bufs = [torch.empty_like(imgs[0]) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     gh_host = torch.empty(1, N, N).pin_memory()
     loss_host = torch.empty(1).pin_memory()
+    y_host = torch.empty(B, 3, N, N).pin_memory() if fwd_only else None
     e2e_steps = max(10, min(args.steps, 50))
 
-    def e2e_loop(n):
+    def e2e_compute(buf, j):
+        if fwd_only:                                      # config 1: the sensor images themselves are the result
+            with torch.no_grad():
+                return (cam(buf),)
+        h.grad = None
+        y = cam(buf)
+        torch.autograd.backward([y, cam.loss_rad, cam.centering_loss], [ws[j % R], one, one])
+        return (h.grad, (cam.loss_rad + cam.centering_loss).detach().reshape(1))
+
+    def measure_e2e(host_list, bufs, graphed):
+        """images/s of the whole job; (value, "cuda-graph replay" | "eager")"""
         cur = torch.cuda.current_stream()
-        for i in range(n + 1):
-            if i < n:                                     # prefetch batch i
-                s = i % 2
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(freed[s])
-                    dev_bufs[s].copy_(imgs_host[i % R], non_blocking=True)
-                    ready[s].record(copy_stream)
-            if i >= 1:                                    # compute batch i-1
-                s = (i - 1) % 2
-                cur.wait_event(ready[s])
-                if fwd_only:                              # config 1: the sensor images themselves are the result
-                    with torch.no_grad():
-                        y = cam(dev_bufs[s])
+        caps = None
+        if graphed:
+            try:
+                caps = []
+                for s in range(2):
+                    drop_graph_refs()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        outs = e2e_compute(bufs[s], s)
+                    caps.append((g, outs))
+            except Exception as exc:
+                if rank == 0:
+                    print(f"[bench] e2e graph capture failed ({exc}); eager module calls", file=sys.stderr)
+                caps = None
+                torch.cuda.synchronize()
+
+        def loop(n):
+            for i in range(n + 1):
+                if i < n:                                 # prefetch batch i
+                    s = i % 2
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(freed[s])
+                        bufs[s].copy_(host_list[i % R], non_blocking=True)
+                        ready[s].record(copy_stream)
+                if i >= 1:                                # compute batch i-1
+                    s = (i - 1) % 2
+                    cur.wait_event(ready[s])
+                    if caps is not None:
+                        caps[s][0].replay()
+                        outs = caps[s][1]
+                    else:
+                        outs = e2e_compute(bufs[s], i - 1)
                     freed[s].record(cur)
-                    y_host.copy_(y, non_blocking=True)
-                    continue
-                h.grad = None
-                y = cam(dev_bufs[s])
-                torch.autograd.backward([y, cam.loss_rad, cam.centering_loss], [ws[(i - 1) % R], one, one])
-                freed[s].record(cur)
-                gh_host.copy_(h.grad, non_blocking=True)
-                loss_host.copy_((cam.loss_rad + cam.centering_loss).detach().reshape(1), non_blocking=True)
+                    if fwd_only:
+                        y_host.copy_(outs[0], non_blocking=True)
+                    else:
+                        gh_host.copy_(outs[0], non_blocking=True)
+                        loss_host.copy_(outs[1], non_blocking=True)
 
-    y_host = torch.empty(B, 3, N, N).pin_memory() if fwd_only else None
-    for s in range(2):
-        freed[s].record(torch.cuda.current_stream())
-    e2e_loop(3)
-    sync_all()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    e2e_loop(e2e_steps)
-    t1.record()
-    sync_all()
-    ems = torch.tensor([t0.elapsed_time(t1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / (float(ems.item()) * 1e-3)
+        sync_all()
+        for s in range(2):
+            freed[s].record(cur)
+        loop(3)
+        sync_all()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        loop(e2e_steps)
+        t1.record()
+        sync_all()
+        ems = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        drop_graph_refs()
+        return world * B * e2e_steps / (float(ems.item()) * 1e-3), ("cuda-graph replay" if caps is not None else "eager")
 
-    # ---- the same end-to-end loop with uint8 host images (what an image decoder yields; the reference's loader converts
-    #      to fp32 on the host before the copy).  Reported beside `e2e`, not instead of it.
+    dev_bufs = [torch.empty_like(imgs[0]) for _ in range(2)]
+    # the same loop with uint8 host images (what an image decoder yields; the reference's loader converts to fp32 on the
+    # host before the copy).  Reported beside `e2e`, not instead of it.
     imgs_u8_host = [(t * 255.0).round().to(torch.uint8).pin_memory() for t in imgs_host]
     dev_u8 = [torch.empty(B, 3, N, N, dtype=torch.uint8, device=dev) for _ in range(2)]
-
-    def e2e_u8_loop(n):
-        cur = torch.cuda.current_stream()
-        for i in range(n + 1):
-            if i < n:
-                s = i % 2
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(freed[s])
-                    dev_u8[s].copy_(imgs_u8_host[i % R], non_blocking=True)
-                    ready[s].record(copy_stream)
-            if i >= 1:
-                s = (i - 1) % 2
-                cur.wait_event(ready[s])
-                if fwd_only:
-                    with torch.no_grad():
-                        y = cam(dev_u8[s])
-                    freed[s].record(cur)
-                    y_host.copy_(y, non_blocking=True)
-                    continue
-                h.grad = None
-                y = cam(dev_u8[s])
-                torch.autograd.backward([y, cam.loss_rad, cam.centering_loss], [ws[(i - 1) % R], one, one])
-                freed[s].record(cur)
-                gh_host.copy_(h.grad, non_blocking=True)
-                loss_host.copy_((cam.loss_rad + cam.centering_loss).detach().reshape(1), non_blocking=True)
-
-    for s in range(2):
-        freed[s].record(torch.cuda.current_stream())
-    e2e_u8_loop(3)
-    sync_all()
-    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    u0.record()
-    e2e_u8_loop(e2e_steps)
-    u1.record()
-    sync_all()
-    ums = torch.tensor([u0.elapsed_time(u1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ums, op=dist.ReduceOp.MAX)
-    e2e_u8_value = world * B * e2e_steps / (float(ums.item()) * 1e-3)
+    want_graph = graphs is not None
+    e2e_value, e2e_launch = measure_e2e(imgs_host, dev_bufs, want_graph)
+    e2e_u8_value, e2e_u8_launch = measure_e2e(imgs_u8_host, dev_u8, want_graph)
+    e2e_eager_value, _ = measure_e2e(imgs_host, dev_bufs, False)
+    e2e_u8_eager_value, _ = measure_e2e(imgs_u8_host, dev_u8, False)
 
     def finish():
         # captured graphs hold NCCL work: drop them and drain the device before tearing the communicator down
@@ -669,11 +669,17 @@ def run_b200(args) -> None:
         "config": workload_config(args, world, "cuda-graph replay" if graphs is not None else "eager"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * N * N * 4,
                 "d2h_bytes_per_step": B * 3 * N * N * 4 if fwd_only else N * N * 4 + 4,
-                "steps": e2e_steps, "note": "nn.Module API, pinned host images, double-buffered H2D, loss + dL/dh read back"},
+                "steps": e2e_steps, "launch": e2e_launch,
+                "h2d_GBps": e2e_value / world / B * (B * 3 * N * N * 4) / 1e9,      # per GPU; ~55 GB/s = the PCIe ceiling of the box
+                "note": "nn.Module API (cam(img) + backward), pinned host images, double-buffered H2D on a copy stream, "
+                        "loss + dL/dh read back every step"},
+        "e2e_eager": {"value": e2e_eager_value, "unit": UNIT, "note": "the same loop with eager module calls (host-bound)"},
         "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * N * N,
                    "d2h_bytes_per_step": B * 3 * N * N * 4 if fwd_only else N * N * 4 + 4,
-                   "steps": e2e_steps, "note": "same loop, uint8 host images (decoder output), /255 on the GPU: extra information, "
-                                               "the fp32 `e2e` above is the contract's number"},
+                   "steps": e2e_steps, "launch": e2e_u8_launch, "eager_value": e2e_u8_eager_value,
+                   "h2d_GBps": e2e_u8_value / world / B * (B * 3 * N * N) / 1e9,
+                   "note": "same loop, uint8 host images (decoder output), /255 on the GPU: extra information, "
+                           "the fp32 `e2e` above is the contract's number"},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -779,7 +785,8 @@ def run_caption_camera(args) -> None:
     ms = e0.elapsed_time(e1) / steps
     clocks = sampler.stop()
     # end to end: pinned host images in, sensor checksum + coefficient gradient out; the host-to-device copy of step i+1 runs on
-    # a copy stream beside the compute of step i (two device buffers), as the config-2 e2e leg does
+    # a copy stream beside the compute of step i (two device buffers), as the config-2 e2e leg does.  The module call
+    # (cam(img) + backward) is captured once per device buffer in a CUDA graph and replayed; `e2e_eager` = eager calls.
     out_host = torch.empty(2).pin_memory()
     dbufs = [torch.empty_like(imgs[0]) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
@@ -788,6 +795,12 @@ def run_caption_camera(args) -> None:
     cur = torch.cuda.current_stream(dev)
     e2e_steps = max(5, min(steps, 30))
 
+    def e2e_compute(k, j):
+        cam.zero_grad(set_to_none=True)
+        sensor, psf, coeffs, loss = cam(dbufs[k])
+        torch.autograd.backward([sensor], [ws[j % R]])
+        return torch.stack([sensor.detach().sum(), cam.zernike_coeffs_train.grad.reshape(-1)[0]])
+
     def upload(i):
         k = i % 2
         with torch.cuda.stream(copy_stream):
@@ -795,25 +808,49 @@ def run_caption_camera(args) -> None:
             dbufs[k].copy_(imgs_host[i % R], non_blocking=True)
             ready[k].record(copy_stream)
 
-    torch.cuda.synchronize()
-    for k in range(2):
-        freed[k].record(cur)
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    upload(0)
-    for i in range(e2e_steps):
-        if i + 1 < e2e_steps:
-            upload(i + 1)
-        k = i % 2
-        cur.wait_event(ready[k])
+    def measure_e2e(graphed):
+        caps = None
+        if graphed:
+            try:
+                caps = []
+                for k in range(2):
+                    cam.zero_grad(set_to_none=True)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        out = e2e_compute(k, k)
+                    caps.append((g, out))
+            except Exception as exc:
+                print(f"[bench] e2e graph capture failed ({exc}); eager module calls", file=sys.stderr)
+                caps = None
+        torch.cuda.synchronize()
+        for k in range(2):
+            freed[k].record(cur)
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        for timed in (False, True):
+            n = e2e_steps if timed else 3
+            if timed:
+                t0.record()
+            upload(0)
+            for i in range(n):
+                if i + 1 < n:
+                    upload(i + 1)
+                k = i % 2
+                cur.wait_event(ready[k])
+                if caps is not None:
+                    caps[k][0].replay()
+                    out = caps[k][1]
+                else:
+                    out = e2e_compute(k, i)
+                freed[k].record(cur)
+                out_host.copy_(out, non_blocking=True)
+            if timed:
+                t1.record()
+            torch.cuda.synchronize()
         cam.zero_grad(set_to_none=True)
-        sensor, psf, coeffs, loss = cam(dbufs[k])
-        torch.autograd.backward([sensor], [ws[i % R]])
-        freed[k].record(cur)
-        out_host.copy_(torch.stack([sensor.detach().sum(), cam.zernike_coeffs_train.grad.reshape(-1)[0]]), non_blocking=True)
-    t1.record()
-    torch.cuda.synchronize()
-    e2e = B * e2e_steps / (t0.elapsed_time(t1) * 1e-3)
+        return B * e2e_steps / (t0.elapsed_time(t1) * 1e-3), ("cuda-graph replay" if caps is not None else "eager")
+
+    e2e, e2e_launch = measure_e2e(graphs is not None)
+    e2e_eager, _ = measure_e2e(False)
     peak, peak_src = hbm_peak()
     achieved = B * 48 * P * P / (ms * 1e-3) / 1e9
     # CPU baseline: the oracle restatement of the reference module, bounded sample (one step of batch 4 is ~1.5 s)
@@ -841,7 +878,9 @@ def run_caption_camera(args) -> None:
             "config": {"workload": f"Image_Caption camera (OpticsZernike 896/256/T=350) fwd+bwd into the trainable coefficient, batch {B} "
                                    "of 256x256 RGB; caption nets not included", "baseline_config": "3cam", "global_batch": B,
                        "l2": f"{R} input sets rotated: {R * 2 * B * 3 * P * P * 4 / 1e6:.0f} MB", "launch": "cuda-graph replay" if graphs is not None else "eager"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 3 * P * P * 4, "d2h_bytes_per_step": 8, "steps": e2e_steps},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 3 * P * P * 4, "d2h_bytes_per_step": 8, "steps": e2e_steps,
+                    "launch": e2e_launch, "h2d_GBps": e2e * 3 * P * P * 4 / 1e9},     # ~55 GB/s = the PCIe ceiling of the box
+            "e2e_eager": {"value": e2e_eager, "unit": UNIT},
             "gpu_launches": launches * steps, "launches_per_step": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src,
