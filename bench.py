@@ -520,8 +520,8 @@ def run_b200(args) -> None:
     # backward on them, D2H of the step's results (loss + dL/dh; config 1: the sensor images).  The module call is made
     # the way a training loop that cares about speed makes it - captured once per device buffer in a CUDA graph
     # (torch.cuda.graph around `cam(img)` + backward; static input = the device buffer the copy lands in) and replayed;
-    # the same loop with eager module calls is reported beside it as `e2e_eager` (host-bound: ~2.9 ms of Python,
-    # ctypes and autograd per step for ~0.17 ms of device work).
+    # the same loop with eager module calls is reported beside it as `e2e_eager` (an eager step costs ~0.4 ms of Python,
+    # ctypes and autograd for ~0.17 ms of device work: that bounds the uint8 loop, the fp32 one is PCIe-bound either way).
     copy_stream = torch.cuda.Stream()
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
@@ -673,7 +673,7 @@ def run_b200(args) -> None:
                 "h2d_GBps": e2e_value / world / B * (B * 3 * N * N * 4) / 1e9,      # per GPU; ~55 GB/s = the PCIe ceiling of the box
                 "note": "nn.Module API (cam(img) + backward), pinned host images, double-buffered H2D on a copy stream, "
                         "loss + dL/dh read back every step"},
-        "e2e_eager": {"value": e2e_eager_value, "unit": UNIT, "note": "the same loop with eager module calls (host-bound)"},
+        "e2e_eager": {"value": e2e_eager_value, "unit": UNIT, "note": "the same loop with eager module calls (fp32 images: PCIe-bound either way; uint8: see e2e_u8.eager_value)"},
         "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * N * N,
                    "d2h_bytes_per_step": B * 3 * N * N * 4 if fwd_only else N * N * 4 + 4,
                    "steps": e2e_steps, "launch": e2e_u8_launch, "eager_value": e2e_u8_eager_value,
