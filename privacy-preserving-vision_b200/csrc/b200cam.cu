@@ -750,23 +750,43 @@ struct Carver {
 };
 
 // The column kernels are persistent over images: CTA (colgroup, chunk) walks its chunk of the batch.  The number of
-// chunks is chosen so that the whole grid is ONE wave of resident CTAs (slots = SMs x occupancy, measured at init):
-// a second, partly filled wave costs as much as a full one.
+// chunks is normally chosen so that the whole grid is ONE wave of resident CTAs (slots = SMs x occupancy, measured at
+// init): a second, partly filled wave costs as much as a full one.  Where one wave leaves SMs idle (N = 512 accumulate:
+// 97 column groups on 148 one-CTA SMs) or cannot hold the grid at all (N = 1024: 193 column groups), a simple wave model
+// - CTAs start in rounds of `slots`, a CTA costs its images plus a fixed prologue - picks a finer split when that is
+// predicted at least 10 % faster (N = 512: 1 -> 3 chunks = two full rounds of 11 images instead of one of 32 on 2/3 of
+// the SMs; N = 1024: 1 -> 2 chunks = three rounds of 4 images instead of two of 8).
 constexpr int MAX_CHUNKS = 16;          // sizes the partial-sum workspace of the backward
 static int col_chunks(int N, int B, int slots) {
     const int colgroups = (3 * (N / 2 + 1) + Tile<64>::COLS - 1) / Tile<64>::COLS;
+    const int cap = B < MAX_CHUNKS ? (B < 1 ? 1 : B) : MAX_CHUNKS;
     int n = slots / colgroups;
-    if (n > MAX_CHUNKS) n = MAX_CHUNKS;
-    if (n > B) n = B;
+    if (n > cap) n = cap;
     if (n < 1) n = 1;
+    static const bool one_wave_only = [] { const char* e = getenv("B200CAM_ONE_WAVE"); return e && e[0] == '1'; }();
+    if (one_wave_only) return n;
+    auto cost = [&](int k) {
+        const int rounds = (colgroups * k + slots - 1) / slots;
+        return static_cast<float>(rounds) * (static_cast<float>((B + k - 1) / k) + 0.5f);
+    };
+    float best = cost(n);
+    for (int k = 1; k <= cap; ++k)
+        if (cost(k) < 0.9f * best) {
+            best = cost(k);
+            n = k;
+        }
     return n;
 }
 static int conv_chunks(int N, int B) {
     int dev = 0;
     const int slots = (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MAX_DEV) ? g_state[dev].conv_slots[log2i(N)] : 0;
+    static const int forced = [] { const char* e = getenv("B200CAM_CONV_CHUNKS"); return e ? atoi(e) : 0; }();   // experiments
+    if (forced > 0) return forced > B ? B : (forced > MAX_CHUNKS ? MAX_CHUNKS : forced);
     return col_chunks(N, B, slots > 0 ? slots : 592);
 }
 static int accum_chunks(int N, int B) {
+    static const int forced = [] { const char* e = getenv("B200CAM_ACCUM_CHUNKS"); return e ? atoi(e) : 0; }();
+    if (forced > 0) return forced > B ? B : (forced > MAX_CHUNKS ? MAX_CHUNKS : forced);
     int dev = 0;
     const int slots = (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MAX_DEV) ? g_state[dev].accum_slots[log2i(N)] : 0;
     return col_chunks(N, B, slots > 0 ? slots : 592);

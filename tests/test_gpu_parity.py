@@ -76,7 +76,7 @@ def test_config2_forward_backward_batch64():
     assert rel_l2(h.grad, gh) <= TOL_GRAD
 
 
-@pytest.mark.parametrize("N,B", [(64, 3), (128, 5), (512, 2), (1024, 1), (256, 1), (256, 37), (512, 9), (64, 150)])
+@pytest.mark.parametrize("N,B", [(64, 3), (128, 5), (512, 2), (1024, 1), (256, 1), (256, 37), (512, 9), (64, 150), (1024, 3)])
 def test_other_resolutions(N, B):
     """Other sizes and ragged batches: fewer tiles than persistent CTAs (B = 1), chunk splits that do not divide (B = 37)."""
     h_cpu, img, w = synth.height_map(N, 5), synth.images(B, N, 6), synth.upstream_grad(B, N, 7)
