@@ -49,6 +49,10 @@ const char* b200cam_error_string(int code);
 int b200cam_supported(int N);
 /* number of kernels this library has enqueued so far in this process (bench.py's gpu_launches) */
 unsigned long long b200cam_launch_count(void);
+/* diagnostic, no device needed: the number of batch chunks the column kernels of an N x N step split B images into when
+ * `slots` CTAs are resident at once (SMs x occupancy) - the wave model of col_chunks() in csrc/b200cam.cu; 0 for an
+ * unsupported N or B < 1 */
+int b200cam_col_chunks(int N, int B, int slots);
 
 /* Build the per-device twiddle table for N and opt the kernels into large dynamic shared
  * memory.  Allocates (once per device and N) - call outside stream capture. */

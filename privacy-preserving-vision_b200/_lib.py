@@ -30,6 +30,7 @@ _SIGNATURES = {
     "b200cam_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "b200cam_supported": (ctypes.c_int, [ctypes.c_int]),
     "b200cam_launch_count": (ctypes.c_ulonglong, []),
+    "b200cam_col_chunks": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "b200cam_device_error": (ctypes.c_int, [ctypes.c_int]),
     "b200cam_init": (ctypes.c_int, [ctypes.c_int]),
     "b200cam_otf_bytes": (ctypes.c_size_t, [ctypes.c_int]),

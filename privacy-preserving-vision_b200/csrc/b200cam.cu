@@ -1465,6 +1465,10 @@ const char* b200cam_error_string(int code) {
 }
 
 unsigned long long b200cam_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int b200cam_col_chunks(int N, int B, int slots) {
+    if (!b200cam_supported(N) || B < 1 || slots < 1) return 0;
+    return col_chunks(N, B, slots);
+}
 
 int b200cam_device_error(int clear) {
     const DeviceState* st = cur_state();

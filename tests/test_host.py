@@ -31,6 +31,21 @@ def test_abi_exports_every_declared_symbol(library):
         assert getattr(library, name) is not None
 
 
+def test_column_kernel_batch_split(library):
+    """col_chunks (b200cam.cu): one wave of CTAs where that fills the SMs, a finer split where the wave model predicts >= 10 %."""
+    f = library.b200cam_col_chunks
+    assert f(256, 64, 592) == 12 and f(256, 64, 444) == 9          # config 2: convolve (4 CTAs/SM), accumulate (3 CTAs/SM)
+    assert f(256, 512, 592) == 12
+    assert f(512, 32, 296) == 3 and f(512, 32, 148) == 3           # N = 512: 97 column groups; accumulate runs one CTA per SM
+    assert f(1024, 8, 148) == 2                                    # 193 column groups cannot be one wave
+    assert f(100, 8, 148) == 0 and f(256, 0, 148) == 0
+    for N in (64, 128, 256, 512, 1024):
+        for B in (1, 2, 3, 7, 16, 37, 64, 150):
+            for slots in (148, 296, 444, 592):
+                n = f(N, B, slots)
+                assert 1 <= n <= min(B, 16)
+
+
 def test_abi_size_queries_without_gpu(library):
     assert library.b200cam_version() == 100
     assert [library.b200cam_supported(n) for n in (64, 100, 256, 1024, 2048)] == [1, 0, 1, 1, 0]
